@@ -1,0 +1,33 @@
+// common.cu — small shared host utilities of libalgorithm.so.
+#include "common.cuh"
+
+namespace aresb {
+
+int smCount() {
+  static int cached[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  int &c = cached[dev & 63];
+  if (c == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    c = n;
+  }
+  return c;
+}
+
+void Scratch::reset(size_t n, cudaStream_t s) {
+  release();
+  stream = s;
+  bytes = n;
+  ptr = aresbPoolAllocAsync(n, s);
+  if (!ptr) throw EngineError("out of device memory for engine scratch (" + std::to_string(n) + " bytes)");
+}
+
+void Scratch::release() {
+  if (ptr) aresbPoolFreeAsync(ptr, stream);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+}  // namespace aresb

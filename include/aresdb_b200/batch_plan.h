@@ -1,0 +1,134 @@
+/*
+ * batch_plan.h — ADDITIVE whole-batch API of the B200 engine (no counterpart symbol in the
+ * reference; SURVEY.md §0.1-0.2 / §8b explain why it must exist).
+ *
+ * The reference executes one cgo call (= 1-2 Thrust launches, a 5 B/row scratch vector and a
+ * stream sync for every filter) per AST node: query/time_series_aggregate.go:493-593.  Here
+ * the Go batch executor (query/aql_batchexecutor.go:102-273: preExec + filter + project +
+ * reduce) hands the WHOLE batch to one call.  The plan is the same post-order walk
+ * processExpression() performs, flattened: every PlanInst is exactly one non-leaf AST node
+ * with the meaning of the legacy Unary/Binary Transform/Filter call it replaces — leaf
+ * operands (VarRef columns, literals) are referenced in place, sub-expression operands come
+ * from an evaluation stack that lives in registers instead of scratch vectors, and the root
+ * of each expression is routed to a filter / dimension / measure sink.
+ *
+ * Aggregation state lives across batches in an AggState (a device hash table keyed by the
+ * packed dimension row), replacing the "carry previous results in the input buffers and
+ * re-sort / re-insert them every batch" protocol (query/aql_processor.go:743-776,
+ * query/time_series_aggregate.go:683-716).  AggStateFinalize emits exactly what the last
+ * Reduce / HashReduce of the reference would have left in the output DimensionVector and
+ * measure vector: groups identified by the murmur3 hash of the packed row (64-bit low word
+ * for ARES_REDUCE_SORT, 32-bit for ARES_REDUCE_HASH), ascending-hash order for SORT.
+ */
+#ifndef ARESDB_B200_BATCH_PLAN_H_
+#define ARESDB_B200_BATCH_PLAN_H_
+
+#include "aql_abi.h"
+
+enum {
+  ARES_MAX_PLAN_COLUMNS = MAX_COLUMNS_OF_A_TABLE,
+  ARES_MAX_PLAN_INSTS = 64,
+  ARES_PLAN_STACK_DEPTH = 4
+};
+
+enum PlanOperandKind {
+  PLAN_OPERAND_NONE = 0,
+  PLAN_OPERAND_COLUMN = 1, /* BatchPlan.Columns[Column]: what makeVectorPartySliceInput passes   */
+  PLAN_OPERAND_CONST = 2,  /* what makeConstantInput passes (ConstInt / ConstFloat + IsValid)   */
+  PLAN_OPERAND_STACK = 3   /* result of an earlier PLAN_SINK_STACK instruction (LIFO)            */
+};
+
+typedef struct {
+  uint8_t Kind;       /* enum PlanOperandKind */
+  uint8_t Column;     /* PLAN_OPERAND_COLUMN: index into BatchPlan.Columns */
+  uint8_t ConstType;  /* PLAN_OPERAND_CONST: ConstInt or ConstFloat */
+  uint8_t ConstValid; /* PLAN_OPERAND_CONST: ConstantVector.IsValid */
+  union {
+    int32_t IntVal;
+    float FloatVal;
+  } Const;
+} PlanOperand;
+
+enum PlanSink {
+  PLAN_SINK_STACK = 0,     /* non-root node: ScratchSpaceOutput of DataType SinkDataType       */
+  PLAN_SINK_FILTER = 1,    /* root of a filter: row survives iff bool(value) (filterAction)      */
+  PLAN_SINK_DIMENSION = 2, /* root of dimension #SinkArg (layout order), DimensionOutput         */
+  PLAN_SINK_MEASURE = 3    /* root of the measure, MeasureOutput of SinkDataType / AggSpec.AggFunc */
+};
+
+typedef struct {
+  uint8_t NumOperands;  /* 1: Functor is a UnaryFunctorType; 2: a BinaryFunctorType */
+  uint8_t Functor;
+  uint8_t Sink;         /* enum PlanSink */
+  uint8_t SinkArg;      /* dimension ordinal for PLAN_SINK_DIMENSION */
+  uint8_t SinkDataType; /* enum DataType of the sink element */
+  uint8_t Reserved[3];
+  PlanOperand A;
+  PlanOperand B;
+} PlanInst;
+
+/* One batch of one table shard: column slices already resident on the device. */
+typedef struct {
+  VectorPartySlice Columns[ARES_MAX_PLAN_COLUMNS];
+  int32_t NumColumns;
+  PlanInst Insts[ARES_MAX_PLAN_INSTS];
+  int32_t NumInsts;
+  /* Index space of the batch = rows of the first column (as in the reference).  BaseCounts
+   * is that column's cumulative count vector for RLE (archive, sorted) batches, or NULL;
+   * StartCount is the row number of index 0 when BaseCounts is NULL
+   * (oopkBatchContext.baseCountD / startRow, query/aql_context.go:151-235). */
+  uint32_t *BaseCounts;
+  uint32_t StartCount;
+  uint32_t NumRows;
+} BatchPlan;
+
+enum AresReduceMode {
+  ARES_REDUCE_SORT = 0, /* semantics of Sort + Reduce (64-bit hash identity, hash-ascending output) */
+  ARES_REDUCE_HASH = 1  /* semantics of HashReduce (32-bit hash identity, unordered output)        */
+};
+
+typedef struct {
+  uint8_t NumDimsPerDimWidth[NUM_DIM_WIDTH]; /* as DimensionVector */
+  uint8_t Reserved[3];
+  int32_t AggFunc;         /* enum AggregateFunction (SUM/MIN/MAX families) */
+  int32_t MeasureDataType; /* enum DataType of one measure element: Int32/Uint32/Float32/Int64/Float64 */
+  int32_t ReduceMode;      /* enum AresReduceMode */
+  uint32_t ExpectedGroups; /* capacity hint, 0 = default; the table grows when needed */
+} AggSpec;
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* res = opaque state handle.  Allocates the group table on `device`. */
+CGoCallResHandle AggStateCreate(AggSpec spec, void *cudaStream, int device);
+
+/* Fused preExec+filter+project+reduce of one batch into `state`.  Asynchronous on
+ * cudaStream: nothing is returned to the host, nothing is synchronised (res = 0). */
+CGoCallResHandle ExecuteBatchPlan(void *state, const BatchPlan *plan, void *cudaStream, int device);
+
+/* Folds already-reduced rows (a DimensionVector block + measure vector, e.g. the carried
+ * result of the legacy protocol, or the all-gathered results of other GPUs) into `state`
+ * with the aggregate's combine rule (broker/result_merge.go:80-105 semantics). */
+CGoCallResHandle AggStateMerge(void *state, DimensionVector inputKeys, uint8_t *inputValues,
+                               int length, void *cudaStream, int device);
+
+/* res = number of occupied group slots (>= number of output groups); synchronises. */
+CGoCallResHandle AggStateGroupCount(void *state, void *cudaStream, int device);
+
+/* Writes the groups into outputKeys (capacity outputKeys.VectorCapacity; DimValues required,
+ * HashValues / IndexVector filled when non-NULL) and outputValues; res = number of groups.
+ * Synchronises cudaStream.  The state stays valid (it can be finalized again or reset). */
+CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8_t *outputValues,
+                                  void *cudaStream, int device);
+
+/* Empties the table, keeping its memory. */
+CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device);
+
+CGoCallResHandle AggStateDestroy(void *state, int device);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ARESDB_B200_BATCH_PLAN_H_ */
