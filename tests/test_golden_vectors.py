@@ -322,3 +322,84 @@ def test_hash_reduce(backend):
                int(d[42 + i]), int(d[48 + i]), int(d[54 + i]))
         got[key] = int(ov.get(np.uint32, 3)[i])
     assert got == {(2, 2, 2, 1, 1, 1): 3, (1, 1, 1, 1, 1, 1): 11, (3, 3, 3, 1, 1, 1): 7}
+
+
+def _free_outputs(be, *ptrs):
+    import ctypes as C
+    for p in ptrs:
+        if not p:
+            continue
+        if be.name == "ref":
+            be.lib.deviceFree(p)
+        elif be.name == "oracle":
+            C.CDLL(None).free(C.c_void_p(p))
+        else:
+            be.lib.DeviceFree(p, be.device)
+
+
+def _read_raw(be, ptr, nbytes):
+    """Reads engine-allocated memory (HyperLogLog allocates its outputs itself, hll.cu:117,150)."""
+    import ctypes as C
+    if not be.is_gpu:
+        return np.frombuffer(C.string_at(ptr, nbytes), dtype=np.uint8).copy()
+    host = np.zeros(max(nbytes, 1), np.uint8)
+    be.lib.AsyncCopyDeviceToHost(host.ctypes.data, ptr, nbytes, be.space.stream, be.device)
+    be.lib.WaitForCudaStream(be.space.stream, be.device)
+    return host[:nbytes]
+
+
+def run_hll(be, prev_dim, cur_values, nd, capacity, prev_size, batch, last=True, prev_values=None,
+            prev_hash=None):
+    import ctypes as C
+    pd = be.put(np.asarray(prev_dim, np.uint8))
+    pv = be.put(np.zeros(capacity, np.uint32) if prev_values is None else np.asarray(prev_values, np.uint32))
+    ph = be.put(np.zeros(capacity, np.uint64) if prev_hash is None else np.asarray(prev_hash, np.uint64))
+    pi = be.put(np.arange(capacity, dtype=np.uint32))
+    cd = be.zeros(len(prev_dim))
+    cv = be.put(np.asarray(cur_values, np.uint32))
+    ch = be.zeros(8 * capacity)
+    ci = be.put(np.arange(prev_size, prev_size + capacity, dtype=np.uint32))
+    hll, size, cnt = C.c_void_p(), C.c_size_t(), C.c_void_p()
+    n = be.lib.HyperLogLog(A.make_dimension_vector(pd.ptr, ph.ptr, pi.ptr, nd, capacity),
+                           A.make_dimension_vector(cd.ptr, ch.ptr, ci.ptr, nd, capacity), pv.ptr, cv.ptr,
+                           prev_size, batch, last, C.byref(hll), C.byref(size), C.byref(cnt),
+                           be.space.stream, be.device)
+    out = dict(n=n, dims=cd.get(np.uint8), hash=ch.get(np.uint64), index=ci.get(np.uint32), values=cv.get(np.uint32))
+    if last and n > 0:
+        out["hll"] = _read_raw(be, hll.value, size.value)
+        out["counts"] = _read_raw(be, cnt.value, 2 * n).view(np.uint16)
+        _free_outputs(be, hll.value, cnt.value)
+    return out
+
+
+def test_hll_sparse_mode(backend):
+    """HyperLogLogTest.CheckSparseMode :1229 — byte-exact sparse register vector."""
+    r = run_hll(backend, [1, 1, 2, 2, 3, 3, 4, 4] + [1] * 8,
+                [0x010001, 0x020002, 0x010002, 0x020002, 0x010003, 0x020003, 0x010004, 0x020004],
+                (0, 0, 0, 0, 1), 8, 0, 8)
+    assert r["n"] == 4
+    assert r["dims"].tolist() == [2, 4, 3, 1, 0, 0, 0, 0, 1, 1, 1, 1, 0, 0, 0, 0]
+    assert r["hll"].tolist() == [2, 0, 3, 0, 4, 0, 3, 0, 3, 0, 3, 0, 1, 0, 2, 0, 2, 0, 3, 0]
+    assert r["counts"].tolist() == [1, 1, 1, 2]
+
+
+def test_hll_dense_mode(backend):
+    """HyperLogLogTest.CheckDenseMode :1305 — a dim with 4996 registers goes dense (16384 B)."""
+    prev = np.zeros(10000, np.uint8)
+    prev[0:4] = [1, 1, 2, 2]
+    prev[5000:] = 1
+    vals = np.zeros(5000, np.uint32)
+    vals[0:4] = [0x010001, 0x020002, 0x010002, 0x020002]
+    vals[4:] = 0x010000 | np.arange(4996, dtype=np.uint32)
+    r = run_hll(backend, prev, vals, (0, 0, 0, 0, 1), 5000, 0, 5000)
+    assert r["n"] == 3
+    exp_dims = np.zeros(10000, np.uint8)
+    exp_dims[0:3] = [2, 0, 1]
+    exp_dims[5000:5003] = 1
+    assert r["dims"].tolist() == exp_dims.tolist()
+    exp = np.zeros(16396, np.uint8)
+    exp[0:4] = [2, 0, 3, 0]
+    exp[4:5000] = 2
+    exp[16388:16396] = [1, 0, 2, 0, 2, 0, 3, 0]
+    assert r["hll"].size == 16396 and r["hll"].tolist() == exp.tolist()
+    assert r["counts"].tolist() == [1, 4996, 2]
