@@ -83,10 +83,10 @@ def build(verbose: bool = False, jobs: int | None = None) -> dict:
     link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-cudart", "shared"]
     newest = max(Path(o).stat().st_mtime for o in mem_objs + alg_objs)
     if not libmem.exists() or libmem.stat().st_mtime < newest:
-        subprocess.run([*link, *mem_objs, "-o", str(libmem)], check=True)
+        subprocess.run([*link, *mem_objs, "-o", str(libmem), "-Xlinker", "-soname", "-Xlinker", "libmem.so"], check=True)
     if not libalg.exists() or libalg.stat().st_mtime < newest:
-        subprocess.run([*link, *alg_objs, "-o", str(libalg), f"-L{LIB}", "-lmem",
-                        "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"], check=True)
+        subprocess.run([*link, *alg_objs, "-o", str(libalg), f"-L{LIB}", "-lmem", "-Xlinker", "-soname", "-Xlinker",
+                        "libalgorithm.so", "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"], check=True)
     return {"libmem": str(libmem), "libalgorithm": str(libalg)}
 
 

@@ -359,8 +359,10 @@ class Library:
     def __init__(self, algorithm_path: str | os.PathLike, mem_path: str | os.PathLike | None = None,
                  has_plan_api: bool = True, name: str = ""):
         self.name = name or Path(algorithm_path).parent.name
-        self.mem = C.CDLL(str(mem_path), mode=C.RTLD_GLOBAL) if mem_path else None
-        self.alg = C.CDLL(str(algorithm_path), mode=C.RTLD_GLOBAL)
+        # RTLD_LOCAL: several implementations of the same symbols may live in one process (tests);
+        # each libalgorithm must bind to ITS OWN libmem through DT_NEEDED, never through the global scope.
+        self.mem = C.CDLL(str(mem_path)) if mem_path else None
+        self.alg = C.CDLL(str(algorithm_path))
         self.has_plan_api = has_plan_api
         self._fns = {}
         for nm, args in _ALGO_SIGS.items():
@@ -410,6 +412,12 @@ class Library:
 
     def get_flags(self) -> int:
         return int(self.mem.GetFlags())
+
+    def kernel_launch_count(self) -> int:
+        fn = self.alg.AresKernelLaunchCount
+        fn.restype = C.c_ulonglong
+        fn.argtypes = []
+        return int(fn())
 
 
 PACKAGE_DIR = Path(__file__).resolve().parent

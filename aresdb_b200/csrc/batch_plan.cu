@@ -1,12 +1,1224 @@
-// batch_plan.cu — additive whole-batch API (include/aresdb_b200/batch_plan.h).  Placeholder.
-#include "common.cuh"
-using namespace aresb;
-extern "C" {
-CGoCallResHandle AggStateCreate(AggSpec, void *, int) { return unsupported("AggStateCreate", "not implemented yet"); }
-CGoCallResHandle ExecuteBatchPlan(void *, const BatchPlan *, void *, int) { return unsupported("ExecuteBatchPlan", "not implemented yet"); }
-CGoCallResHandle AggStateMerge(void *, DimensionVector, uint8_t *, int, void *, int) { return unsupported("AggStateMerge", "not implemented yet"); }
-CGoCallResHandle AggStateGroupCount(void *, void *, int) { return unsupported("AggStateGroupCount", "not implemented yet"); }
-CGoCallResHandle AggStateFinalize(void *, DimensionVector, uint8_t *, void *, int) { return unsupported("AggStateFinalize", "not implemented yet"); }
-CGoCallResHandle AggStateReset(void *, void *, int) { return unsupported("AggStateReset", "not implemented yet"); }
-CGoCallResHandle AggStateDestroy(void *, int) { return unsupported("AggStateDestroy", "not implemented yet"); }
+// batch_plan.cu — the fused whole-batch engine behind include/aresdb_b200/batch_plan.h.
+//
+// ExecuteBatchPlan = ONE persistent kernel per batch (fusedBatchKernel):
+//   * column slices are staged tile by tile into shared memory by the TMA engine
+//     (cp.async.bulk global->shared, completion on an mbarrier, kStages-deep ring), so HBM is
+//     read exactly once, fully coalesced, with no LSU issue slots or registers spent on it;
+//   * every thread owns quads of 4 consecutive rows (128-bit LDS for 4-byte columns, 64-bit for
+//     2-byte, 32-bit for 1-byte, nibbles of the null bitmaps) and interprets the plan's
+//     instruction list in registers: filters clear bits of an alive mask, dimension roots pack
+//     the row key, the measure root yields the value (NULL -> identity, x RLE count);
+//   * surviving rows are aggregated into a CTA-private open-addressing table in SHARED memory
+//     (native shared atomics: measured 0.5-2 Tops/s on B200, profiles/r01_agg_microbench.txt),
+//     which is flushed into the L2-resident global group table when the CTA retires; rows that
+//     do not fit the shared table (high cardinality) go to the global table directly.
+// The global table lives in an AggState across batches.  AggStateFinalize compacts it, hashes
+// each group's packed dimension row with the reference's murmur3, sorts the g groups by hash,
+// merges equal hashes and writes the reference's output layout — the observable result of the
+// reference's Sort+Reduce (ARES_REDUCE_SORT) or HashReduce (ARES_REDUCE_HASH) over all batches.
+#include <vector>
+
+#include "agg.cuh"
+#include "column.cuh"
+#include "dimrow.cuh"
+#include "radix_sort.cuh"
+#include "scan.cuh"
+
+namespace aresb {
+
+// from sort_reduce.cu
+int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *measures, int width, AggOp op, int n,
+                 uint32_t *outIndex, uint8_t *outValues, cudaStream_t s, uint64_t *outHash = nullptr);
+
+constexpr int kFusedThreads = 512;
+constexpr int kStages = 4;
+constexpr int kMaxPlanCols = 16;
+constexpr int kSmemBudget = 220 * 1024;       // of the 227 KB a CTA may opt into
+constexpr uint32_t kSmemProbeLimit = 16;
+constexpr uint32_t kGlobalProbeLimit = 8192;
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr uint64_t kMix = 0x9E3779B97F4A7C15ull;
+
+enum KeyMode : uint8_t { KEY_PACKED = 0, KEY_HASHED = 1 };
+enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3 };
+
+struct DevColumn {
+  InputDesc in;            // how to read it straight from global memory (any mode)
+  uint32_t smemValues;     // byte offsets inside one stage (staged path)
+  uint32_t smemNulls;
+  uint32_t tileValueBytes; // bytes of one full tile
+  uint32_t tileNullBytes;
+  uint8_t width;           // bytes per value, 0 for bit-packed bool
+  uint8_t staged;          // values staged
+  uint8_t hasNulls;        // mode 2 bitmap staged
+  uint8_t pad;
+};
+
+struct DevInst {
+  uint32_t aconst, bconst;
+  uint8_t nops, fn, sink, sinkArg;
+  uint8_t akind, acol, aclass, avalid;
+  uint8_t bkind, bcol, bclass, bvalid;
+  uint8_t tclass;   // class the functor runs in
+  uint8_t rclass;   // class of the functor result
+  uint8_t oclass;   // class of the sink element
+  uint8_t wide;     // 1: 8/16-byte column copied verbatim into a dimension
+  uint8_t rowOff, width, nullOff, pad;
+};
+
+struct DevTable {
+  unsigned long long *keys;
+  unsigned long long *acc;
+  uint64_t *rows;        // [capacity][4] packed rows, KEY_HASHED only
+  uint32_t *counters;    // [0] occupied slots, [1] overflow flag
+  uint32_t mask;
+};
+
+struct DevPlan {
+  DevColumn cols[kMaxPlanCols];
+  DevInst insts[ARES_MAX_PLAN_INSTS];
+  const uint32_t *baseCounts;
+  uint32_t startCount;
+  uint32_t numRows;
+  uint32_t tileRows;
+  uint32_t numFullTiles;   // staged tiles; the tail goes through the direct path
+  uint32_t stageBytes;
+  uint32_t smemSlots;      // shared table slots (power of two)
+  int32_t ncols, ninsts, lastFilter;
+  uint64_t measureIdentity;  // NULL measure -> this (sink class bits)
+  uint64_t accNeutral;       // neutral element of the combine op
+  uint8_t keyMode, rowBytes, valueBytes, hashBits;
+  uint8_t aggOp, measWidth, measClass, skipCount;
+  uint8_t hasMeasure, staged, pad0, pad1;
+};
+
+// ---------------------------------------------------------------------------------------
+// device helpers: TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
 }
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmaLoad1D(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smemAddr(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// global group table
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
+  uint32_t slot = (uint32_t)((key * kMix) >> 29) & G.mask;
+  for (uint32_t probe = 0; probe < kGlobalProbeLimit; probe++) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&G.keys[slot]);
+    if (k == key) return slot;
+    if (k == kEmptyKey) {
+      unsigned long long old = atomicCAS(&G.keys[slot], kEmptyKey, key);
+      if (old == kEmptyKey) {
+        atomicAdd(&G.counters[0], 1u);
+        if (roww != nullptr && G.rows != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) G.rows[(size_t)slot * 4 + i] = roww[i];
+        }
+        return slot;
+      }
+      if (old == key) return slot;
+    }
+    slot = (slot + 1) & G.mask;
+  }
+  atomicExch(&G.counters[1], 1u);
+  return 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsigned long long key, const uint64_t *roww,
+                                             uint64_t val) {
+  uint32_t slot = globalFindOrClaim(G, key, roww);
+  if (slot != 0xFFFFFFFFu) aggAtomic(op, &G.acc[slot], val);
+}
+
+// ---------------------------------------------------------------------------------------
+// CTA-private shared-memory table
+// ---------------------------------------------------------------------------------------
+struct SmemTable {
+  unsigned long long *keys;
+  unsigned long long *acc;
+  uint32_t *claims;   // number of occupied slots
+  uint32_t mask;
+};
+
+__device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, uint64_t v) {
+  switch (op) {
+    case OP_SUM_I32: atomicAdd(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
+    case OP_SUM_F32: atomicAdd(reinterpret_cast<float *>(addr), __uint_as_float((uint32_t)v)); break;
+    case OP_SUM_I64: atomicAdd(addr, (unsigned long long)v); break;
+    case OP_SUM_F64: atomicAdd(reinterpret_cast<double *>(addr), __longlong_as_double((long long)v)); break;
+    case OP_MIN_U32: atomicMin(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
+    case OP_MIN_I32: atomicMin(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
+    case OP_MAX_U32: atomicMax(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
+    case OP_MAX_I32: atomicMax(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
+    default: {  // float min / max
+      unsigned int *a = reinterpret_cast<unsigned int *>(addr);
+      unsigned int old = *a, assumed;
+      do {
+        assumed = old;
+        unsigned int want = (unsigned int)aggCombine(op, assumed, v);
+        if (want == assumed) break;
+        old = atomicCAS(a, assumed, want);
+      } while (old != assumed);
+      break;
+    }
+  }
+}
+
+// Returns false when the row has to go to the global table (shared table full around its home).
+__device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
+                                           const uint64_t *roww, uint64_t val, bool allowClaim) {
+  uint32_t slot = (uint32_t)((key * kMix) >> 40) & T.mask;
+  for (uint32_t probe = 0; probe < kSmemProbeLimit; probe++) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+    if (k == kEmptyKey) {
+      if (!allowClaim) return false;
+      unsigned long long old = atomicCAS(&T.keys[slot], kEmptyKey, key);
+      if (old == kEmptyKey) {
+        atomicAdd(T.claims, 1u);
+        // wide keys: the packed row is recorded in the global table once, by whoever claims first
+        if (roww != nullptr) globalFindOrClaim(G, key, roww);
+        k = key;
+      } else {
+        k = old;
+      }
+    }
+    if (k == key) {
+      smemAtomic(op, &T.acc[slot], val);
+      return true;
+    }
+    slot = (slot + 1) & T.mask;
+  }
+  return false;
+}
+
+// ---------------------------------------------------------------------------------------
+// 4-row vector evaluation
+// ---------------------------------------------------------------------------------------
+constexpr int R = 4;  // rows per quad
+
+__device__ __forceinline__ void cvtVec(uint32_t (&v)[R], ValClass from, ValClass to) {
+  if (from == to) return;
+  const bool fi = from == VC_I32 || from == VC_U32 || from == VC_BOOL;
+  const bool ti = to == VC_I32 || to == VC_U32;
+  if (fi && ti) return;  // bit-identical (bool is stored as 0/1)
+#pragma unroll
+  for (int r = 0; r < R; r++) v[r] = (uint32_t)cvt(v[r], from, to);
+}
+
+// Binary functor on R rows; NULL results carry value 0 like the reference's (0, false).
+__device__ __forceinline__ void binVec(int fn, ValClass tc, const uint32_t (&a)[R], uint32_t av, const uint32_t (&b)[R],
+                                       uint32_t bv, uint32_t (&out)[R], uint32_t &ov) {
+  const uint32_t both = av & bv;
+  ov = 0;
+#define ARES_ROWS(expr_f, expr_i, expr_u)                                                                 \
+  {                                                                                                       \
+    ov = both;                                                                                            \
+    if (tc == VC_F32) {                                                                                   \
+      _Pragma("unroll") for (int r = 0; r < R; r++) {                                                     \
+        float x = __uint_as_float(a[r]), y = __uint_as_float(b[r]); (void)x; (void)y;                     \
+        out[r] = (both >> r) & 1 ? (uint32_t)(expr_f) : 0u;                                               \
+      }                                                                                                   \
+    } else if (tc == VC_I32) {                                                                            \
+      _Pragma("unroll") for (int r = 0; r < R; r++) {                                                     \
+        int32_t x = (int32_t)a[r], y = (int32_t)b[r]; (void)x; (void)y;                                   \
+        out[r] = (both >> r) & 1 ? (uint32_t)(expr_i) : 0u;                                               \
+      }                                                                                                   \
+    } else {                                                                                              \
+      _Pragma("unroll") for (int r = 0; r < R; r++) {                                                     \
+        uint32_t x = a[r], y = b[r]; (void)x; (void)y;                                                    \
+        out[r] = (both >> r) & 1 ? (uint32_t)(expr_u) : 0u;                                               \
+      }                                                                                                   \
+    }                                                                                                     \
+  }
+  switch (fn) {
+    case Equal: ARES_ROWS(x == y, x == y, x == y) return;
+    case NotEqual: ARES_ROWS(x != y, x != y, x != y) return;
+    case LessThan: ARES_ROWS(x < y, x < y, x < y) return;
+    case LessThanOrEqual: ARES_ROWS(x <= y, x <= y, x <= y) return;
+    case GreaterThan: ARES_ROWS(x > y, x > y, x > y) return;
+    case GreaterThanOrEqual: ARES_ROWS(x >= y, x >= y, x >= y) return;
+    case Plus: ARES_ROWS(__float_as_uint(__fadd_rn(x, y)), (uint32_t)x + (uint32_t)y, x + y) return;
+    case Minus: ARES_ROWS(__float_as_uint(__fsub_rn(x, y)), (uint32_t)x - (uint32_t)y, x - y) return;
+    case Multiply: ARES_ROWS(__float_as_uint(__fmul_rn(x, y)), (uint32_t)x * (uint32_t)y, x * y) return;
+    default: break;
+  }
+#undef ARES_ROWS
+  // everything else (And/Or/Divide/Mod/bitwise/Floor): scalar functor per row
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    Cell ca, cb;
+    ca.v = a[r]; ca.valid = (av >> r) & 1;
+    cb.v = b[r]; cb.valid = (bv >> r) & 1;
+    ValClass rc;
+    Cell cr = evalBinary(fn, ca, cb, tc, &rc);
+    out[r] = (uint32_t)cr.v;
+    ov = (ov & ~(1u << r)) | ((cr.valid ? 1u : 0u) << r);
+  }
+}
+
+__device__ __forceinline__ void unVec(int fn, ValClass ic, const uint32_t (&a)[R], uint32_t av, uint32_t (&out)[R],
+                                      uint32_t &ov) {
+  if (fn == Noop) {
+#pragma unroll
+    for (int r = 0; r < R; r++) out[r] = a[r];
+    ov = av;
+    return;
+  }
+  ov = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    Cell ca;
+    ca.v = a[r]; ca.valid = (av >> r) & 1;
+    ValClass rc;
+    Cell cr = evalUnary(fn, ca, ic, &rc);
+    out[r] = (uint32_t)cr.v;
+    ov = (ov & ~(1u << r)) | ((cr.valid ? 1u : 0u) << r);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// operand fetch
+// ---------------------------------------------------------------------------------------
+// Staged: `stage` is the shared-memory copy of the tile; q is the quad index inside the tile.
+__device__ __forceinline__ void fetchStaged(const DevColumn &c, const uint8_t *stage, uint32_t q, uint32_t (&v)[R],
+                                            uint32_t &valid) {
+  const uint8_t *vals = stage + c.smemValues;
+  switch (c.width) {
+    case 4: {
+      uint4 x = *reinterpret_cast<const uint4 *>(vals + 16 * q);
+      v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+      break;
+    }
+    case 2: {
+      uint2 x = *reinterpret_cast<const uint2 *>(vals + 8 * q);
+      if (c.in.dtype == Int16) {
+        v[0] = (uint32_t)(int32_t)(int16_t)(x.x & 0xffff); v[1] = (uint32_t)(int32_t)(int16_t)(x.x >> 16);
+        v[2] = (uint32_t)(int32_t)(int16_t)(x.y & 0xffff); v[3] = (uint32_t)(int32_t)(int16_t)(x.y >> 16);
+      } else {
+        v[0] = x.x & 0xffff; v[1] = x.x >> 16; v[2] = x.y & 0xffff; v[3] = x.y >> 16;
+      }
+      break;
+    }
+    case 1: {
+      uint32_t x = *reinterpret_cast<const uint32_t *>(vals + 4 * q);
+      if (c.in.dtype == Int8) {
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = (uint32_t)(int32_t)(int8_t)((x >> (8 * r)) & 0xff);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = (x >> (8 * r)) & 0xff;
+      }
+      break;
+    }
+    default: {  // bit-packed bool
+      uint32_t bit = 4 * q + c.in.startBit;
+      uint32_t w = vals[bit >> 3] | ((uint32_t)vals[(bit >> 3) + 1] << 8);
+      w >>= (bit & 7);
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = (w >> r) & 1;
+      break;
+    }
+  }
+  if (c.hasNulls) {
+    const uint8_t *nb = stage + c.smemNulls;
+    uint32_t bit = 4 * q + c.in.startBit;
+    uint32_t w = nb[bit >> 3] | ((uint32_t)nb[(bit >> 3) + 1] << 8);
+    valid = (w >> (bit & 7)) & 0xF;
+  } else {
+    valid = 0xF;
+  }
+}
+
+// Direct: straight from global memory, any column mode, row by row (tail tiles, unaligned or
+// RLE columns).
+__device__ __forceinline__ void fetchDirect(const DevPlan &P, const DevColumn &c, uint32_t row0, uint32_t nrows,
+                                            uint32_t (&v)[R], uint32_t &valid) {
+  valid = 0;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    v[r] = 0;
+    if ((uint32_t)r < nrows) {
+      Cell x = loadInput(c.in, row0 + r, nullptr, P.baseCounts, P.startCount, nullptr);
+      v[r] = (uint32_t)x.v;
+      valid |= (x.valid ? 1u : 0u) << r;
+    }
+  }
+}
+
+struct QuadState {
+  uint32_t st[ARES_PLAN_STACK_DEPTH][R];
+  uint32_t stv[ARES_PLAN_STACK_DEPTH];
+};
+
+template <bool STAGED>
+__device__ __forceinline__ void getOperand(const DevPlan &P, const DevInst &I, bool second, const uint8_t *stage,
+                                           uint32_t q, uint32_t row0, uint32_t nrows, QuadState &S, int &sp,
+                                           uint32_t (&v)[R], uint32_t &valid) {
+  const uint8_t kind = second ? I.bkind : I.akind;
+  if (kind == OPK_COLUMN) {
+    const DevColumn &c = P.cols[second ? I.bcol : I.acol];
+    if (c.in.mode == 0) {
+#pragma unroll
+      for (int r = 0; r < R; r++) v[r] = (uint32_t)c.in.constLo;
+      valid = c.in.constValid ? 0xF : 0;
+    } else if (STAGED) {
+      fetchStaged(c, stage, q, v, valid);
+    } else {
+      fetchDirect(P, c, row0, nrows, v, valid);
+    }
+  } else if (kind == OPK_CONST) {
+    const uint32_t k = second ? I.bconst : I.aconst;
+#pragma unroll
+    for (int r = 0; r < R; r++) v[r] = k;
+    valid = (second ? I.bvalid : I.avalid) ? 0xF : 0;
+  } else {  // stack pop (static unrolled select keeps the stack in registers)
+    sp--;
+#pragma unroll
+    for (int d = 0; d < ARES_PLAN_STACK_DEPTH; d++) {
+      if (d == sp) {
+#pragma unroll
+        for (int r = 0; r < R; r++) v[r] = S.st[d][r];
+        valid = S.stv[d];
+      }
+    }
+  }
+}
+
+// Processes one quad (rows row0 .. row0+nrows-1 of the batch).
+template <int KW>
+__device__ __forceinline__ void keyInsert(uint64_t (&w)[KW], int byteOff, uint64_t v) {
+  if (KW == 1) {
+    w[0] |= v << ((byteOff & 7) * 8);
+  } else {
+    const int word = byteOff >> 3, sh = (byteOff & 7) * 8;
+#pragma unroll
+    for (int k = 0; k < KW; k++)
+      if (k == word) w[k] |= v << sh;
+  }
+}
+
+template <bool STAGED, bool WIDEKEY>
+__device__ __forceinline__ void processQuad(const DevPlan &P, const DevTable &G, const SmemTable &T, bool useSmem,
+                                            bool allowClaim, const uint8_t *stage, uint32_t q, uint32_t row0,
+                                            uint32_t nrows) {
+  QuadState S;
+  int sp = 0;
+  uint32_t alive = (1u << nrows) - 1u;
+  constexpr int KW = WIDEKEY ? 4 : 1;
+  uint64_t kw[R][KW];
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+#pragma unroll
+    for (int k = 0; k < KW; k++) kw[r][k] = 0;
+  }
+  uint64_t meas[R];
+#pragma unroll
+  for (int r = 0; r < R; r++) meas[r] = P.measureIdentity;
+
+  for (int pc = 0; pc < P.ninsts; pc++) {
+    const DevInst &I = P.insts[pc];
+    if (I.wide) {  // 8/16-byte column copied verbatim into a dimension (Int64 / UUID dims)
+      const DevColumn &c = P.cols[I.acol];
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        if ((uint32_t)r < nrows) {
+          uint64_t hi = 0;
+          Cell x = loadInput(c.in, row0 + r, nullptr, P.baseCounts, P.startCount, &hi);
+          keyInsert<KW>(kw[r], I.rowOff, x.v);
+          if (I.width == 16) keyInsert<KW>(kw[r], I.rowOff + 8, hi);
+          keyInsert<KW>(kw[r], I.nullOff, x.valid ? 1 : 0);
+        }
+      }
+      continue;
+    }
+    uint32_t a[R], b[R], res[R];
+    uint32_t av = 0, bv = 0, rv = 0;
+    if (I.nops == 2) {
+      // both on the stack: rhs was pushed last
+      if (I.bkind == OPK_STACK) getOperand<STAGED>(P, I, true, stage, q, row0, nrows, S, sp, b, bv);
+      getOperand<STAGED>(P, I, false, stage, q, row0, nrows, S, sp, a, av);
+      if (I.bkind != OPK_STACK) getOperand<STAGED>(P, I, true, stage, q, row0, nrows, S, sp, b, bv);
+      cvtVec(a, (ValClass)I.aclass, (ValClass)I.tclass);
+      cvtVec(b, (ValClass)I.bclass, (ValClass)I.tclass);
+      binVec(I.fn, (ValClass)I.tclass, a, av, b, bv, res, rv);
+    } else {
+      getOperand<STAGED>(P, I, false, stage, q, row0, nrows, S, sp, a, av);
+      unVec(I.fn, (ValClass)I.aclass, a, av, res, rv);
+    }
+    switch (I.sink) {
+      case PLAN_SINK_STACK: {
+        cvtVec(res, (ValClass)I.rclass, (ValClass)I.oclass);
+#pragma unroll
+        for (int d = 0; d < ARES_PLAN_STACK_DEPTH; d++) {
+          if (d == sp) {
+#pragma unroll
+            for (int r = 0; r < R; r++) S.st[d][r] = res[r];
+            S.stv[d] = rv;
+          }
+        }
+        sp++;
+        break;
+      }
+      case PLAN_SINK_FILTER: {
+        uint32_t keep = 0;
+        if (I.rclass == VC_F32) {
+#pragma unroll
+          for (int r = 0; r < R; r++) keep |= (__uint_as_float(res[r]) != 0.0f ? 1u : 0u) << r;
+        } else {
+#pragma unroll
+          for (int r = 0; r < R; r++) keep |= (res[r] != 0 ? 1u : 0u) << r;
+        }
+        alive &= keep;
+        if (pc == P.lastFilter && !__any_sync(__activemask(), alive != 0)) return;
+        break;
+      }
+      case PLAN_SINK_DIMENSION: {
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          uint64_t o = cvt(res[r], (ValClass)I.rclass, (ValClass)I.oclass);
+          keyInsert<KW>(kw[r], I.rowOff, o);
+          keyInsert<KW>(kw[r], I.nullOff, (rv >> r) & 1);
+        }
+        break;
+      }
+      default: {  // PLAN_SINK_MEASURE
+#pragma unroll
+        for (int r = 0; r < R; r++) {
+          if ((rv >> r) & 1) {
+            uint64_t o = cvt(res[r], (ValClass)I.rclass, (ValClass)I.oclass);
+            if (!P.skipCount && P.baseCounts != nullptr && (uint32_t)r < nrows) {
+              uint32_t cnt = P.baseCounts[row0 + r + 1] - P.baseCounts[row0 + r];
+              switch ((ValClass)I.oclass) {
+                case VC_I32: case VC_U32: o = (uint32_t)o * cnt; break;
+                case VC_F32: o = fromF32(asF32(o) * (float)cnt); break;
+                case VC_I64: o = (uint64_t)((int64_t)o * (int64_t)(uint64_t)cnt); break;
+                default: o = fromF64(asF64(o) * (double)cnt); break;
+              }
+            }
+            meas[r] = o;
+          }
+        }
+        break;
+      }
+    }
+  }
+
+  if (alive == 0) return;
+  const AggOp op = (AggOp)P.aggOp;
+#pragma unroll
+  for (int r = 0; r < R; r++) {
+    if (!((alive >> r) & 1)) continue;
+    unsigned long long key;
+    const uint64_t *roww = nullptr;
+    if constexpr (WIDEKEY) {
+      key = P.hashBits == 64 ? murmur3_128_lo(kw[r], P.rowBytes, 0) : (unsigned long long)murmur3_32(kw[r], P.rowBytes, 0);
+      roww = kw[r];
+    } else {
+      key = kw[r][0];
+    }
+    if (!useSmem || !smemUpdate(T, G, op, key, roww, meas[r], allowClaim)) globalUpdate(G, op, key, roww, meas[r]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// the fused kernel
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void issueTile(const DevPlan &P, uint32_t tile, uint8_t *stage, uint64_t *bar) {
+  // one elected thread: arm the barrier with the byte count, then one bulk copy per column part
+  uint32_t total = 0;
+  for (int c = 0; c < P.ncols; c++) {
+    const DevColumn &col = P.cols[c];
+    if (col.staged) total += col.tileValueBytes;
+    if (col.hasNulls) total += col.tileNullBytes;
+  }
+  mbarExpectTx(bar, total);
+  const size_t row0 = (size_t)tile * P.tileRows;
+  for (int c = 0; c < P.ncols; c++) {
+    const DevColumn &col = P.cols[c];
+    if (col.staged) {
+      const uint8_t *src = col.in.base + col.in.valuesOff + (col.width ? row0 * col.width : row0 / 8);
+      tmaLoad1D(stage + col.smemValues, src, col.tileValueBytes, bar);
+    }
+    if (col.hasNulls) {
+      const uint8_t *src = col.in.base + col.in.nullsOff + row0 / 8;
+      tmaLoad1D(stage + col.smemNulls, src, col.tileNullBytes, bar);
+    }
+  }
+}
+
+template <bool WIDEKEY>
+__global__ void __launch_bounds__(kFusedThreads, 1)
+fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                       // kStages barriers
+  uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);
+  unsigned long long *tKeys = reinterpret_cast<unsigned long long *>(smem + 128);
+  unsigned long long *tAcc = tKeys + P.smemSlots;
+  uint8_t *stages = reinterpret_cast<uint8_t *>(tAcc + P.smemSlots);
+
+  SmemTable T;
+  T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = P.smemSlots - 1;
+  const bool useSmem = P.smemSlots > 0;
+  for (uint32_t i = threadIdx.x; i < P.smemSlots; i += blockDim.x) {
+    tKeys[i] = kEmptyKey;
+    tAcc[i] = P.accNeutral;
+  }
+  if (threadIdx.x == 0) {
+    *claims = 0;
+    for (int s = 0; s < kStages; s++) mbarInit(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  const uint32_t quadsPerTile = P.tileRows / R;
+  // ---- staged full tiles: tile t handled by CTA (t mod gridDim), ring of kStages buffers ----
+  if (P.staged && P.numFullTiles > 0) {
+    const uint32_t first = blockIdx.x, step = gridDim.x;
+    if (threadIdx.x == 0) {
+      for (int s = 0; s < kStages; s++) {
+        uint32_t t = first + s * step;
+        if (t < P.numFullTiles) issueTile(P, t, stages + (size_t)s * P.stageBytes, &bars[s]);
+      }
+    }
+    uint32_t it = 0;
+    for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
+      const uint32_t s = it % kStages, parity = (it / kStages) & 1;
+      mbarWait(&bars[s], parity);
+      const uint8_t *stage = stages + (size_t)s * P.stageBytes;
+      // shared-table admission is decided per tile (uniform in the CTA)
+      const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (P.smemSlots / 4) * 3;
+      for (uint32_t q = threadIdx.x; q < quadsPerTile; q += blockDim.x)
+        processQuad<true, WIDEKEY>(P, G, T, useSmem, allowClaim, stage, q, t * P.tileRows + q * R, R);
+      __syncthreads();  // everyone is done reading stage s
+      if (threadIdx.x == 0) {
+        uint32_t nt = t + kStages * step;
+        if (nt < P.numFullTiles) issueTile(P, nt, stages + (size_t)s * P.stageBytes, &bars[s]);
+      }
+    }
+  }
+  // ---- rows not covered by staged tiles (tail, or the whole batch on the direct path) --------
+  {
+    const uint32_t begin = P.staged ? P.numFullTiles * P.tileRows : 0;
+    const uint32_t quads = (P.numRows - begin + R - 1) / R;
+    const bool allowClaim = true;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
+      uint32_t row0 = begin + q * R;
+      uint32_t nrows = P.numRows - row0 < R ? P.numRows - row0 : R;
+      processQuad<false, WIDEKEY>(P, G, T, useSmem, allowClaim, nullptr, q, row0, nrows);
+    }
+  }
+  // ---- flush the shared table into the global one ---------------------------------------------
+  __syncthreads();
+  const AggOp op = (AggOp)P.aggOp;
+  for (uint32_t i = threadIdx.x; i < P.smemSlots; i += blockDim.x) {
+    unsigned long long k = tKeys[i];
+    if (k != kEmptyKey) globalUpdate(G, op, k, nullptr, tAcc[i]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// merge of already-reduced rows, finalize
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+mergeRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint8_t *__restrict__ measures, int width,
+                AggOp op, int n, uint8_t keyMode, uint8_t hashBits, DevTable G) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride) {
+    uint64_t w[4];
+    packRow(block, L, i, w);
+    unsigned long long key = keyMode == KEY_PACKED ? w[0]
+                           : (hashBits == 64 ? murmur3_128_lo(w, L.rowBytes, 0) : (unsigned long long)murmur3_32(w, L.rowBytes, 0));
+    globalUpdate(G, op, key, keyMode == KEY_HASHED ? w : nullptr, loadMeasure(measures, i, width));
+  }
+}
+
+constexpr int kCmpThreads = 256;
+constexpr int kCmpItems = 8;
+constexpr int kCmpTile = kCmpThreads * kCmpItems;
+
+// Compacts occupied slots: slotOf[g] = slot index, hash[g] = reference hash of the group's row,
+// vals[g] = accumulator (tight `width`-byte elements).
+__global__ void __launch_bounds__(kCmpThreads)
+compactGroupsKernel(DevTable G, size_t cap, uint8_t keyMode, uint8_t hashBits, int rowBytes, int width, ScanTileState st,
+                    uint32_t *__restrict__ slotOf, uint64_t *__restrict__ hash, uint8_t *__restrict__ vals,
+                    uint32_t *__restrict__ outCount) {
+  __shared__ uint32_t sTile, sPrefix;
+  __shared__ uint32_t sWarp[kCmpThreads / 32 + 1];
+  if (threadIdx.x == 0) sTile = atomicAdd(st.ticket, 1u);
+  __syncthreads();
+  const uint32_t tile = sTile;
+  const size_t base = (size_t)tile * kCmpTile + (size_t)threadIdx.x * kCmpItems;
+  uint32_t mask = 0;
+#pragma unroll
+  for (int k = 0; k < kCmpItems; k++) {
+    size_t i = base + k;
+    if (i < cap && G.keys[i] != kEmptyKey) mask |= 1u << k;
+  }
+  uint32_t blockTotal;
+  const uint32_t excl = blockExclusiveScan<kCmpThreads>(__popc(mask), sWarp, &blockTotal);
+  if (threadIdx.x < 32) {
+    uint32_t p = decoupledLookback(st, tile, blockTotal);
+    if (threadIdx.x == 0) {
+      sPrefix = p;
+      if (((size_t)tile + 1) * kCmpTile >= cap) *outCount = p + blockTotal;
+    }
+  }
+  __syncthreads();
+  uint32_t pos = sPrefix + excl;
+#pragma unroll
+  for (int k = 0; k < kCmpItems; k++) {
+    if (!(mask & (1u << k))) continue;
+    size_t i = base + k;
+    unsigned long long key = G.keys[i];
+    uint64_t h;
+    if (keyMode == KEY_PACKED) {
+      uint64_t w[4] = {key, 0, 0, 0};
+      h = hashBits == 64 ? murmur3_128_lo(w, rowBytes, 0) : (uint64_t)murmur3_32(w, rowBytes, 0);
+    } else {
+      h = key;
+    }
+    slotOf[pos] = (uint32_t)i;
+    hash[pos] = h;
+    storeMeasure(vals, pos, width, G.acc[i]);
+    pos++;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+emitGroupsKernel(DevTable G, uint8_t keyMode, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ repIndex,
+                 uint32_t g, uint8_t *__restrict__ outBlock, DimLayout L, uint32_t *__restrict__ outIndex) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < g; s += stride) {
+    const uint32_t slot = slotOf[repIndex[s]];
+    uint64_t w[4];
+    if (keyMode == KEY_PACKED) {
+      w[0] = G.keys[slot]; w[1] = w[2] = w[3] = 0;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[i] = G.rows[(size_t)slot * 4 + i];
+    }
+    unpackRow(outBlock, L, s, w);
+    if (outIndex) outIndex[s] = s;
+  }
+}
+
+__global__ void iotaKernel(uint32_t *p, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = (uint32_t)i;
+}
+
+__global__ void __launch_bounds__(256)
+fillTableKernel(unsigned long long *keys, unsigned long long *acc, size_t cap, unsigned long long neutral) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += stride) {
+    keys[i] = kEmptyKey;
+    acc[i] = neutral;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
+struct AggState {
+  AggSpec spec;
+  int device;
+  DimLayout rowLayout;     // capacity-independent parts (rowOff / width / numDims)
+  KeyMode keyMode;
+  int hashBits;
+  AggOp op;
+  int measWidth;
+  ValClass measClass;
+  uint64_t accNeutral;
+  size_t capacity;
+  DevTable table;
+  void *mem;               // single allocation behind the table
+};
+
+static uint64_t neutralOf(AggOp op) {
+  switch (op) {
+    case OP_SUM_F32: return 0x80000000ull;                // -0.0f: (-0) + x == x for every x
+    case OP_SUM_F64: return 0x8000000000000000ull;        // -0.0
+    case OP_MIN_U32: return 0xFFFFFFFFull;
+    case OP_MIN_I32: return 0x7FFFFFFFull;
+    case OP_MAX_I32: return 0x80000000ull;
+    case OP_MIN_F32: return 0x7F800000ull;                // +inf
+    case OP_MAX_F32: return 0xFF800000ull;                // -inf
+    default: return 0;                                     // integer sums, unsigned max
+  }
+}
+
+static ValClass measureClassOf(int dt) {
+  switch (dt) {
+    case Int32: return VC_I32;
+    case Uint32: return VC_U32;
+    case Float32: return VC_F32;
+    case Int64: return VC_I64;
+    case Float64: return VC_F64;
+    default: throw EngineError("Unsupported data type for MeasureOutput");
+  }
+}
+
+static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
+  const bool rows = st->keyMode == KEY_HASHED;
+  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256;
+  void *mem = nullptr;
+  CGoCallResHandle h = deviceMalloc(&mem, bytes);
+  if (h.pStrErr) { std::string m(h.pStrErr); free((void *)h.pStrErr); throw EngineError(m); }
+  st->mem = mem;
+  st->capacity = cap;
+  uint8_t *p = static_cast<uint8_t *>(mem);
+  st->table.counters = reinterpret_cast<uint32_t *>(p);
+  st->table.keys = reinterpret_cast<unsigned long long *>(p + 256);
+  st->table.acc = st->table.keys + cap;
+  st->table.rows = rows ? reinterpret_cast<uint64_t *>(st->table.acc + cap) : nullptr;
+  st->table.mask = (uint32_t)(cap - 1);
+  ARES_CUDA(cudaMemsetAsync(p, 0, 256, s));
+  fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, cap, st->accNeutral);
+  checkLastError("fillTable");
+}
+
+static AggState *createState(const AggSpec &spec, cudaStream_t s, int device) {
+  AggState *st = new AggState();
+  try {
+    st->spec = spec;
+    st->device = device;
+    st->rowLayout = makeDimLayout(spec.NumDimsPerDimWidth, 1);
+    if (spec.ReduceMode != ARES_REDUCE_SORT && spec.ReduceMode != ARES_REDUCE_HASH)
+      throw EngineError("unknown ReduceMode");
+    st->hashBits = spec.ReduceMode == ARES_REDUCE_SORT ? 64 : 32;
+    st->keyMode = st->rowLayout.rowBytes <= 8 ? KEY_PACKED : KEY_HASHED;
+    st->measClass = measureClassOf(spec.MeasureDataType);
+    int bytes = (st->measClass == VC_I64 || st->measClass == VC_F64) ? 8 : 4;
+    if (spec.AggFunc == AGGR_AVG_FLOAT || spec.AggFunc == AGGR_HLL)
+      throw EngineError("AVG / HLL aggregates are not available on the fused path; use the per-node entry points");
+    st->op = aggOpOf(spec.AggFunc, bytes, &st->measWidth);
+    st->accNeutral = neutralOf(st->op);
+    size_t want = spec.ExpectedGroups ? (size_t)spec.ExpectedGroups * 2 : ((size_t)1 << 21);
+    size_t cap = 1 << 12;
+    while (cap < want) cap <<= 1;
+    allocTable(st, cap, s);
+  } catch (...) {
+    delete st;
+    throw;
+  }
+  return st;
+}
+
+static AggState *asState(void *p) {
+  if (!p) throw EngineError("null AggState handle");
+  return static_cast<AggState *>(p);
+}
+
+static uint8_t operandClassOf(const PlanOperand &o, const BatchPlan &bp, const std::vector<uint8_t> &stackClasses) {
+  switch (o.Kind) {
+    case PLAN_OPERAND_COLUMN: {
+      if (o.Column >= bp.NumColumns) throw EngineError("plan operand references a column outside BatchPlan.Columns");
+      switch (bp.Columns[o.Column].DataType) {
+        case Bool: return VC_BOOL;
+        case Int8: case Int16: case Int32: return VC_I32;
+        case Uint8: case Uint16: case Uint32: return VC_U32;
+        case Float32: return VC_F32;
+        case Int64: return VC_I64;
+        case UUID: return VC_UUID;
+        default: throw EngineError("Unsupported data type for VectorPartyInput");
+      }
+    }
+    case PLAN_OPERAND_CONST:
+      if (o.ConstType == ConstInt) return VC_I32;
+      if (o.ConstType == ConstFloat) return VC_F32;
+      throw EngineError("Unsupported constant type in plan");
+    case PLAN_OPERAND_STACK:
+      if (stackClasses.empty()) throw EngineError("plan pops an empty evaluation stack");
+      return stackClasses.back();
+    default: throw EngineError("plan instruction has a missing operand");
+  }
+}
+
+static ValClass sinkClassOf(int dt, bool dim) {
+  switch (dt) {
+    case Bool: if (dim) return VC_BOOL; break;
+    case Int8: if (dim) return VC_I8; break;
+    case Uint8: if (dim) return VC_U8; break;
+    case Int16: if (dim) return VC_I16; break;
+    case Uint16: if (dim) return VC_U16; break;
+    case Int32: return VC_I32;
+    case Uint32: return VC_U32;
+    case Float32: return VC_F32;
+    case Int64: return VC_I64;
+    case Float64: if (!dim) return VC_F64; break;
+    case UUID: if (dim) return VC_UUID; break;
+    default: break;
+  }
+  throw EngineError("Unsupported sink data type in plan");
+}
+
+static int classWidth(ValClass c) {
+  switch (c) {
+    case VC_BOOL: case VC_I8: case VC_U8: return 1;
+    case VC_I16: case VC_U16: return 2;
+    case VC_I32: case VC_U32: case VC_F32: return 4;
+    case VC_I64: case VC_F64: return 8;
+    default: return 16;
+  }
+}
+
+// Translates the ABI plan into the device form, resolving value classes by the reference's rules.
+static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
+  memset(&P, 0, sizeof(P));
+  if (bp.NumColumns < 0 || bp.NumColumns > kMaxPlanCols)
+    throw EngineError("the fused path stages at most 16 distinct columns per batch");
+  if (bp.NumInsts <= 0 || bp.NumInsts > ARES_MAX_PLAN_INSTS) throw EngineError("invalid plan instruction count");
+  P.ncols = bp.NumColumns;
+  P.ninsts = bp.NumInsts;
+  P.baseCounts = bp.BaseCounts;
+  P.startCount = bp.StartCount;
+  P.numRows = bp.NumRows;
+  for (int c = 0; c < bp.NumColumns; c++) {
+    P.cols[c].in = makeColumnDesc(bp.Columns[c], /*allowWide=*/true);
+    int dt = bp.Columns[c].DataType;
+    P.cols[c].width = dt == Bool ? 0 : (dt == Int8 || dt == Uint8) ? 1 : (dt == Int16 || dt == Uint16) ? 2
+                    : (dt == Int64 || dt == Uint64) ? 8 : dt == UUID ? 16 : 4;
+  }
+  const DimLayout &RL = st->rowLayout;
+  std::vector<uint8_t> stack;
+  std::vector<bool> dimSeen(RL.numDims, false);
+  bool measureSeen = false;
+  P.lastFilter = -1;
+  for (int i = 0; i < bp.NumInsts; i++) {
+    const PlanInst &pi = bp.Insts[i];
+    DevInst &I = P.insts[i];
+    if (pi.NumOperands != 1 && pi.NumOperands != 2) throw EngineError("plan instruction must have 1 or 2 operands");
+    I.nops = pi.NumOperands; I.fn = pi.Functor; I.sink = pi.Sink; I.sinkArg = pi.SinkArg;
+    // operand classes (rhs popped first when both come from the stack)
+    uint8_t bcls = VC_NONE, acls;
+    if (pi.NumOperands == 2) {
+      if (pi.B.Kind == PLAN_OPERAND_STACK) { bcls = operandClassOf(pi.B, bp, stack); stack.pop_back(); }
+    }
+    acls = operandClassOf(pi.A, bp, stack);
+    if (pi.A.Kind == PLAN_OPERAND_STACK) stack.pop_back();
+    if (pi.NumOperands == 2 && pi.B.Kind != PLAN_OPERAND_STACK) bcls = operandClassOf(pi.B, bp, stack);
+    auto fill = [&](const PlanOperand &o, uint8_t &kind, uint8_t &col, uint8_t &valid, uint32_t &k) {
+      kind = o.Kind; col = o.Column; valid = o.ConstValid;
+      if (o.Kind == PLAN_OPERAND_CONST) {
+        if (o.ConstType == ConstFloat) memcpy(&k, &o.Const.FloatVal, 4); else k = (uint32_t)o.Const.IntVal;
+      }
+    };
+    fill(pi.A, I.akind, I.acol, I.avalid, I.aconst);
+    if (pi.NumOperands == 2) fill(pi.B, I.bkind, I.bcol, I.bvalid, I.bconst);
+    I.aclass = acls; I.bclass = bcls;
+
+    const bool wideIn = acls == VC_I64 || acls == VC_UUID || bcls == VC_I64 || bcls == VC_UUID;
+    if (wideIn) {
+      // only "dimension = 8/16-byte column" is meaningful (what UnaryTransform Noop to a
+      // DimensionOutput of the same type does)
+      ValClass oc = pi.Sink == PLAN_SINK_DIMENSION ? sinkClassOf(pi.SinkDataType, true) : VC_NONE;
+      if (pi.NumOperands != 1 || pi.Functor != Noop || pi.Sink != PLAN_SINK_DIMENSION || pi.A.Kind != PLAN_OPERAND_COLUMN ||
+          oc != (ValClass)acls)
+        throw EngineError("int64/UUID columns are only supported as verbatim dimensions on the fused path");
+      I.wide = 1;
+    } else if (pi.NumOperands == 2) {
+      I.tclass = commonClass((ValClass)acls, (ValClass)bcls);
+      Cell z; z.v = 0; z.valid = true;
+      ValClass rc;
+      evalBinary(pi.Functor, z, z, (ValClass)I.tclass, &rc);
+      I.rclass = rc;
+    } else {
+      I.tclass = acls;
+      Cell z; z.v = 0; z.valid = true;
+      ValClass rc;
+      evalUnary(pi.Functor, z, (ValClass)acls, &rc);
+      I.rclass = rc;
+    }
+    switch (pi.Sink) {
+      case PLAN_SINK_STACK: {
+        ValClass oc = sinkClassOf(pi.SinkDataType, false);
+        if (oc != VC_I32 && oc != VC_U32 && oc != VC_F32) throw EngineError("stack temporaries are Int32/Uint32/Float32");
+        if ((int)stack.size() >= ARES_PLAN_STACK_DEPTH) throw EngineError("plan exceeds the evaluation stack depth");
+        I.oclass = oc;
+        stack.push_back(oc);
+        break;
+      }
+      case PLAN_SINK_FILTER:
+        I.oclass = VC_BOOL;
+        P.lastFilter = i;
+        break;
+      case PLAN_SINK_DIMENSION: {
+        if (pi.SinkArg >= RL.numDims) throw EngineError("dimension ordinal outside AggSpec.NumDimsPerDimWidth");
+        ValClass oc = sinkClassOf(pi.SinkDataType, true);
+        if (classWidth(oc) != RL.width[pi.SinkArg]) throw EngineError("dimension data type does not match its layout width");
+        if (dimSeen[pi.SinkArg]) throw EngineError("dimension written twice");
+        dimSeen[pi.SinkArg] = true;
+        I.oclass = oc;
+        I.rowOff = RL.rowOff[pi.SinkArg];
+        I.width = RL.width[pi.SinkArg];
+        I.nullOff = (uint8_t)(RL.valueBytes + pi.SinkArg);
+        break;
+      }
+      case PLAN_SINK_MEASURE: {
+        if (measureSeen) throw EngineError("only one measure per plan");
+        measureSeen = true;
+        ValClass oc = sinkClassOf(pi.SinkDataType, false);
+        if (oc != st->measClass) throw EngineError("measure data type differs from AggSpec.MeasureDataType");
+        I.oclass = oc;
+        break;
+      }
+      default: throw EngineError("unknown plan sink");
+    }
+  }
+  if (!stack.empty()) throw EngineError("plan leaves values on the evaluation stack");
+  for (int d = 0; d < RL.numDims; d++)
+    if (!dimSeen[d]) throw EngineError("plan does not produce every dimension of AggSpec");
+  if (!measureSeen) throw EngineError("plan has no measure instruction");
+  P.hasMeasure = 1;
+  P.keyMode = st->keyMode;
+  P.rowBytes = (uint8_t)RL.rowBytes;
+  P.valueBytes = (uint8_t)RL.valueBytes;
+  P.hashBits = (uint8_t)st->hashBits;
+  P.aggOp = st->op;
+  P.measWidth = (uint8_t)st->measWidth;
+  P.measClass = st->measClass;
+  const int agg = st->spec.AggFunc;
+  P.skipCount = !((agg >= AGGR_SUM_UNSIGNED && agg <= AGGR_SUM_FLOAT) || agg == AGGR_AVG_FLOAT);
+  P.measureIdentity = aggIdentity(agg, st->measClass);
+  P.accNeutral = st->accNeutral;
+}
+
+// Decides staged vs direct, the tile size, the stage layout and the shared table size.
+static size_t layoutStages(DevPlan &P) {
+  bool canStage = P.numRows >= 1024;
+  uint32_t rowBits = 0;
+  for (int c = 0; c < P.ncols; c++) {
+    DevColumn &col = P.cols[c];
+    if (col.in.mode == 0) continue;
+    if (col.in.mode == 3) { canStage = false; break; }  // RLE: positional search, direct path
+    if (col.width > 4) continue;                          // wide dims are read directly
+    const uintptr_t v = reinterpret_cast<uintptr_t>(col.in.base + col.in.valuesOff);
+    if (v & 15) canStage = false;
+    if (col.in.mode == 2 && (reinterpret_cast<uintptr_t>(col.in.base + col.in.nullsOff) & 15)) canStage = false;
+    rowBits += col.width ? col.width * 8 : 1;
+    if (col.in.mode == 2) rowBits += 1;
+  }
+  bool anyStaged = false;
+  uint32_t tileRows = 0;
+  if (canStage && rowBits > 0) {
+    // largest tile such that kStages stages leave >= 32 KB for the shared table
+    for (uint32_t tr : {4096u, 2048u, 1024u}) {
+      size_t stage = 0;
+      for (int c = 0; c < P.ncols; c++) {
+        const DevColumn &col = P.cols[c];
+        if (col.in.mode == 0 || col.width > 4) continue;
+        stage += ((col.width ? (size_t)tr * col.width : tr / 8 + 16) + 15) / 16 * 16;
+        if (col.in.mode == 2) stage += (tr / 8 + 16 + 15) / 16 * 16;
+      }
+      if (stage * kStages + 32 * 1024 + 128 <= (size_t)kSmemBudget) { tileRows = tr; break; }
+    }
+  }
+  size_t stageBytes = 0;
+  if (tileRows) {
+    for (int c = 0; c < P.ncols; c++) {
+      DevColumn &col = P.cols[c];
+      if (col.in.mode == 0 || col.width > 4) continue;
+      col.staged = 1;
+      anyStaged = true;
+      col.smemValues = (uint32_t)stageBytes;
+      // bit-packed bools and bitmaps copy one 16-byte chunk beyond the tile so that a non-zero
+      // StartingIndex can read across the tile's last byte; the source has the row's own
+      // following bytes there (tiles are full), so the copy stays inside the column.
+      col.tileValueBytes = col.width ? tileRows * col.width : tileRows / 8 + 16;
+      stageBytes += (col.tileValueBytes + 15) / 16 * 16;
+      if (col.in.mode == 2) {
+        col.hasNulls = 1;
+        col.smemNulls = (uint32_t)stageBytes;
+        col.tileNullBytes = tileRows / 8 + 16;
+        stageBytes += (col.tileNullBytes + 15) / 16 * 16;
+      }
+    }
+  }
+  P.staged = anyStaged;
+  P.tileRows = anyStaged ? tileRows : 4 * kFusedThreads;
+  // the last full tile must leave >= 16 readable bytes after its bitmaps: keep one tile's worth
+  // of rows (at least 128) for the direct tail.
+  P.numFullTiles = anyStaged && P.numRows > 128 ? (P.numRows - 128) / tileRows : 0;
+  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; }
+  P.stageBytes = (uint32_t)stageBytes;
+  size_t left = (size_t)kSmemBudget - 128 - stageBytes * kStages;
+  uint32_t slots = 1024;
+  while ((size_t)slots * 2 * 16 <= left && slots < 8192) slots <<= 1;
+  P.smemSlots = slots;
+  return 128 + (size_t)slots * 16 + stageBytes * kStages;
+}
+
+static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
+  if (bp.NumRows == 0) return;
+  if (bp.NumRows > 0x7FFFFFFFu) throw EngineError("a batch holds at most 2^31-1 rows");
+  static thread_local DevPlan P;  // ~3 KB; passed by value as a __grid_constant__ parameter
+  compilePlan(st, bp, P);
+  const size_t smemBytes = layoutStages(P);
+  static bool attrSet[64] = {false};
+  if (!attrSet[st->device & 63]) {
+    ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
+    attrSet[st->device & 63] = true;
+  }
+  int grid = smCount();
+  const uint32_t work = P.staged ? P.numFullTiles : (P.numRows + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
+  if ((uint32_t)grid > work) grid = work ? (int)work : 1;
+  if (st->keyMode == KEY_HASHED) fusedBatchKernel<true><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
+  else fusedBatchKernel<false><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
+  checkLastError("ExecuteBatchPlan");
+}
+
+static void mergeRows(AggState *st, const DimensionVector &in, const uint8_t *values, int length, cudaStream_t s) {
+  if (length <= 0) return;
+  for (int i = 0; i < NUM_DIM_WIDTH; i++)
+    if (in.NumDimsPerDimWidth[i] != st->spec.NumDimsPerDimWidth[i]) throw EngineError("dimension layout differs from AggSpec");
+  DimLayout L = makeDimLayout(in.NumDimsPerDimWidth, in.VectorCapacity);
+  int blocks = divUp(length, 256);
+  if (blocks > smCount() * 8) blocks = smCount() * 8;
+  mergeRowsKernel<<<blocks, 256, 0, s>>>(in.DimValues, L, values, st->measWidth, st->op, length, st->keyMode,
+                                        (uint8_t)st->hashBits, st->table);
+  checkLastError("AggStateMerge");
+}
+
+static void checkOverflow(AggState *st, const uint32_t counters[2]) {
+  if (counters[1])
+    throw EngineError("group table overflow: more than " + std::to_string(st->capacity) +
+                      " slots needed; recreate the AggState with a larger AggSpec.ExpectedGroups and replay the batches");
+}
+
+static int64_t groupCount(AggState *st, cudaStream_t s) {
+  uint32_t c[2];
+  ARES_CUDA(cudaMemcpyAsync(c, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  checkOverflow(st, c);
+  return c[0];
+}
+
+static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outValues, cudaStream_t s) {
+  for (int i = 0; i < NUM_DIM_WIDTH; i++)
+    if (out.NumDimsPerDimWidth[i] != st->spec.NumDimsPerDimWidth[i]) throw EngineError("dimension layout differs from AggSpec");
+  const int64_t occupied = groupCount(st, s);
+  if (occupied == 0) return 0;
+  const int n = (int)occupied;
+  const int width = st->measWidth;
+  // 1. compact occupied slots (table order) with their reference hash and accumulator
+  const int tiles = divUp((int64_t)st->capacity, kCmpTile);
+  Scratch state(scanStateBytes(tiles) + sizeof(uint32_t), s);
+  ARES_CUDA(cudaMemsetAsync(state.ptr, 0, state.bytes, s));
+  ScanTileState sst = makeScanState(state.ptr, tiles);
+  uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
+  Scratch slotOf(sizeof(uint32_t) * (size_t)n, s), hash(sizeof(uint64_t) * (size_t)n, s), vals((size_t)width * n, s);
+  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, (uint8_t)st->hashBits,
+                                                   st->rowLayout.rowBytes, width, sst, slotOf.as<uint32_t>(),
+                                                   hash.as<uint64_t>(), vals.as<uint8_t>(), dCount);
+  checkLastError("compactGroups");
+  // 2. sort the groups by hash (stable), 3. merge equal hashes (reference group identity)
+  Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
+  iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);
+  radixSortPairs<uint32_t>(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 0,
+                           st->hashBits, s);
+  Scratch rep(sizeof(uint32_t) * (size_t)n, s);
+  Scratch mergedVals((size_t)width * n, s);
+  const int g = reduceByHash(hash.as<uint64_t>(), order.as<uint32_t>(), vals.as<uint8_t>(), width, st->op, n,
+                             rep.as<uint32_t>(), mergedVals.as<uint8_t>(), s,
+                             n <= out.VectorCapacity ? out.HashValues : nullptr);
+  if (g > out.VectorCapacity) throw EngineError("output DimensionVector capacity is smaller than the number of groups");
+  // 4. emit in the reference's layout
+  DimLayout L = makeDimLayout(out.NumDimsPerDimWidth, out.VectorCapacity);
+  int blocks = divUp(g, 256);
+  emitGroupsKernel<<<blocks, 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), rep.as<uint32_t>(), (uint32_t)g,
+                                          out.DimValues, L, out.IndexVector);
+  checkLastError("emitGroups");
+  ARES_CUDA(cudaMemcpyAsync(outValues, mergedVals.ptr, (size_t)width * g, cudaMemcpyDeviceToDevice, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  return g;
+}
+
+}  // namespace aresb
+
+using namespace aresb;
+
+extern "C" {
+
+CGoCallResHandle AggStateCreate(AggSpec spec, void *cudaStream, int device) {
+  CGoCallResHandle h = {nullptr, nullptr};
+  try {
+    ARES_CUDA(cudaSetDevice(device));
+    h.res = createState(spec, (cudaStream_t)cudaStream, device);
+  } catch (const std::exception &e) {
+    h.pStrErr = strdup((std::string("AggStateCreate: ") + e.what()).c_str());
+  }
+  return h;
+}
+
+CGoCallResHandle ExecuteBatchPlan(void *state, const BatchPlan *plan, void *cudaStream, int device) {
+  return guarded("ExecuteBatchPlan", device, [&]() -> int64_t {
+    if (!plan) throw EngineError("null plan");
+    executePlan(asState(state), *plan, (cudaStream_t)cudaStream);
+    return 0;
+  });
+}
+
+CGoCallResHandle AggStateMerge(void *state, DimensionVector inputKeys, uint8_t *inputValues, int length,
+                               void *cudaStream, int device) {
+  return guarded("AggStateMerge", device, [&]() -> int64_t {
+    mergeRows(asState(state), inputKeys, inputValues, length, (cudaStream_t)cudaStream);
+    return 0;
+  });
+}
+
+CGoCallResHandle AggStateGroupCount(void *state, void *cudaStream, int device) {
+  return guarded("AggStateGroupCount", device, [&]() -> int64_t { return groupCount(asState(state), (cudaStream_t)cudaStream); });
+}
+
+CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8_t *outputValues, void *cudaStream,
+                                  int device) {
+  return guarded("AggStateFinalize", device, [&]() -> int64_t {
+    return finalize(asState(state), outputKeys, outputValues, (cudaStream_t)cudaStream);
+  });
+}
+
+CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device) {
+  return guarded("AggStateReset", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    cudaStream_t s = (cudaStream_t)cudaStream;
+    ARES_CUDA(cudaMemsetAsync(st->table.counters, 0, 256, s));
+    fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, st->capacity, st->accNeutral);
+    checkLastError("AggStateReset");
+    return 0;
+  });
+}
+
+CGoCallResHandle AggStateDestroy(void *state, int device) {
+  return guarded("AggStateDestroy", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    if (st->mem) deviceFree(st->mem);
+    delete st;
+    return 0;
+  });
+}
+
+}  // extern "C"

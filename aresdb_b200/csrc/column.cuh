@@ -31,6 +31,7 @@ struct InputDesc {
 
 // Host: ABI struct -> descriptor; throws EngineError for inputs outside the hot path.
 InputDesc makeInputDesc(const InputVector &in, bool allowWide);
+InputDesc makeColumnDesc(const VectorPartySlice &vp, bool allowWide);
 
 #ifdef __CUDACC__
 __device__ __forceinline__ bool bitAt(const uint8_t *p, uint32_t bit) {

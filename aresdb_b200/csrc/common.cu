@@ -1,7 +1,12 @@
 // common.cu — small shared host utilities of libalgorithm.so.
 #include "common.cuh"
 
+#include <atomic>
+
 namespace aresb {
+
+static std::atomic<unsigned long long> g_launches{0};
+void noteLaunches(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int smCount() {
   static int cached[64] = {0};
@@ -31,3 +36,6 @@ void Scratch::release() {
 }
 
 }  // namespace aresb
+
+// Additive (not part of the reference ABI): number of engine kernels launched by this process so far.
+extern "C" unsigned long long AresKernelLaunchCount() { return aresb::g_launches.load(); }

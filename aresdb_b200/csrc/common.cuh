@@ -31,7 +31,10 @@ inline void cudaCheck(cudaError_t e, const char *what) {
 }
 #define ARES_CUDA(expr) ::aresb::cudaCheck((expr), #expr)
 
-inline void checkLastError(const char *what) { cudaCheck(cudaGetLastError(), what); }
+// Every kernel launch site is followed by checkLastError (or noteLaunches for grouped launches),
+// which also feeds the launch counter reported by bench.py as `gpu_launches`.
+void noteLaunches(int n);
+inline void checkLastError(const char *what) { noteLaunches(1); cudaCheck(cudaGetLastError(), what); }
 
 // Runs `body` (returns the integer result) with the device selected; never lets an
 // exception cross the C boundary.

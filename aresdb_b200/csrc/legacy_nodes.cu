@@ -27,6 +27,31 @@ static ValClass columnClass(int dtype) {
   }
 }
 
+InputDesc makeColumnDesc(const VectorPartySlice &vp, bool allowWide) {
+  InputDesc d;
+  memset(&d, 0, sizeof(d));
+  d.kind = IN_COLUMN;
+  d.dtype = (uint8_t)vp.DataType;
+  d.vclass = columnClass(vp.DataType);
+  if ((d.vclass == VC_I64 || d.vclass == VC_UUID) && !allowWide)
+    throw EngineError("int64/UUID data types are only supported in UnaryTransform");
+  d.base = vp.BasePtr; d.nullsOff = vp.NullsOffset; d.valuesOff = vp.ValuesOffset;
+  d.length = vp.Length; d.startBit = vp.StartingIndex;
+  if (vp.BasePtr == nullptr) {
+    d.mode = 0;
+    d.constValid = vp.DefaultValue.HasDefault;
+    switch (d.vclass) {
+      case VC_BOOL: d.constLo = vp.DefaultValue.Value.BoolVal ? 1 : 0; break;
+      case VC_I64: d.constLo = (uint64_t)vp.DefaultValue.Value.Int64Val; break;
+      case VC_UUID: d.constLo = vp.DefaultValue.Value.UUIDVal.p1; d.constHi = vp.DefaultValue.Value.UUIDVal.p2; break;
+      default: d.constLo = vp.DefaultValue.Value.Uint32Val; break;  // int32 / uint32 / float share the bits
+    }
+  } else {
+    d.mode = vp.ValuesOffset == 0 ? 1 : (vp.NullsOffset == 0 ? 2 : 3);
+  }
+  return d;
+}
+
 InputDesc makeInputDesc(const InputVector &in, bool allowWide) {
   InputDesc d;
   memset(&d, 0, sizeof(d));
@@ -54,29 +79,8 @@ InputDesc makeInputDesc(const InputVector &in, bool allowWide) {
       if (d.vclass == VC_UUID && !allowWide) throw EngineError("UUID operand is only supported as a unary root input");
       return d;
     }
-    case VectorPartyInput: {
-      const VectorPartySlice &vp = in.Vector.VP;
-      d.kind = IN_COLUMN;
-      d.dtype = (uint8_t)vp.DataType;
-      d.vclass = columnClass(vp.DataType);
-      if ((d.vclass == VC_I64 || d.vclass == VC_UUID) && !allowWide)
-        throw EngineError("int64/UUID data types are only supported in UnaryTransform");
-      d.base = vp.BasePtr; d.nullsOff = vp.NullsOffset; d.valuesOff = vp.ValuesOffset;
-      d.length = vp.Length; d.startBit = vp.StartingIndex;
-      if (vp.BasePtr == nullptr) {
-        d.mode = 0;
-        d.constValid = vp.DefaultValue.HasDefault;
-        switch (d.vclass) {
-          case VC_BOOL: d.constLo = vp.DefaultValue.Value.BoolVal ? 1 : 0; break;
-          case VC_I64: d.constLo = (uint64_t)vp.DefaultValue.Value.Int64Val; break;
-          case VC_UUID: d.constLo = vp.DefaultValue.Value.UUIDVal.p1; d.constHi = vp.DefaultValue.Value.UUIDVal.p2; break;
-          default: d.constLo = vp.DefaultValue.Value.Uint32Val; break;  // int32 / uint32 / float share the bits
-        }
-      } else {
-        d.mode = vp.ValuesOffset == 0 ? 1 : (vp.NullsOffset == 0 ? 2 : 3);
-      }
-      return d;
-    }
+    case VectorPartyInput:
+      return makeColumnDesc(in.Vector.VP, allowWide);
     case ForeignColumnInput:
       throw EngineError("ForeignColumnInput (dimension-table join) is outside the B200 hot path");
     default:

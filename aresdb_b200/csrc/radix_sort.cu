@@ -167,6 +167,7 @@ void radixSortPairs(uint64_t *keys, V *vals, uint64_t *keysTmp, V *valsTmp, int 
     digitHistogram<<<g.blocks, kSortThreads, 0, s>>>(kin, n, shift, g.chunk, hist.as<uint32_t>());
     scanHistograms<<<1, 1024, 0, s>>>(hist.as<uint32_t>(), kRadix * g.blocks);
     scatterByDigit<V><<<g.blocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, g.chunk, hist.as<uint32_t>());
+    noteLaunches(2);
     checkLastError("radixSortPairs");
     uint64_t *tk = kin; kin = kout; kout = tk;
     V *tv = vin; vin = vout; vout = tv;

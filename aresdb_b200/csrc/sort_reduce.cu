@@ -77,11 +77,13 @@ constexpr uint32_t kLongRun = 1u << 15;
 __global__ void __launch_bounds__(256)
 segmentReduceKernel(const uint32_t *__restrict__ index, const uint8_t *__restrict__ measures, int width, AggOp op,
                     const uint32_t *__restrict__ segStart, uint32_t g, uint32_t *__restrict__ outIndex,
-                    uint8_t *__restrict__ outValues, uint32_t *__restrict__ longList, uint32_t *__restrict__ longCount) {
+                    uint8_t *__restrict__ outValues, uint32_t *__restrict__ longList, uint32_t *__restrict__ longCount,
+                    const uint64_t *__restrict__ hash, uint64_t *__restrict__ outHash) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
   for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < g; s += warpsPerGrid) {
     const uint32_t begin = segStart[s], end = segStart[s + 1];
+    if (outHash != nullptr && lane == 0) outHash[s] = hash[begin];
     if (end - begin > kLongRun) {
       if (lane == 0) longList[atomicAdd(longCount, 1u)] = s;
       continue;
@@ -174,7 +176,7 @@ void gatherDims(const uint8_t *in, const DimLayout &Lin, const uint32_t *rows, i
 
 // Device-side reduce_by_key over equal consecutive hashes.  Returns the number of runs.
 int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *measures, int width, AggOp op,
-                 int n, uint32_t *outIndex, uint8_t *outValues, cudaStream_t s) {
+                 int n, uint32_t *outIndex, uint8_t *outValues, cudaStream_t s, uint64_t *outHash = nullptr) {
   if (n <= 0) return 0;
   const int tiles = divUp(n, kHeadTile);
   Scratch state(scanStateBytes(tiles) + 2 * sizeof(uint32_t), s);
@@ -191,7 +193,8 @@ int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *mea
   const uint32_t maxLong = (uint32_t)(n / kLongRun) + 1;
   Scratch longList(sizeof(uint32_t) * maxLong, s);
   segmentReduceKernel<<<gridFor((int64_t)g * 32, 256), 256, 0, s>>>(index, measures, width, op, segStart.as<uint32_t>(), g,
-                                                                   outIndex, outValues, longList.as<uint32_t>(), dLongCount);
+                                                                   outIndex, outValues, longList.as<uint32_t>(), dLongCount,
+                                                                   hash, outHash);
   checkLastError("segmentReduce");
   if ((uint32_t)n > kLongRun) {
     int blocks = (int)(maxLong < (uint32_t)smCount() * 2 ? maxLong : (uint32_t)smCount() * 2);

@@ -1,0 +1,266 @@
+"""Host-side batch executors: the driver of the hot path, mirroring the reference's Go
+`BatchExecutorImpl` (query/aql_batchexecutor.go:68-273) above the C ABI.
+
+* `LegacyBatchExecutor` issues exactly the per-node call sequence of the reference
+  (preExec -> filter -> project -> reduce -> postExec, with carried result vectors,
+  query/aql_processor.go:718-776) against ANY library exporting the reference's symbols — the B200
+  engine, or (in tests / the CPU baseline) a HOST-mode build running on host memory.
+* `FusedBatchExecutor` is the B200-native form: one ExecuteBatchPlan call per batch into a
+  device-resident AggState, one AggStateFinalize per query.
+
+Both take batches as lists of `VectorPartySlice`s that already live in the executor's memory space.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import cabi as A
+from . import expr as E
+from .memory import Buf
+from .query import AggQuery, QueryResult
+
+
+@dataclass
+class Batch:
+    """One live/archive batch of a table shard: column slices in device (or host) memory."""
+    columns: list            # list[cabi.VectorPartySlice], indexed by expr.Col.index
+    num_rows: int
+    base_counts: Buf | None = None   # cumulative counts of the first (RLE) column, or None
+    start_count: int = 0
+    keep: list = field(default_factory=list)  # owning buffers
+
+
+def dim_offsets(num_dims_per_width, capacity: int):
+    """Value / validity byte offsets of every dim in a DimensionVector block
+    (reference query/common/dimval.go:122-145)."""
+    offs, widths, pos = [], [], 0
+    for w, cnt in zip(A.DIM_WIDTHS, num_dims_per_width):
+        for _ in range(cnt):
+            offs.append(pos)
+            widths.append(w)
+            pos += w * capacity
+    nulls = [pos + i * capacity for i in range(len(widths))]
+    return offs, nulls, widths, pos + len(widths) * capacity
+
+
+class _ResultBuffers:
+    def __init__(self, space, query: AggQuery, capacity: int):
+        self.capacity = capacity
+        _, _, _, total = dim_offsets(query.num_dims_per_width, capacity)
+        self.dims = space.zeros(total)
+        self.hash = space.zeros(8 * capacity)
+        self.index = space.zeros(4 * capacity)
+        self.measures = space.zeros(query.measure_bytes * capacity)
+
+    def dimension_vector(self, query: AggQuery) -> A.DimensionVector:
+        return A.make_dimension_vector(self.dims.ptr, self.hash.ptr, self.index.ptr, query.num_dims_per_width,
+                                       self.capacity)
+
+
+class LegacyBatchExecutor:
+    """The reference's one-operator-per-kernel call sequence, batch after batch."""
+
+    def __init__(self, lib: A.Library, space, query: AggQuery):
+        self.lib, self.space, self.q = lib, space, query
+        self.result_size = 0
+        self.out: _ResultBuffers | None = None   # results of the batches processed so far
+        self.calls = 0                           # C-ABI calls issued (the reference's kernel-launch proxy)
+
+    # -- processExpression (reference query/time_series_aggregate.go:493-593) ----------------------
+    def _call(self, name, *args):
+        self.calls += 1
+        return getattr(self.lib, name)(*args)
+
+    def _eval(self, e: E.Expr, batch: Batch, ctx, action):
+        """Post-order walk; `action(functor, inputs)` consumes the root, inner nodes go to scratch."""
+        sp, lib, stream, dev = self.space, self.lib, self.space.stream, self.space.device
+        if isinstance(e, E.Col):
+            iv = A.vp_input(batch.columns[e.index])
+            if action:
+                action(A.Noop, [iv])
+                return None
+            return iv
+        if isinstance(e, E.Lit):
+            iv = A.const_input(e.value, True, is_float=e.type == E.Type.Float)
+            if action:
+                action(A.Noop, [iv])
+                return None
+            return iv
+        if isinstance(e, E.Unary):
+            inputs = [self._eval(e.expr, batch, ctx, None)]
+        else:
+            inputs = [self._eval(e.lhs, batch, ctx, None), self._eval(e.rhs, batch, ctx, None)]
+        if action:
+            action(e.op, inputs)
+            return None
+        dt = E.scratch_data_type(e.type)
+        size = ctx["size"]
+        frame = sp.zeros(5 * max(size, 1))         # allocateStackFrame: values[4B] + valid[1B] per row
+        ctx["frames"].append(frame)
+        ov = A.scratch_output(frame.ptr, 4 * size, dt)
+        bc = batch.base_counts.ptr if batch.base_counts else None
+        if size > 0:
+            if len(inputs) == 1:
+                self._call("UnaryTransform", inputs[0], ov, ctx["index"].ptr, size, bc, batch.start_count, e.op, stream, dev)
+            else:
+                self._call("BinaryTransform", inputs[0], inputs[1], ov, ctx["index"].ptr, size, bc, batch.start_count,
+                           e.op, stream, dev)
+        return A.scratch_input(frame.ptr, 4 * size, dt)
+
+    def process_batch(self, batch: Batch):
+        q, sp, stream, dev = self.q, self.space, self.space.stream, self.space.device
+        bc = batch.base_counts.ptr if batch.base_counts else None
+        size = batch.num_rows
+        # preExec: prepareForFiltering + InitIndexVector (aql_batchexecutor.go:256)
+        ctx = {"size": size, "index": sp.zeros(4 * max(size, 1)), "frames": []}
+        predicate = sp.zeros(max(size, 1))
+        self._call("InitIndexVector", ctx["index"].ptr, 0, size, stream, dev)
+
+        # filter (aql_batchexecutor.go:103; filterAction time_series_aggregate.go:369-396)
+        def filter_action(fn, inputs):
+            if ctx["size"] <= 0:
+                return
+            if len(inputs) == 1:
+                ctx["size"] = self._call("UnaryFilter", inputs[0], ctx["index"].ptr, predicate.ptr, ctx["size"], None, 0,
+                                         bc, batch.start_count, fn, stream, dev)
+            else:
+                ctx["size"] = self._call("BinaryFilter", inputs[0], inputs[1], ctx["index"].ptr, predicate.ptr,
+                                         ctx["size"], None, 0, bc, batch.start_count, fn, stream, dev)
+
+        for f in q.filters:
+            self._eval(f, batch, ctx, filter_action)
+            ctx["frames"].clear()
+        size = ctx["size"]
+
+        # project: prepareForDimAndMeasureEval (aql_processor.go:743-776) — input buffers hold the
+        # carried results in rows [0, resultSize) followed by this batch's rows
+        prev = self.result_size
+        cap = max(prev + size, 1)
+        inb = _ResultBuffers(sp, q, cap)
+        if prev > 0:
+            self._copy_results(self.out, inb, prev)
+        offs, nulls, widths, _ = dim_offsets(q.num_dims_per_width, cap)
+        for pos, qi in enumerate(q.dim_order):
+            dexpr, dt, w = q.dimensions[qi], q.dim_types[qi], widths[pos]
+
+            def dim_action(fn, inputs, pos=pos, dt=dt, w=w):
+                if ctx["size"] <= 0:
+                    return
+                ov = A.dimension_output(inb.dims.at(offs[pos] + w * prev), inb.dims.at(nulls[pos] + prev), dt)
+                if len(inputs) == 1:
+                    self._call("UnaryTransform", inputs[0], ov, ctx["index"].ptr, ctx["size"], bc, batch.start_count, fn, stream, dev)
+                else:
+                    self._call("BinaryTransform", inputs[0], inputs[1], ov, ctx["index"].ptr, ctx["size"], bc,
+                               batch.start_count, fn, stream, dev)
+
+            self._eval(dexpr, batch, ctx, dim_action)
+            ctx["frames"].clear()
+
+        def measure_action(fn, inputs):
+            if ctx["size"] <= 0:
+                return
+            ov = A.measure_output(inb.measures.at(prev * q.measure_bytes), q.measure_data_type, q.agg_func)
+            if len(inputs) == 1:
+                self._call("UnaryTransform", inputs[0], ov, ctx["index"].ptr, ctx["size"], bc, batch.start_count, fn, stream, dev)
+            else:
+                self._call("BinaryTransform", inputs[0], inputs[1], ov, ctx["index"].ptr, ctx["size"], bc,
+                           batch.start_count, fn, stream, dev)
+
+        self._eval(q.measure, batch, ctx, measure_action)
+        ctx["frames"].clear()
+
+        # reduce (aql_batchexecutor.go:219-253)
+        length = prev + size
+        outb = _ResultBuffers(sp, q, cap)
+        kin, kout = inb.dimension_vector(q), outb.dimension_vector(q)
+        if length > 0:
+            if q.reduce_mode == A.ARES_REDUCE_HASH:
+                self.result_size = self._call("HashReduce", kin, inb.measures.ptr, kout, outb.measures.ptr,
+                                              q.measure_bytes, length, q.agg_func, stream, dev)
+            else:
+                self._call("InitIndexVector", inb.index.ptr, 0, length, stream, dev)
+                self._call("Sort", kin, length, stream, dev)
+                self.result_size = self._call("Reduce", kin, inb.measures.ptr, kout, outb.measures.ptr, q.measure_bytes,
+                                              length, q.agg_func, stream, dev)
+        # postExec: swapResultBufferForNextBatch (aql_processor.go:718-723)
+        self.out = outb
+
+    def _copy_results(self, src: _ResultBuffers, dst: _ResultBuffers, rows: int):
+        q, sp = self.q, self.space
+        so, sn, widths, _ = dim_offsets(q.num_dims_per_width, src.capacity)
+        do, dn, _, _ = dim_offsets(q.num_dims_per_width, dst.capacity)
+        for p, w in enumerate(widths):
+            sp.copy(dst.dims, do[p], src.dims, so[p], w * rows)
+            sp.copy(dst.dims, dn[p], src.dims, sn[p], rows)
+        sp.copy(dst.measures, 0, src.measures, 0, q.measure_bytes * rows)
+
+    def result(self) -> QueryResult:
+        if self.out is None or self.result_size == 0:
+            return QueryResult(self.q, np.zeros(0, np.uint8), 1, np.zeros(0, np.uint8), 0)
+        return QueryResult(self.q, self.out.dims.get(np.uint8), self.out.capacity, self.out.measures.get(np.uint8),
+                           self.result_size)
+
+
+class FusedBatchExecutor:
+    """B200-native: one fused kernel per batch into a device-resident group table."""
+
+    def __init__(self, lib: A.Library, space, query: AggQuery, expected_groups: int = 0):
+        if not lib.has_plan_api:
+            raise RuntimeError("this library does not export the whole-batch plan API")
+        self.lib, self.space, self.q = lib, space, query
+        self.insts = query.plan_instructions()
+        self.state = C.c_void_p(lib.AggStateCreate(query.agg_spec(expected_groups), space.stream, space.device))
+        self._plan = A.BatchPlan()
+        self._plan.NumInsts = len(self.insts)
+        for i, pi in enumerate(self.insts):
+            self._plan.Insts[i] = pi
+        self.calls = 0
+
+    def process_batch(self, batch: Batch, stream=None):
+        p = self._plan
+        p.NumColumns = len(batch.columns)
+        for i, vp in enumerate(batch.columns):
+            p.Columns[i] = vp
+        p.BaseCounts = batch.base_counts.ptr if batch.base_counts else None
+        p.StartCount = batch.start_count
+        p.NumRows = batch.num_rows
+        self.calls += 1
+        self.lib.ExecuteBatchPlan(self.state, C.byref(p), self.space.stream if stream is None else stream,
+                                  self.space.device)
+
+    def merge(self, dim_vector: A.DimensionVector, measures_ptr: int, length: int):
+        self.lib.AggStateMerge(self.state, dim_vector, measures_ptr, length, self.space.stream, self.space.device)
+
+    def group_count(self) -> int:
+        return self.lib.AggStateGroupCount(self.state, self.space.stream, self.space.device)
+
+    def finalize_into(self, capacity: int | None = None):
+        """Returns (groups, _ResultBuffers) with the result left in device memory."""
+        cap = max(capacity if capacity is not None else self.group_count(), 1)
+        out = _ResultBuffers(self.space, self.q, cap)
+        g = self.lib.AggStateFinalize(self.state, out.dimension_vector(self.q), out.measures.ptr, self.space.stream,
+                                      self.space.device)
+        return g, out
+
+    def result(self) -> QueryResult:
+        g, out = self.finalize_into()
+        if g == 0:
+            return QueryResult(self.q, np.zeros(0, np.uint8), 1, np.zeros(0, np.uint8), 0)
+        return QueryResult(self.q, out.dims.get(np.uint8), out.capacity, out.measures.get(np.uint8), g)
+
+    def reset(self):
+        self.lib.AggStateReset(self.state, self.space.stream, self.space.device)
+
+    def close(self):
+        if self.state:
+            self.lib.AggStateDestroy(self.state, self.space.device)
+            self.state = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

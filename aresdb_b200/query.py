@@ -1,0 +1,167 @@
+"""Aggregate-query description and its translation into the two call forms of the hot path.
+
+An `AggQuery` carries what AQLQueryContext.OOPK carries after compilation (reference
+query/aql_context.go:151-235, query/aql_compiler.go:1139-1370): the main-table common filters,
+the dimension expressions with their output widths sorted into layout order
+(sortDimensionColumns), and the single measure with its aggregate function and byte width
+(count -> SUM_UNSIGNED of the literal 1 in 4 bytes; sum -> 8-byte accumulators).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import cabi as A
+from . import expr as E
+
+
+@dataclass
+class Measure:
+    kind: str                 # "count" | "sum" | "min" | "max"
+    expr: E.Expr | None = None
+
+
+class AggQuery:
+    def __init__(self, filters, dimensions, measure: Measure, reduce_mode: int = A.ARES_REDUCE_SORT):
+        self.filters = [E.resolve(f) for f in filters]
+        self.dimensions = [E.resolve(d) for d in dimensions]
+        self.reduce_mode = reduce_mode
+        # ---- dimensions: widest first, stable (reference query/aql_compiler.go:1341-1370) ----------
+        self.dim_types = [E.dimension_data_type(d) for d in self.dimensions]
+        widths = [max(A.DATA_TYPE_BYTES[t], 1) for t in self.dim_types]
+        self.dim_order = sorted(range(len(widths)), key=lambda i: -widths[i])  # layout position -> query dim
+        self.num_dims_per_width = [sum(1 for w in widths if w == W) for W in A.DIM_WIDTHS]
+        self.layout_widths = [widths[i] for i in self.dim_order]
+        if sum(widths) + len(widths) > A.MAX_DIMENSION_BYTES:
+            raise ValueError("dimension row exceeds MAX_DIMENSION_BYTES")
+        # ---- measure (reference query/aql_compiler.go:1139-1250) -------------------------------------
+        self.measure_kind = measure.kind
+        if measure.kind == "count":
+            self.measure = E.Lit(1, E.Type.Unsigned)
+            self.agg_func, self.measure_bytes = A.AGGR_SUM_UNSIGNED, 4
+        else:
+            self.measure = E.resolve(measure.expr)
+            t = self.measure.type
+            fam = {"sum": (A.AGGR_SUM_UNSIGNED, A.AGGR_SUM_SIGNED, A.AGGR_SUM_FLOAT),
+                   "min": (A.AGGR_MIN_UNSIGNED, A.AGGR_MIN_SIGNED, A.AGGR_MIN_FLOAT),
+                   "max": (A.AGGR_MAX_UNSIGNED, A.AGGR_MAX_SIGNED, A.AGGR_MAX_FLOAT)}[measure.kind]
+            if t not in (E.Type.Unsigned, E.Type.Signed, E.Type.Float):
+                raise ValueError(f"unsupported input type for {measure.kind}")
+            self.agg_func = fam[{E.Type.Unsigned: 0, E.Type.Signed: 1, E.Type.Float: 2}[t]]
+            self.measure_bytes = 8 if measure.kind == "sum" else 4
+        self.measure_data_type = self._output_data_type(self.measure.type, self.measure_bytes)
+
+    @staticmethod
+    def _output_data_type(t: E.Type, width: int) -> int:
+        """getOutputDataType — reference query/time_series_aggregate.go:337-363."""
+        if width == 4:
+            return A.Float32 if t == E.Type.Float else (A.Uint32 if t == E.Type.Unsigned else A.Int32)
+        return A.Float64 if t == E.Type.Float else A.Int64
+
+    @property
+    def row_bytes(self) -> int:
+        return sum(self.layout_widths) + len(self.layout_widths)
+
+    def agg_spec(self, expected_groups: int = 0) -> A.AggSpec:
+        spec = A.AggSpec()
+        for i in range(A.NUM_DIM_WIDTH):
+            spec.NumDimsPerDimWidth[i] = self.num_dims_per_width[i]
+        spec.AggFunc = self.agg_func
+        spec.MeasureDataType = self.measure_data_type
+        spec.ReduceMode = self.reduce_mode
+        spec.ExpectedGroups = expected_groups
+        return spec
+
+    # ---- fused plan ------------------------------------------------------------------------------
+    def plan_instructions(self) -> list[A.PlanInst]:
+        """Post-order flattening of every expression: one PlanInst per non-leaf AST node (what
+        processExpression turns into one cgo call, reference query/time_series_aggregate.go:493-593)."""
+        insts: list[A.PlanInst] = []
+
+        def operand(e: E.Expr) -> A.PlanOperand:
+            o = A.PlanOperand()
+            if isinstance(e, E.Col):
+                o.Kind, o.Column = A.PLAN_OPERAND_COLUMN, e.index
+            elif isinstance(e, E.Lit):
+                o.Kind, o.ConstValid = A.PLAN_OPERAND_CONST, 1
+                if e.type == E.Type.Float:
+                    o.ConstType, o.Const.FloatVal = A.ConstFloat, float(e.value)
+                else:
+                    o.ConstType, o.Const.IntVal = A.ConstInt, int(e.value)
+            else:
+                emit(e, A.PLAN_SINK_STACK, 0, E.scratch_data_type(e.type))
+                o.Kind = A.PLAN_OPERAND_STACK
+            return o
+
+        def emit(e: E.Expr, sink: int, sink_arg: int, sink_dt: int):
+            pi = A.PlanInst()
+            if isinstance(e, E.Binary):
+                a = operand(e.lhs)
+                b = operand(e.rhs)
+                pi.NumOperands, pi.Functor, pi.A, pi.B = 2, e.op, a, b
+            elif isinstance(e, E.Unary):
+                pi.NumOperands, pi.Functor, pi.A = 1, e.op, operand(e.expr)
+            else:  # a bare column / literal at the root: the Noop action
+                pi.NumOperands, pi.Functor, pi.A = 1, A.Noop, operand(e)
+            pi.Sink, pi.SinkArg, pi.SinkDataType = sink, sink_arg, sink_dt
+            insts.append(pi)
+
+        for f in self.filters:
+            emit(f, A.PLAN_SINK_FILTER, 0, A.Bool)
+        for pos, qi in enumerate(self.dim_order):
+            emit(self.dimensions[qi], A.PLAN_SINK_DIMENSION, pos, self.dim_types[qi])
+        emit(self.measure, A.PLAN_SINK_MEASURE, 0, self.measure_data_type)
+        if len(insts) > A.ARES_MAX_PLAN_INSTS:
+            raise ValueError("plan too long")
+        return insts
+
+
+class QueryResult:
+    """Groups of an aggregate query, decoded from the output DimensionVector block + measures."""
+
+    def __init__(self, query: AggQuery, block: np.ndarray, capacity: int, measures_raw: np.ndarray, groups: int):
+        self.query, self.groups = query, groups
+        np_meas = {A.Int32: np.int32, A.Uint32: np.uint32, A.Float32: np.float32, A.Int64: np.int64,
+                   A.Float64: np.float64}[query.measure_data_type]
+        if query.agg_func == A.AGGR_SUM_UNSIGNED and query.measure_bytes == 8:
+            np_meas = np.uint64
+        self.measures = measures_raw[:groups * query.measure_bytes].view(np_meas).copy()
+        self.dim_values: list[np.ndarray] = [None] * len(query.dimensions)
+        self.dim_valid: list[np.ndarray] = [None] * len(query.dimensions)
+        n = len(query.layout_widths)
+        pos = 0
+        value_offs = []
+        for w in query.layout_widths:
+            value_offs.append(pos)
+            pos += w * capacity
+        self.rows = []
+        raw_cols = []
+        for p, qi in enumerate(query.dim_order):
+            w = query.layout_widths[p]
+            vals = block[value_offs[p]:value_offs[p] + w * groups].reshape(groups, w).copy()
+            valid = block[pos + p * capacity: pos + p * capacity + groups].copy()
+            raw_cols.append((vals, valid))
+            self.dim_values[qi] = vals
+            self.dim_valid[qi] = valid
+        # packed rows in layout order (values then validity bytes): the reference's group identity
+        for g in range(groups):
+            self.rows.append(b"".join(bytes(v[g]) for v, _ in raw_cols) + bytes(bytearray(int(vd[g]) for _, vd in raw_cols)))
+
+    def as_dict(self) -> dict:
+        """packed dim row (bytes) -> measure value."""
+        return {r: self.measures[i].item() for i, r in enumerate(self.rows)}
+
+    def decoded_dims(self):
+        """Per query dimension: python values (None for NULL)."""
+        out = []
+        for qi, dt in enumerate(self.query.dim_types):
+            npdt = {A.Bool: np.uint8, A.Int8: np.int8, A.Uint8: np.uint8, A.Int16: np.int16, A.Uint16: np.uint16,
+                    A.Int32: np.int32, A.Uint32: np.uint32, A.Float32: np.float32, A.Int64: np.int64}.get(dt)
+            vals = self.dim_values[qi]
+            if npdt is None:
+                col = [bytes(v) for v in vals]
+            else:
+                col = vals.reshape(-1).view(npdt).tolist()
+            out.append([c if v else None for c, v in zip(col, self.dim_valid[qi])])
+        return out

@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py — the headline benchmark: rows/s of a time-bucketed SUM group-by over a 1e9-row
+synthetic fact table (BASELINE.json, config "1e9 rows, 3 filters + time-bucketizer + SUM group-by
+2 dims"), on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            the B200 engine
+    python bench.py --impl reference [--gpus N] ...                the reference's CPU path
+
+A step = one whole query: every archive batch of the table goes through ExecuteBatchPlan (one fused
+kernel per batch), then AggStateFinalize; with N > 1 the 8 day-batches are dealt round-robin to the
+ranks (strong scaling: the table stays 1e9 rows) and the per-GPU group tables are all-gathered over
+NCCL and merged on every rank.  One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+WORKLOAD = ("cfg3: 1e9-row fact table as 8 day-batches; filters status==1, fare>5.0, city_id!=0, "
+            "request_at in [t0+1800, t0+8d-1800); dims floor(request_at,3600) x city_id; SUM(fare) in f64")
+NUM_BATCHES = 8
+ALGO_BYTES_PER_ROW = 4 + 2 + 1 + 4 + 4 / 8.0  # request_at + city_id + status + fare + 4 null bitmaps (11.5)
+
+
+def build_query():
+    from aresdb_b200 import expr as E, synth
+    from aresdb_b200.query import AggQuery, Measure
+    TS, CITY, STATUS, FARE = (E.Col(i, t, n) for i, (t, n) in enumerate(zip(synth.COLUMN_TYPES, synth.COLUMN_NAMES)))
+    t0 = synth.BASE_TS
+    return AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0)), E.ne(CITY, E.Lit(0)),
+                     E.ge(TS, E.Lit(t0 + 1800)), E.lt(TS, E.Lit(t0 + NUM_BATCHES * 86400 - 1800))],
+                    [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE))
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the reference's own per-node call sequence on host cores
+# ---------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    """One worker process = one table shard slice: runs the reference call sequence over its rows."""
+    kind, day, rows, reps = args
+    sys.path.insert(0, str(ROOT))
+    from aresdb_b200 import cabi, columns, synth
+    from aresdb_b200.executor import Batch, LegacyBatchExecutor
+    from aresdb_b200.memory import HostSpace
+    if kind == "reference":
+        lib = cabi.Library(ROOT / "oracle" / "_ref" / "libalgorithm.so", ROOT / "oracle" / "_ref" / "libmem_ref.so",
+                           has_plan_api=False, name="ref")
+    else:
+        lib = cabi.Library(ROOT / "oracle" / "build" / "liboracle.so", None, has_plan_api=False, name="oracle")
+    sp = HostSpace()
+    hb = synth.generate_batch(day % NUM_BATCHES, rows, seed=777 + day)
+    cols, keep = [], []
+    for dt, v, ok in zip(synth.COLUMN_TYPES, hb.values, hb.valid):
+        buf, vp = columns.make_column(sp, dt, v, valid=ok)
+        cols.append(vp)
+        keep.append(buf)
+    q = build_query()
+    devnull = os.open(os.devnull, os.O_WRONLY)
+    saved = os.dup(1)
+    os.dup2(devnull, 1)  # the reference's HOST build prints a line per call (utils.cu:41-57)
+    times, groups = [], 0
+    try:
+        for _ in range(reps):
+            t = time.perf_counter()
+            ex = LegacyBatchExecutor(lib, sp, q)
+            ex.process_batch(Batch(cols, rows))
+            groups = ex.result_size
+            times.append(time.perf_counter() - t)
+    finally:
+        os.dup2(saved, 1)
+        os.close(devnull)
+    return times, groups
+
+
+def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: int | None = None):
+    """Times the reference CPU path: `workers` processes, each running the reference's
+    single-threaded batch executor over its own slice (the reference's unit of parallelism is the
+    table shard / batch).  A step = every worker processing its slice once, concurrently."""
+    import multiprocessing as mp
+    kind = "reference" if (ROOT / "oracle" / "_ref" / "libalgorithm.so").exists() else "port"
+    if kind == "port":
+        sys.path.insert(0, str(ROOT / "oracle"))
+        import build_oracle
+        build_oracle.build()
+    cores = os.cpu_count() or 1
+    workers = workers or max(1, min(cores, 64))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        t0 = time.perf_counter()
+        res = pool.map(_cpu_worker, [(kind, d, rows_per_worker, steps + warmup) for d in range(workers)])
+        wall = time.perf_counter() - t0
+    # per step, the job time is the slowest worker (they run concurrently)
+    per_step = [max(r[0][i] for r in res) for i in range(warmup, warmup + steps)]
+    ms = float(np.mean(per_step)) * 1e3
+    sample_rows = rows_per_worker * workers
+    return {"value": sample_rows / (ms / 1e3), "ms_per_step": ms, "kind": kind, "cores": workers,
+            "host_cores": cores, "sample": f"{workers} concurrent single-threaded workers x {rows_per_worker} rows of the "
+                                          f"cfg3 query per step (reference HOST path is single-threaded per batch)",
+            "groups": int(res[0][1]), "wall_s": wall}
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    def __init__(self, index: int):
+        self.samples, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0, set()
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = max(mx, float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# the B200 arm
+# ---------------------------------------------------------------------------------------------------
+def gpu_run(args):
+    import torch
+    import torch.distributed as dist
+    from aresdb_b200 import cabi as A
+    from aresdb_b200 import columns, synth
+    from aresdb_b200.executor import Batch, FusedBatchExecutor
+    from aresdb_b200.memory import CudaSpace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = A.load_engine()
+    stream = torch.cuda.current_stream().cuda_stream
+    space = CudaSpace(local, stream)
+    q = build_query()
+    rows_total = args.rows
+    rows_per_batch = rows_total // NUM_BATCHES
+    my_days = [d for d in range(NUM_BATCHES) if d % world == rank]
+
+    # ---- data: generated on the GPU, mirrored into pinned host memory for the e2e leg -------------
+    dev_bufs, batches, host_bufs = [], [], []
+    for d in my_days:
+        bufs, values_off = synth.generate_batch_cuda(d, rows_per_batch, dev)
+        dev_bufs.append(bufs)
+        cols = [columns.slice_of(b.data_ptr(), dt, rows_per_batch, 0, values_off, 2) for b, dt in zip(bufs, synth.COLUMN_TYPES)]
+        batches.append(Batch(cols, rows_per_batch))
+        if not args.no_e2e:
+            hb = []
+            for b in bufs:
+                h = torch.empty(b.numel(), dtype=torch.uint8, pin_memory=True)
+                h.copy_(b)
+                hb.append(h)
+            host_bufs.append(hb)
+    torch.cuda.synchronize()
+
+    ex = FusedBatchExecutor(lib, space, q, expected_groups=1 << 16)
+    merged = FusedBatchExecutor(lib, space, q, expected_groups=1 << 16) if world > 1 else None
+
+    def merge_across_ranks():
+        """All-gather every rank's (dim block, measures) and fold them into `merged` on every rank."""
+        g, out = ex.finalize_into()
+        counts = torch.zeros(world, dtype=torch.int64, device=dev)
+        counts[rank] = g
+        dist.all_reduce(counts)
+        cap = int(counts.max().item())
+        from aresdb_b200.executor import _ResultBuffers, dim_offsets
+        pad = _ResultBuffers(space, q, max(cap, 1))
+        offs_s, nulls_s, widths, _ = dim_offsets(q.num_dims_per_width, out.capacity)
+        offs_d, nulls_d, _, _ = dim_offsets(q.num_dims_per_width, pad.capacity)
+        for p, w in enumerate(widths):
+            space.copy(pad.dims, offs_d[p], out.dims, offs_s[p], w * g)
+            space.copy(pad.dims, nulls_d[p], out.dims, nulls_s[p], g)
+        space.copy(pad.measures, 0, out.measures, 0, q.measure_bytes * g)
+        all_dims = [torch.empty_like(pad.dims.handle) for _ in range(world)]
+        all_meas = [torch.empty_like(pad.measures.handle) for _ in range(world)]
+        dist.all_gather(all_dims, pad.dims.handle)
+        dist.all_gather(all_meas, pad.measures.handle)
+        merged.reset()
+        for r in range(world):
+            n = int(counts[r].item())
+            if n:
+                dv = A.make_dimension_vector(all_dims[r].data_ptr(), None, None, q.num_dims_per_width, pad.capacity)
+                merged.merge(dv, all_meas[r].data_ptr(), n)
+        return merged.finalize_into()
+
+    def step_device():
+        ex.reset()
+        for b in batches:
+            ex.process_batch(b)
+        if world > 1:
+            return merge_across_ranks()
+        return ex.finalize_into()
+
+    # e2e: host (pinned) columns -> H2D on a copy stream, double-buffered against the fused kernel
+    copy_stream = torch.cuda.Stream(device=dev)
+    staging = None
+    if not args.no_e2e and batches:
+        staging = [[torch.empty_like(b) for b in dev_bufs[0]] for _ in range(2)]
+
+    def step_e2e():
+        ex.reset()
+        main = torch.cuda.current_stream()
+        free_ev = [None, None]
+        h2d = 0
+        for i, hb in enumerate(host_bufs):
+            slot = i & 1
+            with torch.cuda.stream(copy_stream):
+                if free_ev[slot] is not None:
+                    copy_stream.wait_event(free_ev[slot])
+                elif i == 0:
+                    copy_stream.wait_stream(main)
+                for dst, src in zip(staging[slot], hb):
+                    dst.copy_(src, non_blocking=True)
+                    h2d += src.numel()
+                ready = torch.cuda.Event()
+                ready.record(copy_stream)
+            main.wait_event(ready)
+            values_off = (rows_per_batch + 7) // 8 + 1
+            values_off = (values_off + 63) // 64 * 64
+            cols = [columns.slice_of(t.data_ptr(), dt, rows_per_batch, 0, values_off, 2)
+                    for t, dt in zip(staging[slot], synth.COLUMN_TYPES)]
+            ex.process_batch(Batch(cols, rows_per_batch))
+            free_ev[slot] = torch.cuda.Event()
+            free_ev[slot].record(main)
+        g, out = merge_across_ranks() if world > 1 else ex.finalize_into()
+        dims_h = out.dims.handle[: max(out.dims.nbytes, 1)].cpu()
+        meas_h = out.measures.handle[: g * q.measure_bytes].cpu()
+        return g, h2d, dims_h.numel() + meas_h.numel()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        launches0 = lib.kernel_launch_count()
+        s.record()
+        last = None
+        for _ in range(steps):
+            last = fn()
+        e.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        ms = s.elapsed_time(e) / steps
+        launches = (lib.kernel_launch_count() - launches0) // steps
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, last
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms, launches, last = timed(step_device, args.steps, args.warmup)
+    groups = last[0]
+
+    # dominant kernel (fusedBatchKernel) timed alone, L2 cold because each batch (1.4 GB) >> L2
+    kern_ms = None
+    if batches:
+        ex.reset()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(2, min(args.steps, 5))
+        s.record()
+        for _ in range(reps):
+            for b in batches:
+                ex.process_batch(b)
+        e.record()
+        torch.cuda.synchronize()
+        kern_ms = s.elapsed_time(e) / (reps * len(batches))
+
+    e2e = None
+    if not args.no_e2e and host_bufs:
+        e_ms, _, e_last = timed(step_e2e, max(1, args.steps // 2), 1)
+        e2e = {"value": rows_total / (e_ms / 1e3), "unit": "rows/s", "ms_per_step": e_ms,
+               "h2d_bytes_per_step": int(e_last[1]) * world, "d2h_bytes_per_step": int(e_last[2])}
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    algo_bytes = ALGO_BYTES_PER_ROW * rows_per_batch
+    achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        cpu = cpu_reference_run(steps=2, warmup=1, rows_per_worker=args.cpu_rows)
+        cpu = {k: cpu[k] for k in ("value", "kind", "cores", "host_cores", "sample")}
+        cpu["unit"] = "rows/s"
+    out = {
+        "metric": "rows/s, 1e9-row time-bucketed SUM group-by (cfg3)", "value": rows_total / (ms / 1e3), "unit": "rows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "p50_query_ms": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32/u16/u8 filters, f32->f64 sum",
+        "data": "synthetic", "groups": int(groups),
+        "config": {"workload": WORKLOAD, "rows": rows_total, "batches": NUM_BATCHES, "rows_per_batch": rows_per_batch,
+                   "parallelism": f"batches round-robin over {world} GPU(s), NCCL all-gather merge" if world > 1 else "1 GPU",
+                   "l2": "inputs (1.44 GB per batch) larger than L2; no flush needed"},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "fusedBatchKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "traffic": None,
+                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
+                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
+        "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def reference_run(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.steps, args.warmup, rows_per_worker=args.cpu_rows)
+    out = {"impl": "reference", "metric": "rows/s, 1e9-row time-bucketed SUM group-by (cfg3)", "value": r["value"],
+           "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32/u16/u8 filters, f32->f64 sum",
+           "data": "synthetic", "config": {"workload": WORKLOAD, "rows": r["cores"] * args.cpu_rows,
+                                           "note": "bounded sample of the workload; CPU throughput is size-independent"},
+           "cpu_baseline": {"value": r["value"], "unit": "rows/s", "kind": r["kind"], "cores": r["cores"],
+                            "host_cores": r["host_cores"], "sample": r["sample"]},
+           "e2e": {"value": r["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--rows", type=int, default=1_000_000_000)
+    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows per CPU worker per step (baseline sample)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_run(args)
+    else:
+        gpu_run(args)
+
+
+if __name__ == "__main__":
+    main()

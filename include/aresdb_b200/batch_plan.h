@@ -127,6 +127,10 @@ CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device);
 
 CGoCallResHandle AggStateDestroy(void *state, int device);
 
+/* Diagnostics: engine kernels launched by this process so far (bench.py reports the delta over the
+ * timed region as `gpu_launches`). */
+unsigned long long AresKernelLaunchCount();
+
 #ifdef __cplusplus
 }
 #endif

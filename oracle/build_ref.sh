@@ -1,7 +1,7 @@
 #!/usr/bin/env bash
 # TEST INFRASTRUCTURE — builds the reference's own QUERY_MODE=HOST implementation of the
 # AQL batch-execution hot path (query/*.cu compiled as plain C++ with Thrust's CPP backend)
-# into oracle/_ref/{libmem.so,libalgorithm.so}.
+# into oracle/_ref/{libmem_ref.so,libalgorithm.so}.
 #
 # - Sources are read where they lie under $ARESDB_REFERENCE (default /root/reference).
 # - They need a small mechanical patch for Thrust 2.8 API drift; the patch
@@ -24,7 +24,7 @@ if [[ ! -d "$REF/query" ]]; then
   echo "build_ref: $REF/query not present; keeping any prebuilt oracle/_ref" >&2
   exit 0
 fi
-if [[ -f "$OUT/libalgorithm.so" && -f "$OUT/libmem.so" && "${1:-}" != "--force" ]]; then
+if [[ -f "$OUT/libalgorithm.so" && -f "$OUT/libmem_ref.so" && "${1:-}" != "--force" ]]; then
   echo "build_ref: oracle/_ref already built (use --force to rebuild)"
   exit 0
 fi
@@ -69,7 +69,9 @@ using std::max;
 EOF
 
 cd "$TMP"
-gcc $OPT -fPIC -shared cgoutils/memory/malloc.c -o "$OUT/libmem.so"
+# Distinct file names / sonames: a process that also loads the B200 engine (tests) must not let the
+# dynamic loader alias this malloc-backed libmem with the engine's CUDA libmem.
+gcc $OPT -fPIC -shared cgoutils/memory/malloc.c -Wl,-soname,libmem_ref.so -o "$OUT/libmem_ref.so"
 
 SRCS=(sort_reduce filter transform dimension_transform measure_transform scratch_space_transform
       hash_reduction hll hash_lookup functor utils iterator algorithm memory)
@@ -78,7 +80,7 @@ printf '%s\n' "${SRCS[@]}" | xargs -P "$JOBS" -I{} \
       -DTHRUST_DEVICE_SYSTEM=THRUST_DEVICE_SYSTEM_CPP -DSUPPORT_HASH_REDUCTION=1 \
       -I. -I"$CUDA_INC" -c query/{}.cu -o {}.o
 
-g++ -shared -o "$OUT/libalgorithm.so" ./*.o -L"$OUT" -lmem \
+g++ -shared -Wl,-soname,libalgorithm_ref.so -o "$OUT/libalgorithm.so" ./*.o -L"$OUT" -lmem_ref \
     -L"${CUDA_HOME:-/usr/local/cuda}/lib64" -lcudart -Wl,-rpath,'$ORIGIN'
 echo "built from $REF with g++ $(g++ -dumpversion) $OPT on $(date -u +%FT%TZ)" > "$OUT/BUILD_STAMP"
-echo "build_ref: wrote $OUT/libmem.so $OUT/libalgorithm.so"
+echo "build_ref: wrote $OUT/libmem_ref.so $OUT/libalgorithm.so"

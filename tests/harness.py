@@ -19,85 +19,7 @@ REF_DIR = ROOT / "oracle" / "_ref"
 ORACLE_LIB = ROOT / "oracle" / "build" / "liboracle.so"
 
 
-class Buf:
-    """A byte buffer in the memory space of a backend."""
-
-    def __init__(self, space, handle, nbytes):
-        self.space, self.handle, self.nbytes = space, handle, nbytes
-
-    @property
-    def ptr(self) -> int:
-        return self.space.ptr_of(self.handle)
-
-    def at(self, offset: int) -> int:
-        return self.ptr + offset
-
-    def get(self, dtype=np.uint8, count: int | None = None, offset: int = 0) -> np.ndarray:
-        raw = self.space.download(self.handle)
-        item = np.dtype(dtype).itemsize
-        if count is None:
-            count = (self.nbytes - offset) // item
-        return raw[offset:offset + count * item].view(dtype).copy()
-
-
-class HostSpace:
-    """Plain host memory (the reference's HOST build treats host pointers as device pointers)."""
-    device = 0
-    stream = None
-
-    def zeros(self, nbytes: int) -> Buf:
-        arr = np.zeros(max(int(nbytes), 1) + 64, dtype=np.uint8)
-        off = (-arr.ctypes.data) % 64
-        view = arr[off:off + max(int(nbytes), 1)]
-        return Buf(self, (arr, view), int(nbytes))
-
-    def put(self, data) -> Buf:
-        data = np.ascontiguousarray(data)
-        raw = data.view(np.uint8).reshape(-1)
-        b = self.zeros(raw.size)
-        b.handle[1][:raw.size] = raw
-        return b
-
-    def ptr_of(self, handle) -> int:
-        return handle[1].ctypes.data
-
-    def download(self, handle) -> np.ndarray:
-        return handle[1]
-
-    def sync(self):
-        pass
-
-
-class CudaSpace:
-    """Device memory owned by torch (plumbing only); pointers go through the C ABI."""
-
-    def __init__(self, device: int = 0):
-        import torch
-        self.torch = torch
-        self.device = device
-        self.stream = None  # legacy default stream, like the reference's unit tests
-
-    def zeros(self, nbytes: int) -> Buf:
-        t = self.torch.zeros(max(int(nbytes), 1), dtype=self.torch.uint8, device=f"cuda:{self.device}")
-        return Buf(self, t, int(nbytes))
-
-    def put(self, data) -> Buf:
-        data = np.ascontiguousarray(data)
-        raw = data.view(np.uint8).reshape(-1)
-        t = self.torch.from_numpy(raw.copy()).to(f"cuda:{self.device}")
-        if t.numel() == 0:
-            t = self.torch.zeros(1, dtype=self.torch.uint8, device=f"cuda:{self.device}")
-        return Buf(self, t, raw.size)
-
-    def ptr_of(self, handle) -> int:
-        return handle.data_ptr()
-
-    def download(self, handle) -> np.ndarray:
-        self.torch.cuda.synchronize(self.device)
-        return handle.cpu().numpy()
-
-    def sync(self):
-        self.torch.cuda.synchronize(self.device)
+from aresdb_b200.memory import Buf, CudaSpace, HostSpace  # noqa: E402,F401
 
 
 class Backend:
@@ -120,7 +42,7 @@ class Backend:
 @functools.lru_cache(maxsize=None)
 def get_backend(name: str) -> Backend:
     if name == "ref":
-        alg, mem = REF_DIR / "libalgorithm.so", REF_DIR / "libmem.so"
+        alg, mem = REF_DIR / "libalgorithm.so", REF_DIR / "libmem_ref.so"
         if not alg.exists():
             pytest.skip("oracle/_ref not built (needs /root/reference; run oracle/build_ref.sh)")
         return Backend("ref", cabi.Library(alg, mem, has_plan_api=False, name="ref"), HostSpace())
@@ -140,58 +62,16 @@ def get_backend(name: str) -> Backend:
 
 
 # ---- column / vector builders shared by the tests ---------------------------------------------
+from aresdb_b200.columns import NP_OF as _NP_OF, pack_bits  # noqa: E402,F401
+from aresdb_b200 import columns as _columns  # noqa: E402
+
+
 def align(n: int, a: int = 8) -> int:
     return (n + a - 1) // a * a
 
 
-def pack_bits(bits, start_bit: int = 0) -> np.ndarray:
-    bits = np.asarray(bits, dtype=np.uint8)
-    padded = np.concatenate([np.zeros(start_bit, np.uint8), bits])
-    return np.packbits(padded, bitorder="little")
-
-
-_NP_OF = {cabi.Int8: np.int8, cabi.Uint8: np.uint8, cabi.Int16: np.int16, cabi.Uint16: np.uint16,
-          cabi.Int32: np.int32, cabi.Uint32: np.uint32, cabi.Float32: np.float32, cabi.Int64: np.int64,
-          cabi.Uint64: np.uint64}
-
-
-def make_column(be: Backend, data_type: int, values, valid=None, counts=None, start_bit: int = 0,
-                default: cabi.DefaultValue | None = None, value_align: int = 64):
-    """Builds [counts][nulls][values] like memstore hands it to the query path and returns
-    (Buf, VectorPartySlice).  valid=None -> mode 1; counts given -> mode 3."""
-    n = len(values)
-    if data_type == cabi.Bool:
-        vbytes = pack_bits(np.asarray(values, dtype=np.uint8) != 0, start_bit)
-    elif data_type == cabi.UUID:
-        vbytes = np.ascontiguousarray(values, dtype=np.uint64).view(np.uint8).reshape(-1)
-    else:
-        vbytes = np.ascontiguousarray(values, dtype=_NP_OF[data_type]).view(np.uint8).reshape(-1)
-    parts, nulls_off, values_off = [], 0, 0
-    pos = 0
-    if counts is not None:
-        cb = np.ascontiguousarray(counts, dtype=np.uint32).view(np.uint8)
-        parts.append((pos, cb))
-        pos = align(pos + cb.size, value_align)
-    if valid is not None or counts is not None:
-        v = np.ones(n, np.uint8) if valid is None else np.asarray(valid, dtype=np.uint8)
-        nb = pack_bits(v != 0, start_bit)
-        nulls_off = pos
-        parts.append((pos, nb))
-        pos = align(pos + nb.size, value_align)
-    values_off = pos
-    parts.append((pos, vbytes))
-    total = pos + vbytes.size
-    raw = np.zeros(total, np.uint8)
-    for off, b in parts:
-        raw[off:off + b.size] = b
-    buf = be.put(raw)
-    if counts is None and valid is None:
-        vp = cabi.make_vp_slice(buf.ptr, 0, 0, start_bit, data_type, n, default)          # mode 1
-    elif counts is None:
-        vp = cabi.make_vp_slice(buf.ptr, 0, values_off, start_bit, data_type, n, default)  # mode 2
-    else:
-        vp = cabi.make_vp_slice(buf.ptr, nulls_off, values_off, start_bit, data_type, n, default)  # mode 3
-    return buf, vp
+def make_column(be, data_type, values, valid=None, counts=None, start_bit=0, default=None, value_align=64):
+    return _columns.make_column(be.space, data_type, values, valid, counts, start_bit, default, value_align)
 
 
 def make_scratch(be: Backend, data_type: int, values, valid):
