@@ -2,7 +2,9 @@
 // bindValueAndAggFunc, query/sort_reduce.cu:160-217; RollingAvgFunctor query/functor.hpp:1414-1436).
 #pragma once
 #include "cell.cuh"
+#ifndef __CUDACC_RTC__
 #include "common.cuh"
+#endif
 
 namespace aresb {
 
@@ -11,6 +13,7 @@ enum AggOp : uint8_t {
   OP_MIN_U32, OP_MIN_I32, OP_MIN_F32, OP_MAX_U32, OP_MAX_I32, OP_MAX_F32, OP_AVG, OP_INVALID
 };
 
+#ifndef __CUDACC_RTC__
 // (aggFunc, valueBytes) -> op and the effective element width the reference uses.
 inline AggOp aggOpOf(int aggFunc, int valueBytes, int *width) {
   int w = 4;
@@ -30,6 +33,7 @@ inline AggOp aggOpOf(int aggFunc, int valueBytes, int *width) {
   if (width) *width = w;
   return op;
 }
+#endif  // !__CUDACC_RTC__
 
 #ifdef __CUDACC__
 __device__ __forceinline__ uint64_t rollingAvg(uint64_t lhs, uint64_t rhs) {

@@ -21,6 +21,8 @@
 #include "agg.cuh"
 #include "column.cuh"
 #include "dimrow.cuh"
+#include "fused_device.cuh"
+#include "plan_device.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
 
@@ -30,189 +32,6 @@ namespace aresb {
 int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *measures, int width, AggOp op, int n,
                  uint32_t *outIndex, uint8_t *outValues, cudaStream_t s, uint64_t *outHash = nullptr);
 
-constexpr int kFusedThreads = 512;
-constexpr int kStages = 4;
-constexpr int kMaxPlanCols = 16;
-constexpr int kSmemBudget = 220 * 1024;       // of the 227 KB a CTA may opt into
-constexpr uint32_t kSmemProbeLimit = 16;
-constexpr uint32_t kGlobalProbeLimit = 8192;
-constexpr unsigned long long kEmptyKey = ~0ull;
-constexpr uint64_t kMix = 0x9E3779B97F4A7C15ull;
-
-enum KeyMode : uint8_t { KEY_PACKED = 0, KEY_HASHED = 1 };
-enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3 };
-
-struct DevColumn {
-  InputDesc in;            // how to read it straight from global memory (any mode)
-  uint32_t smemValues;     // byte offsets inside one stage (staged path)
-  uint32_t smemNulls;
-  uint32_t tileValueBytes; // bytes of one full tile
-  uint32_t tileNullBytes;
-  uint8_t width;           // bytes per value, 0 for bit-packed bool
-  uint8_t staged;          // values staged
-  uint8_t hasNulls;        // mode 2 bitmap staged
-  uint8_t pad;
-};
-
-struct DevInst {
-  uint32_t aconst, bconst;
-  uint8_t nops, fn, sink, sinkArg;
-  uint8_t akind, acol, aclass, avalid;
-  uint8_t bkind, bcol, bclass, bvalid;
-  uint8_t tclass;   // class the functor runs in
-  uint8_t rclass;   // class of the functor result
-  uint8_t oclass;   // class of the sink element
-  uint8_t wide;     // 1: 8/16-byte column copied verbatim into a dimension
-  uint8_t rowOff, width, nullOff, pad;
-};
-
-struct DevTable {
-  unsigned long long *keys;
-  unsigned long long *acc;
-  uint64_t *rows;        // [capacity][4] packed rows, KEY_HASHED only
-  uint32_t *counters;    // [0] occupied slots, [1] overflow flag
-  uint32_t mask;
-};
-
-struct DevPlan {
-  DevColumn cols[kMaxPlanCols];
-  DevInst insts[ARES_MAX_PLAN_INSTS];
-  const uint32_t *baseCounts;
-  uint32_t startCount;
-  uint32_t numRows;
-  uint32_t tileRows;
-  uint32_t numFullTiles;   // staged tiles; the tail goes through the direct path
-  uint32_t stageBytes;
-  uint32_t smemSlots;      // shared table slots (power of two)
-  int32_t ncols, ninsts, lastFilter;
-  uint64_t measureIdentity;  // NULL measure -> this (sink class bits)
-  uint64_t accNeutral;       // neutral element of the combine op
-  uint8_t keyMode, rowBytes, valueBytes, hashBits;
-  uint8_t aggOp, measWidth, measClass, skipCount;
-  uint8_t hasMeasure, staged, pad0, pad1;
-};
-
-// ---------------------------------------------------------------------------------------
-// device helpers: TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tmaLoad1D(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smemAddr(dstSmem)),
-               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
-               : "memory");
-}
-
-// ---------------------------------------------------------------------------------------
-// global group table
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
-  uint32_t slot = (uint32_t)((key * kMix) >> 29) & G.mask;
-  for (uint32_t probe = 0; probe < kGlobalProbeLimit; probe++) {
-    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&G.keys[slot]);
-    if (k == key) return slot;
-    if (k == kEmptyKey) {
-      unsigned long long old = atomicCAS(&G.keys[slot], kEmptyKey, key);
-      if (old == kEmptyKey) {
-        atomicAdd(&G.counters[0], 1u);
-        if (roww != nullptr && G.rows != nullptr) {
-#pragma unroll
-          for (int i = 0; i < 4; i++) G.rows[(size_t)slot * 4 + i] = roww[i];
-        }
-        return slot;
-      }
-      if (old == key) return slot;
-    }
-    slot = (slot + 1) & G.mask;
-  }
-  atomicExch(&G.counters[1], 1u);
-  return 0xFFFFFFFFu;
-}
-
-__device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsigned long long key, const uint64_t *roww,
-                                             uint64_t val) {
-  uint32_t slot = globalFindOrClaim(G, key, roww);
-  if (slot != 0xFFFFFFFFu) aggAtomic(op, &G.acc[slot], val);
-}
-
-// ---------------------------------------------------------------------------------------
-// CTA-private shared-memory table
-// ---------------------------------------------------------------------------------------
-struct SmemTable {
-  unsigned long long *keys;
-  unsigned long long *acc;
-  uint32_t *claims;   // number of occupied slots
-  uint32_t mask;
-};
-
-__device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, uint64_t v) {
-  switch (op) {
-    case OP_SUM_I32: atomicAdd(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
-    case OP_SUM_F32: atomicAdd(reinterpret_cast<float *>(addr), __uint_as_float((uint32_t)v)); break;
-    case OP_SUM_I64: atomicAdd(addr, (unsigned long long)v); break;
-    case OP_SUM_F64: atomicAdd(reinterpret_cast<double *>(addr), __longlong_as_double((long long)v)); break;
-    case OP_MIN_U32: atomicMin(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
-    case OP_MIN_I32: atomicMin(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
-    case OP_MAX_U32: atomicMax(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
-    case OP_MAX_I32: atomicMax(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
-    default: {  // float min / max
-      unsigned int *a = reinterpret_cast<unsigned int *>(addr);
-      unsigned int old = *a, assumed;
-      do {
-        assumed = old;
-        unsigned int want = (unsigned int)aggCombine(op, assumed, v);
-        if (want == assumed) break;
-        old = atomicCAS(a, assumed, want);
-      } while (old != assumed);
-      break;
-    }
-  }
-}
-
-// Returns false when the row has to go to the global table (shared table full around its home).
-__device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
-                                           const uint64_t *roww, uint64_t val, bool allowClaim) {
-  uint32_t slot = (uint32_t)((key * kMix) >> 40) & T.mask;
-  for (uint32_t probe = 0; probe < kSmemProbeLimit; probe++) {
-    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
-    if (k == kEmptyKey) {
-      if (!allowClaim) return false;
-      unsigned long long old = atomicCAS(&T.keys[slot], kEmptyKey, key);
-      if (old == kEmptyKey) {
-        atomicAdd(T.claims, 1u);
-        // wide keys: the packed row is recorded in the global table once, by whoever claims first
-        if (roww != nullptr) globalFindOrClaim(G, key, roww);
-        k = key;
-      } else {
-        k = old;
-      }
-    }
-    if (k == key) {
-      smemAtomic(op, &T.acc[slot], val);
-      return true;
-    }
-    slot = (slot + 1) & T.mask;
-  }
-  return false;
-}
 
 // ---------------------------------------------------------------------------------------
 // 4-row vector evaluation
@@ -621,7 +440,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   }
   // ---- rows not covered by staged tiles (tail, or the whole batch on the direct path) --------
   {
-    const uint32_t begin = P.staged ? P.numFullTiles * P.tileRows : 0;
+    const uint32_t begin = P.staged ? P.numFullTiles * P.tileRows : P.tailBegin;
     const uint32_t quads = (P.numRows - begin + R - 1) / R;
     const bool allowClaim = true;
     for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < quads; q += gridDim.x * blockDim.x) {
@@ -800,22 +619,25 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   checkLastError("fillTable");
 }
 
+static void describeState(AggState *st, const AggSpec &spec) {
+  st->spec = spec;
+  st->rowLayout = makeDimLayout(spec.NumDimsPerDimWidth, 1);
+  if (spec.ReduceMode != ARES_REDUCE_SORT && spec.ReduceMode != ARES_REDUCE_HASH) throw EngineError("unknown ReduceMode");
+  st->hashBits = spec.ReduceMode == ARES_REDUCE_SORT ? 64 : 32;
+  st->keyMode = st->rowLayout.rowBytes <= 8 ? KEY_PACKED : KEY_HASHED;
+  st->measClass = measureClassOf(spec.MeasureDataType);
+  int bytes = (st->measClass == VC_I64 || st->measClass == VC_F64) ? 8 : 4;
+  if (spec.AggFunc == AGGR_AVG_FLOAT || spec.AggFunc == AGGR_HLL)
+    throw EngineError("AVG / HLL aggregates are not available on the fused path; use the per-node entry points");
+  st->op = aggOpOf(spec.AggFunc, bytes, &st->measWidth);
+  st->accNeutral = neutralOf(st->op);
+}
+
 static AggState *createState(const AggSpec &spec, cudaStream_t s, int device) {
   AggState *st = new AggState();
   try {
-    st->spec = spec;
+    describeState(st, spec);
     st->device = device;
-    st->rowLayout = makeDimLayout(spec.NumDimsPerDimWidth, 1);
-    if (spec.ReduceMode != ARES_REDUCE_SORT && spec.ReduceMode != ARES_REDUCE_HASH)
-      throw EngineError("unknown ReduceMode");
-    st->hashBits = spec.ReduceMode == ARES_REDUCE_SORT ? 64 : 32;
-    st->keyMode = st->rowLayout.rowBytes <= 8 ? KEY_PACKED : KEY_HASHED;
-    st->measClass = measureClassOf(spec.MeasureDataType);
-    int bytes = (st->measClass == VC_I64 || st->measClass == VC_F64) ? 8 : 4;
-    if (spec.AggFunc == AGGR_AVG_FLOAT || spec.AggFunc == AGGR_HLL)
-      throw EngineError("AVG / HLL aggregates are not available on the fused path; use the per-node entry points");
-    st->op = aggOpOf(spec.AggFunc, bytes, &st->measWidth);
-    st->accNeutral = neutralOf(st->op);
     size_t want = spec.ExpectedGroups ? (size_t)spec.ExpectedGroups * 2 : ((size_t)1 << 21);
     size_t cap = 1 << 12;
     while (cap < want) cap <<= 1;
@@ -1076,6 +898,7 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   if (bp.NumRows > 0x7FFFFFFFu) throw EngineError("a batch holds at most 2^31-1 rows");
   static thread_local DevPlan P;  // ~3 KB; passed by value as a __grid_constant__ parameter
   compilePlan(st, bp, P);
+  P.tailBegin = 0;
   const size_t smemBytes = layoutStages(P);
   static bool attrSet[64] = {false};
   if (!attrSet[st->device & 63]) {
@@ -1086,6 +909,15 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   int grid = smCount();
   const uint32_t work = P.staged ? P.numFullTiles : (P.numRows + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
   if ((uint32_t)grid > work) grid = work ? (int)work : 1;
+  if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) {
+    // the specialised kernel covered the staged tiles; the interpreter only sees the tail rows
+    const uint32_t done = P.numFullTiles * P.tileRows;
+    if (done >= P.numRows) return;
+    P.staged = 0;
+    P.tailBegin = done;
+    const uint32_t tailWork = (P.numRows - done + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
+    grid = (int)(tailWork < (uint32_t)smCount() ? tailWork : (uint32_t)smCount());
+  }
   if (st->keyMode == KEY_HASHED) fusedBatchKernel<true><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
   else fusedBatchKernel<false><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
   checkLastError("ExecuteBatchPlan");
@@ -1210,6 +1042,29 @@ CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device) {
     checkLastError("AggStateReset");
     return 0;
   });
+}
+
+// Additive diagnostics, usable without a GPU: generates + NVRTC-compiles the specialised kernel of
+// (spec, plan) and returns the cubin size in res (0: plan not eligible); *sourceOut (optional) gets a
+// malloc'd copy of the generated shape-specific source.
+CGoCallResHandle AresJitDryRun(AggSpec spec, const BatchPlan *plan, char **sourceOut) {
+  CGoCallResHandle h = {nullptr, nullptr};
+  try {
+    AggState st;
+    memset(&st.table, 0, sizeof(st.table));
+    describeState(&st, spec);
+    static thread_local DevPlan P;
+    compilePlan(&st, *plan, P);
+    P.tailBegin = 0;
+    layoutStages(P);
+    std::string src;
+    size_t n = P.staged ? jitCompileOnly(P, &src) : 0;
+    if (sourceOut) *sourceOut = strdup(src.c_str());
+    h.res = reinterpret_cast<void *>(n);
+  } catch (const std::exception &e) {
+    h.pStrErr = strdup((std::string("AresJitDryRun: ") + e.what()).c_str());
+  }
+  return h;
 }
 
 CGoCallResHandle AggStateDestroy(void *state, int device) {

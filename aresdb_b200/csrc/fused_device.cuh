@@ -1,0 +1,147 @@
+// fused_device.cuh — device building blocks shared by the ahead-of-time interpreter kernel
+// (batch_plan.cu) and the NVRTC-specialised kernels (jit.cu): TMA bulk copies + mbarriers, the
+// CTA-private shared-memory group table and the global (L2-resident) group table.
+// NVRTC-clean: no host headers (the JIT prelude provides the fixed-width typedefs).
+#pragma once
+#include "agg.cuh"
+
+namespace aresb {
+
+constexpr int kStages = 4;
+constexpr uint32_t kSmemProbeLimit = 16;
+constexpr uint32_t kGlobalProbeLimit = 8192;
+constexpr unsigned long long kEmptyKey = ~0ull;
+constexpr uint64_t kMix = 0x9E3779B97F4A7C15ull;
+
+struct DevTable {
+  unsigned long long *keys;
+  unsigned long long *acc;
+  uint64_t *rows;        // [capacity][4] packed rows, wide (hashed) keys only
+  uint32_t *counters;    // [0] occupied slots, [1] overflow flag
+  uint32_t mask;
+};
+
+// ---------------------------------------------------------------------------------------
+// device helpers: TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smemAddr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbarInit(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmaLoad1D(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smemAddr(dstSmem)),
+               "l"(srcGlobal), "r"(bytes), "r"(smemAddr(bar))
+               : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// global group table
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
+  uint32_t slot = (uint32_t)((key * kMix) >> 29) & G.mask;
+  for (uint32_t probe = 0; probe < kGlobalProbeLimit; probe++) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&G.keys[slot]);
+    if (k == key) return slot;
+    if (k == kEmptyKey) {
+      unsigned long long old = atomicCAS(&G.keys[slot], kEmptyKey, key);
+      if (old == kEmptyKey) {
+        atomicAdd(&G.counters[0], 1u);
+        if (roww != nullptr && G.rows != nullptr) {
+#pragma unroll
+          for (int i = 0; i < 4; i++) G.rows[(size_t)slot * 4 + i] = roww[i];
+        }
+        return slot;
+      }
+      if (old == key) return slot;
+    }
+    slot = (slot + 1) & G.mask;
+  }
+  atomicExch(&G.counters[1], 1u);
+  return 0xFFFFFFFFu;
+}
+
+__device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsigned long long key, const uint64_t *roww,
+                                             uint64_t val) {
+  uint32_t slot = globalFindOrClaim(G, key, roww);
+  if (slot != 0xFFFFFFFFu) aggAtomic(op, &G.acc[slot], val);
+}
+
+// ---------------------------------------------------------------------------------------
+// CTA-private shared-memory table
+// ---------------------------------------------------------------------------------------
+struct SmemTable {
+  unsigned long long *keys;
+  unsigned long long *acc;
+  uint32_t *claims;   // number of occupied slots
+  uint32_t mask;
+};
+
+__device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, uint64_t v) {
+  switch (op) {
+    case OP_SUM_I32: atomicAdd(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
+    case OP_SUM_F32: atomicAdd(reinterpret_cast<float *>(addr), __uint_as_float((uint32_t)v)); break;
+    case OP_SUM_I64: atomicAdd(addr, (unsigned long long)v); break;
+    case OP_SUM_F64: atomicAdd(reinterpret_cast<double *>(addr), __longlong_as_double((long long)v)); break;
+    case OP_MIN_U32: atomicMin(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
+    case OP_MIN_I32: atomicMin(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
+    case OP_MAX_U32: atomicMax(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
+    case OP_MAX_I32: atomicMax(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
+    default: {  // float min / max
+      unsigned int *a = reinterpret_cast<unsigned int *>(addr);
+      unsigned int old = *a, assumed;
+      do {
+        assumed = old;
+        unsigned int want = (unsigned int)aggCombine(op, assumed, v);
+        if (want == assumed) break;
+        old = atomicCAS(a, assumed, want);
+      } while (old != assumed);
+      break;
+    }
+  }
+}
+
+// Returns false when the row has to go to the global table (shared table full around its home).
+__device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
+                                           const uint64_t *roww, uint64_t val, bool allowClaim) {
+  uint32_t slot = (uint32_t)((key * kMix) >> 40) & T.mask;
+  for (uint32_t probe = 0; probe < kSmemProbeLimit; probe++) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+    if (k == kEmptyKey) {
+      if (!allowClaim) return false;
+      unsigned long long old = atomicCAS(&T.keys[slot], kEmptyKey, key);
+      if (old == kEmptyKey) {
+        atomicAdd(T.claims, 1u);
+        // wide keys: the packed row is recorded in the global table once, by whoever claims first
+        if (roww != nullptr) globalFindOrClaim(G, key, roww);
+        k = key;
+      } else {
+        k = old;
+      }
+    }
+    if (k == key) {
+      smemAtomic(op, &T.acc[slot], val);
+      return true;
+    }
+    slot = (slot + 1) & T.mask;
+  }
+  return false;
+}
+
+
+}  // namespace aresb

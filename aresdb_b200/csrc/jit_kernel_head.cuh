@@ -1,0 +1,58 @@
+// jit_kernel_head.cuh — first half of the NVRTC-specialised fused kernel's source text: runtime
+// parameter block and the quad loaders.  Compiled ONLY by NVRTC (see jit.cu); the generated
+// rowEval() for one plan shape is pasted between this file and jit_kernel_tail.cuh, after a
+// block of #defines / constexpr tables describing the shape (tile size, stage layout, key words,
+// aggregate op).  Everything shape-dependent is a compile-time constant; only pointers, literal
+// operands and row counts are runtime values, so one compiled kernel serves every batch and every
+// query with the same structure.
+namespace aresb {
+
+constexpr int kJitMaxParts = 32;
+constexpr int kJitMaxConsts = 64;
+constexpr int kJitMaxWide = 8;
+
+struct JitParams {
+  const uint8_t *partSrc[kJitMaxParts];   // global base address of every staged part
+  const uint8_t *wideValues[kJitMaxWide]; // 8/16-byte dimension columns read straight from global
+  const uint8_t *wideNulls[kJitMaxWide];
+  uint32_t consts[kJitMaxConsts];         // literal operands / mode-0 defaults (raw 32-bit cells)
+  unsigned long long measureIdentity;
+  unsigned long long accNeutral;
+  DevTable G;
+  uint32_t numFullTiles;
+};
+
+// rows 4q .. 4q+3 of a staged value column of W bytes per value
+template <int W, bool SIGNED>
+__device__ __forceinline__ void ldq(const uint8_t *vals, uint32_t q, uint32_t (&v)[4]) {
+  if (W == 4) {
+    uint4 x = *reinterpret_cast<const uint4 *>(vals + 16 * q);
+    v[0] = x.x; v[1] = x.y; v[2] = x.z; v[3] = x.w;
+  } else if (W == 2) {
+    uint2 x = *reinterpret_cast<const uint2 *>(vals + 8 * q);
+    if (SIGNED) {
+      v[0] = (uint32_t)(int32_t)(int16_t)(x.x & 0xffff); v[1] = (uint32_t)((int32_t)x.x >> 16);
+      v[2] = (uint32_t)(int32_t)(int16_t)(x.y & 0xffff); v[3] = (uint32_t)((int32_t)x.y >> 16);
+    } else {
+      v[0] = x.x & 0xffff; v[1] = x.x >> 16; v[2] = x.y & 0xffff; v[3] = x.y >> 16;
+    }
+  } else {
+    uint32_t x = *reinterpret_cast<const uint32_t *>(vals + 4 * q);
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      v[r] = SIGNED ? (uint32_t)(int32_t)(int8_t)((x >> (8 * r)) & 0xff) : ((x >> (8 * r)) & 0xff);
+  }
+}
+
+// 4 consecutive bits (rows 4q..4q+3) of a bit-packed vector whose row 0 sits at bit START_BIT
+template <int START_BIT>
+__device__ __forceinline__ uint32_t ldbits(const uint8_t *bits, uint32_t q) {
+  if (START_BIT == 0) return (bits[q >> 1] >> ((q & 1) * 4)) & 0xF;
+  const uint32_t bit = 4 * q + START_BIT;
+  const uint32_t w = bits[bit >> 3] | ((uint32_t)bits[(bit >> 3) + 1] << 8);
+  return (w >> (bit & 7)) & 0xF;
+}
+
+__device__ __forceinline__ bool bitOf(const uint8_t *p, uint32_t bit) { return (p[bit >> 3] >> (bit & 7)) & 1; }
+
+}  // namespace aresb

@@ -1,0 +1,86 @@
+// jit_kernel_tail.cuh — second half of the NVRTC-specialised fused kernel: the persistent
+// tile loop (TMA-staged ring of JIT_STAGES buffers), aggregation of the surviving rows into the
+// CTA-private shared table, and the flush into the global table.  The shape macros
+// (JIT_TILE_ROWS, JIT_STAGE_BYTES, JIT_SMEM_SLOTS, JIT_KW, JIT_AGG_OP, JIT_HASH_BITS,
+// JIT_ROW_BYTES, JIT_THREADS, JIT_NUM_PARTS + kPartSmemOff/kPartBytes/kPartTileStride) and
+// rowEval() precede this text.
+namespace aresb {
+
+__device__ __forceinline__ void jitIssueTile(const JitParams &P, uint32_t tile, uint8_t *stage, uint64_t *bar) {
+  mbarExpectTx(bar, JIT_STAGE_TX_BYTES);
+#pragma unroll
+  for (int p = 0; p < JIT_NUM_PARTS; p++)
+    tmaLoad1D(stage + kPartSmemOff[p], P.partSrc[p] + (size_t)tile * kPartTileStride[p], kPartBytes[p], bar);
+}
+
+extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const __grid_constant__ JitParams P) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);
+  unsigned long long *tKeys = reinterpret_cast<unsigned long long *>(smem + 128);
+  unsigned long long *tAcc = tKeys + JIT_SMEM_SLOTS;
+  uint8_t *stages = reinterpret_cast<uint8_t *>(tAcc + JIT_SMEM_SLOTS);
+
+  SmemTable T;
+  T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = JIT_SMEM_SLOTS - 1;
+  for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
+    tKeys[i] = kEmptyKey;
+    tAcc[i] = P.accNeutral;
+  }
+  if (threadIdx.x == 0) {
+    *claims = 0;
+    for (int s = 0; s < kStages; s++) mbarInit(&bars[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  constexpr uint32_t kQuads = JIT_TILE_ROWS / 4;
+  constexpr AggOp op = (AggOp)JIT_AGG_OP;
+  const uint32_t first = blockIdx.x, step = gridDim.x;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) {
+      uint32_t t = first + s * step;
+      if (t < P.numFullTiles) jitIssueTile(P, t, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
+    }
+  }
+  uint32_t it = 0;
+  for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
+    const uint32_t s = it % kStages, parity = (it / kStages) & 1;
+    mbarWait(&bars[s], parity);
+    const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
+    const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
+#pragma unroll 1
+    for (uint32_t q = threadIdx.x; q < kQuads; q += JIT_THREADS) {
+      uint64_t key[4][JIT_KW];
+      uint64_t meas[4];
+      const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
+      if (alive == 0) continue;
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (!((alive >> r) & 1)) continue;
+        unsigned long long k;
+        const uint64_t *roww = nullptr;
+        if (JIT_KW == 1) {
+          k = key[r][0];
+        } else {
+          uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
+          k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+          roww = key[r];
+        }
+        if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) globalUpdate(P.G, op, k, roww, meas[r]);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      uint32_t nt = t + kStages * step;
+      if (nt < P.numFullTiles) jitIssueTile(P, nt, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
+    }
+  }
+  __syncthreads();
+  for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
+    unsigned long long k = tKeys[i];
+    if (k != kEmptyKey) globalUpdate(P.G, op, k, nullptr, tAcc[i]);
+  }
+}
+
+}  // namespace aresb

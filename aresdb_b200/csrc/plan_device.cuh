@@ -1,0 +1,65 @@
+// plan_device.cuh — the device form of a BatchPlan: what compilePlan() (batch_plan.cu) produces and
+// both executors of the staged path consume (the interpreter kernel and the NVRTC generator).
+#pragma once
+#include "column.cuh"
+#include "fused_device.cuh"
+
+namespace aresb {
+
+constexpr int kFusedThreads = 512;
+constexpr int kMaxPlanCols = 16;
+constexpr int kSmemBudget = 220 * 1024;       // of the 227 KB a CTA may opt into
+
+enum KeyMode : uint8_t { KEY_PACKED = 0, KEY_HASHED = 1 };
+enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3 };
+
+struct DevColumn {
+  InputDesc in;            // how to read it straight from global memory (any mode)
+  uint32_t smemValues;     // byte offsets inside one stage (staged path)
+  uint32_t smemNulls;
+  uint32_t tileValueBytes; // bytes of one full tile
+  uint32_t tileNullBytes;
+  uint8_t width;           // bytes per value, 0 for bit-packed bool
+  uint8_t staged;          // values staged
+  uint8_t hasNulls;        // mode 2 bitmap staged
+  uint8_t pad;
+};
+
+struct DevInst {
+  uint32_t aconst, bconst;
+  uint8_t nops, fn, sink, sinkArg;
+  uint8_t akind, acol, aclass, avalid;
+  uint8_t bkind, bcol, bclass, bvalid;
+  uint8_t tclass;   // class the functor runs in
+  uint8_t rclass;   // class of the functor result
+  uint8_t oclass;   // class of the sink element
+  uint8_t wide;     // 1: 8/16-byte column copied verbatim into a dimension
+  uint8_t rowOff, width, nullOff, pad;
+};
+
+struct DevPlan {
+  DevColumn cols[kMaxPlanCols];
+  DevInst insts[ARES_MAX_PLAN_INSTS];
+  const uint32_t *baseCounts;
+  uint32_t startCount;
+  uint32_t numRows;
+  uint32_t tileRows;
+  uint32_t numFullTiles;   // staged tiles; the tail goes through the direct path
+  uint32_t stageBytes;
+  uint32_t smemSlots;      // shared table slots (power of two)
+  uint32_t tailBegin;      // first row of the direct (non-staged) pass
+  int32_t ncols, ninsts, lastFilter;
+  uint64_t measureIdentity;  // NULL measure -> this (sink class bits)
+  uint64_t accNeutral;       // neutral element of the combine op
+  uint8_t keyMode, rowBytes, valueBytes, hashBits;
+  uint8_t aggOp, measWidth, measClass, skipCount;
+  uint8_t hasMeasure, staged, pad0, pad1;
+};
+
+// jit.cu: runs the staged tiles of `P` with a kernel specialised for the plan's shape.  Returns false
+// when NVRTC is unavailable or disabled (ARESDB_B200_JIT=0) so that the caller falls back to the
+// interpreter kernel; throws EngineError when code generation / compilation fails.
+size_t jitCompileOnly(const DevPlan &P, std::string *sourceOut);
+bool jitLaunchStaged(const DevPlan &P, const DevTable &G, size_t smemBytes, int grid, cudaStream_t s);
+
+}  // namespace aresb
