@@ -407,7 +407,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   }
   if (threadIdx.x == 0) {
     *claims = 0;
-    for (int s = 0; s < kStages; s++) mbarInit(&bars[s], 1);
+    for (int s = 0; s < kMaxStages; s++) mbarInit(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -417,14 +417,14 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   if (P.staged && P.numFullTiles > 0) {
     const uint32_t first = blockIdx.x, step = gridDim.x;
     if (threadIdx.x == 0) {
-      for (int s = 0; s < kStages; s++) {
+      for (uint32_t s = 0; s < P.numStages; s++) {
         uint32_t t = first + s * step;
         if (t < P.numFullTiles) issueTile(P, t, stages + (size_t)s * P.stageBytes, &bars[s]);
       }
     }
     uint32_t it = 0;
     for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
-      const uint32_t s = it % kStages, parity = (it / kStages) & 1;
+      const uint32_t s = it % P.numStages, parity = (it / P.numStages) & 1;
       mbarWait(&bars[s], parity);
       const uint8_t *stage = stages + (size_t)s * P.stageBytes;
       // shared-table admission is decided per tile (uniform in the CTA)
@@ -433,7 +433,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
         processQuad<true, WIDEKEY>(P, G, T, useSmem, allowClaim, stage, q, t * P.tileRows + q * R, R);
       __syncthreads();  // everyone is done reading stage s
       if (threadIdx.x == 0) {
-        uint32_t nt = t + kStages * step;
+        uint32_t nt = t + P.numStages * step;
         if (nt < P.numFullTiles) issueTile(P, nt, stages + (size_t)s * P.stageBytes, &bars[s]);
       }
     }
@@ -828,8 +828,10 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
   P.accNeutral = st->accNeutral;
 }
 
-// Decides staged vs direct, the tile size, the stage layout and the shared table size.
-static size_t layoutStages(DevPlan &P) {
+// Decides staged vs direct, the tile size, the stage layout, the TMA ring depth and the shared table
+// size.  The shared table gets what the workload needs first (a table that overflows sends rows to
+// contended L2 atomics, profiles/r01_agg_microbench.txt), the ring takes the rest.
+static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   bool canStage = P.numRows >= 1024;
   uint32_t rowBits = 0;
   for (int c = 0; c < P.ncols; c++) {
@@ -843,22 +845,31 @@ static size_t layoutStages(DevPlan &P) {
     rowBits += col.width ? col.width * 8 : 1;
     if (col.in.mode == 2) rowBits += 1;
   }
-  bool anyStaged = false;
-  uint32_t tileRows = 0;
+  uint32_t slots = 4096;
+  if (expectedGroups) {
+    slots = 1024;
+    while (slots < 2 * expectedGroups && slots < 8192) slots <<= 1;
+  }
+  auto stageBytesFor = [&](uint32_t tr) {
+    size_t stage = 0;
+    for (int c = 0; c < P.ncols; c++) {
+      const DevColumn &col = P.cols[c];
+      if (col.in.mode == 0 || col.width > 4) continue;
+      stage += ((col.width ? (size_t)tr * col.width : tr / 8 + 16) + 15) / 16 * 16;
+      if (col.in.mode == 2) stage += (tr / 8 + 16 + 15) / 16 * 16;
+    }
+    return stage;
+  };
+  uint32_t tileRows = 0, stages = 0;
   if (canStage && rowBits > 0) {
-    // largest tile such that kStages stages leave >= 32 KB for the shared table
     for (uint32_t tr : {4096u, 2048u, 1024u}) {
-      size_t stage = 0;
-      for (int c = 0; c < P.ncols; c++) {
-        const DevColumn &col = P.cols[c];
-        if (col.in.mode == 0 || col.width > 4) continue;
-        stage += ((col.width ? (size_t)tr * col.width : tr / 8 + 16) + 15) / 16 * 16;
-        if (col.in.mode == 2) stage += (tr / 8 + 16 + 15) / 16 * 16;
-      }
-      if (stage * kStages + 32 * 1024 + 128 <= (size_t)kSmemBudget) { tileRows = tr; break; }
+      size_t avail = (size_t)kSmemBudget - 128 - (size_t)slots * 16;
+      uint32_t n = (uint32_t)(avail / stageBytesFor(tr));
+      if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; break; }
     }
   }
   size_t stageBytes = 0;
+  bool anyStaged = false;
   if (tileRows) {
     for (int c = 0; c < P.ncols; c++) {
       DevColumn &col = P.cols[c];
@@ -867,8 +878,7 @@ static size_t layoutStages(DevPlan &P) {
       anyStaged = true;
       col.smemValues = (uint32_t)stageBytes;
       // bit-packed bools and bitmaps copy one 16-byte chunk beyond the tile so that a non-zero
-      // StartingIndex can read across the tile's last byte; the source has the row's own
-      // following bytes there (tiles are full), so the copy stays inside the column.
+      // StartingIndex can read across the tile's last byte; full tiles always have those bytes.
       col.tileValueBytes = col.width ? tileRows * col.width : tileRows / 8 + 16;
       stageBytes += (col.tileValueBytes + 15) / 16 * 16;
       if (col.in.mode == 2) {
@@ -881,16 +891,14 @@ static size_t layoutStages(DevPlan &P) {
   }
   P.staged = anyStaged;
   P.tileRows = anyStaged ? tileRows : 4 * kFusedThreads;
-  // the last full tile must leave >= 16 readable bytes after its bitmaps: keep one tile's worth
-  // of rows (at least 128) for the direct tail.
+  P.numStages = anyStaged ? stages : 0;
+  // keep >= 128 rows for the direct tail so that the last staged tile's 16-byte bitmap over-read
+  // stays inside the column
   P.numFullTiles = anyStaged && P.numRows > 128 ? (P.numRows - 128) / tileRows : 0;
-  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; }
+  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; P.numStages = 0; }
   P.stageBytes = (uint32_t)stageBytes;
-  size_t left = (size_t)kSmemBudget - 128 - stageBytes * kStages;
-  uint32_t slots = 1024;
-  while ((size_t)slots * 2 * 16 <= left && slots < 8192) slots <<= 1;
   P.smemSlots = slots;
-  return 128 + (size_t)slots * 16 + stageBytes * kStages;
+  return 128 + (size_t)slots * 16 + stageBytes * P.numStages;
 }
 
 static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
@@ -899,7 +907,7 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   static thread_local DevPlan P;  // ~3 KB; passed by value as a __grid_constant__ parameter
   compilePlan(st, bp, P);
   P.tailBegin = 0;
-  const size_t smemBytes = layoutStages(P);
+  const size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
   static bool attrSet[64] = {false};
   if (!attrSet[st->device & 63]) {
     ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -1056,7 +1064,7 @@ CGoCallResHandle AresJitDryRun(AggSpec spec, const BatchPlan *plan, char **sourc
     static thread_local DevPlan P;
     compilePlan(&st, *plan, P);
     P.tailBegin = 0;
-    layoutStages(P);
+    layoutStages(P, spec.ExpectedGroups);
     std::string src;
     size_t n = P.staged ? jitCompileOnly(P, &src) : 0;
     if (sourceOut) *sourceOut = strdup(src.c_str());

@@ -7,8 +7,8 @@
 
 namespace aresb {
 
-constexpr int kStages = 4;
-constexpr uint32_t kSmemProbeLimit = 16;
+constexpr int kMaxStages = 4;
+constexpr uint32_t kSmemProbeLimit = 8;
 constexpr uint32_t kGlobalProbeLimit = 8192;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr uint64_t kMix = 0x9E3779B97F4A7C15ull;
@@ -53,8 +53,16 @@ __device__ __forceinline__ void tmaLoad1D(void *dstSmem, const void *srcGlobal, 
 // ---------------------------------------------------------------------------------------
 // global group table
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
-  uint32_t slot = (uint32_t)((key * kMix) >> 29) & G.mask;
+// 64 -> 32 bit key mixer (one 32-bit multiply after folding): table positions only, never group identity
+__device__ __forceinline__ uint32_t mixKey(unsigned long long key) {
+  uint32_t x = (uint32_t)key ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu;
+  x *= 0x9E3779B1u;
+  return x ^ (x >> 15);
+}
+
+static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
+  uint32_t slot = (mixKey(key) >> 3) & G.mask;
+#pragma unroll 1
   for (uint32_t probe = 0; probe < kGlobalProbeLimit; probe++) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&G.keys[slot]);
     if (k == key) return slot;
@@ -119,7 +127,8 @@ __device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, u
 // Returns false when the row has to go to the global table (shared table full around its home).
 __device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
                                            const uint64_t *roww, uint64_t val, bool allowClaim) {
-  uint32_t slot = (uint32_t)((key * kMix) >> 40) & T.mask;
+  uint32_t slot = mixKey(key) & T.mask;
+#pragma unroll 1
   for (uint32_t probe = 0; probe < kSmemProbeLimit; probe++) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
     if (k == kEmptyKey) {

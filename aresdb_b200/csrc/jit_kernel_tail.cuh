@@ -29,7 +29,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   }
   if (threadIdx.x == 0) {
     *claims = 0;
-    for (int s = 0; s < kStages; s++) mbarInit(&bars[s], 1);
+    for (int s = 0; s < JIT_STAGES; s++) mbarInit(&bars[s], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -38,14 +38,14 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   constexpr AggOp op = (AggOp)JIT_AGG_OP;
   const uint32_t first = blockIdx.x, step = gridDim.x;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; s++) {
+    for (int s = 0; s < JIT_STAGES; s++) {
       uint32_t t = first + s * step;
       if (t < P.numFullTiles) jitIssueTile(P, t, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
     }
   }
   uint32_t it = 0;
   for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
-    const uint32_t s = it % kStages, parity = (it / kStages) & 1;
+    const uint32_t s = it % JIT_STAGES, parity = (it / JIT_STAGES) & 1;
     mbarWait(&bars[s], parity);
     const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
     const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
@@ -72,7 +72,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     }
     __syncthreads();
     if (threadIdx.x == 0) {
-      uint32_t nt = t + kStages * step;
+      uint32_t nt = t + JIT_STAGES * step;
       if (nt < P.numFullTiles) jitIssueTile(P, nt, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
     }
   }

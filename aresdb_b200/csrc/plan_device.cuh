@@ -8,7 +8,8 @@ namespace aresb {
 
 constexpr int kFusedThreads = 512;
 constexpr int kMaxPlanCols = 16;
-constexpr int kSmemBudget = 220 * 1024;       // of the 227 KB a CTA may opt into
+constexpr int kSmemBudget = 232448;           // 227 KB: the most dynamic shared memory a CTA may opt into on sm_100
+constexpr int kJitThreads = 1024;
 
 enum KeyMode : uint8_t { KEY_PACKED = 0, KEY_HASHED = 1 };
 enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3 };
@@ -48,6 +49,7 @@ struct DevPlan {
   uint32_t stageBytes;
   uint32_t smemSlots;      // shared table slots (power of two)
   uint32_t tailBegin;      // first row of the direct (non-staged) pass
+  uint32_t numStages;      // depth of the TMA ring (2..kMaxStages)
   int32_t ncols, ninsts, lastFilter;
   uint64_t measureIdentity;  // NULL measure -> this (sink class bits)
   uint64_t accNeutral;       // neutral element of the combine op
