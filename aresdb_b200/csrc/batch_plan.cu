@@ -850,6 +850,10 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
     slots = 1024;
     while (slots < 2 * expectedGroups && slots < 8192) slots <<= 1;
   }
+  if (const char *e = getenv("ARESDB_B200_SMEM_SLOTS")) {  // tuning / experiments
+    uint32_t v = (uint32_t)atoi(e);
+    if (v >= 256 && v <= 8192 && (v & (v - 1)) == 0) slots = v;
+  }
   auto stageBytesFor = [&](uint32_t tr) {
     size_t stage = 0;
     for (int c = 0; c < P.ncols; c++) {

@@ -43,6 +43,9 @@ __device__ __forceinline__ void mbarWait(uint64_t *bar, uint32_t parity) {
       "WAIT_DONE:\n"
       "}\n" ::"r"(smemAddr(bar)), "r"(parity) : "memory");
 }
+__device__ __forceinline__ void mbarArrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
 __device__ __forceinline__ void tmaLoad1D(void *dstSmem, const void *srcGlobal, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                    smemAddr(dstSmem)),
@@ -125,32 +128,35 @@ __device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, u
 }
 
 // Returns false when the row has to go to the global table (shared table full around its home).
+// Common case first: the key already sits in its home slot -> one LDS.64, one compare, one atomic.
 __device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
                                            const uint64_t *roww, uint64_t val, bool allowClaim) {
   uint32_t slot = mixKey(key) & T.mask;
+  unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+  if (k != key) {
+    uint32_t probe = 0;
 #pragma unroll 1
-  for (uint32_t probe = 0; probe < kSmemProbeLimit; probe++) {
-    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
-    if (k == kEmptyKey) {
-      if (!allowClaim) return false;
-      unsigned long long old = atomicCAS(&T.keys[slot], kEmptyKey, key);
-      if (old == kEmptyKey) {
-        atomicAdd(T.claims, 1u);
-        // wide keys: the packed row is recorded in the global table once, by whoever claims first
-        if (roww != nullptr) globalFindOrClaim(G, key, roww);
-        k = key;
-      } else {
+    while (true) {
+      if (k == kEmptyKey) {
+        if (!allowClaim) return false;
+        unsigned long long old = atomicCAS(&T.keys[slot], kEmptyKey, key);
+        if (old == kEmptyKey) {
+          atomicAdd(T.claims, 1u);
+          // wide keys: the packed row is recorded in the global table once, by whoever claims first
+          if (roww != nullptr) globalFindOrClaim(G, key, roww);
+          break;
+        }
         k = old;
+        if (k == key) break;
       }
+      if (++probe >= kSmemProbeLimit) return false;
+      slot = (slot + 1) & T.mask;
+      k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+      if (k == key) break;
     }
-    if (k == key) {
-      smemAtomic(op, &T.acc[slot], val);
-      return true;
-    }
-    slot = (slot + 1) & T.mask;
   }
-  return false;
+  smemAtomic(op, &T.acc[slot], val);
+  return true;
 }
-
 
 }  // namespace aresb

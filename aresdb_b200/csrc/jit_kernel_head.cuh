@@ -10,12 +10,14 @@ namespace aresb {
 constexpr int kJitMaxParts = 32;
 constexpr int kJitMaxConsts = 64;
 constexpr int kJitMaxWide = 8;
+constexpr int kJitMaxMagic = 16;
 
 struct JitParams {
   const uint8_t *partSrc[kJitMaxParts];   // global base address of every staged part
   const uint8_t *wideValues[kJitMaxWide]; // 8/16-byte dimension columns read straight from global
   const uint8_t *wideNulls[kJitMaxWide];
   uint32_t consts[kJitMaxConsts];         // literal operands / mode-0 defaults (raw 32-bit cells)
+  unsigned long long magic[kJitMaxMagic]; // 2^64/d + 1 for literal divisors d > 0 (0: use the generic path)
   unsigned long long measureIdentity;
   unsigned long long accNeutral;
   DevTable G;
@@ -51,6 +53,18 @@ __device__ __forceinline__ uint32_t ldbits(const uint8_t *bits, uint32_t q) {
   const uint32_t bit = 4 * q + START_BIT;
   const uint32_t w = bits[bit >> 3] | ((uint32_t)bits[(bit >> 3) + 1] << 8);
   return (w >> (bit & 7)) & 0xF;
+}
+
+// x mod d for a runtime-constant divisor via one 64-bit multiply and one mul-hi (Lemire's fastmod):
+// M = floor((2^64 - 1) / d) + 1; exact for every 32-bit x and d >= 1.
+__device__ __forceinline__ uint32_t fastModU32(uint32_t x, uint32_t d, unsigned long long M) {
+  return (uint32_t)__umul64hi(M * x, (unsigned long long)d);
+}
+// C-semantics remainder of a signed x by a positive d (sign follows the dividend)
+__device__ __forceinline__ int32_t fastModI32(int32_t x, uint32_t d, unsigned long long M) {
+  const uint32_t ux = x < 0 ? 0u - (uint32_t)x : (uint32_t)x;
+  const uint32_t m = fastModU32(ux, d, M);
+  return x < 0 ? -(int32_t)m : (int32_t)m;
 }
 
 __device__ __forceinline__ bool bitOf(const uint8_t *p, uint32_t bit) { return (p[bit >> 3] >> (bit & 7)) & 1; }

@@ -15,7 +15,8 @@ __device__ __forceinline__ void jitIssueTile(const JitParams &P, uint32_t tile, 
 
 extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const __grid_constant__ JitParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem);        // full[JIT_STAGES]: bytes of a tile have landed
+  uint64_t *empty = bars + kMaxStages;                        // empty[JIT_STAGES]: every warp is done with the stage
   uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);
   unsigned long long *tKeys = reinterpret_cast<unsigned long long *>(smem + 128);
   unsigned long long *tAcc = tKeys + JIT_SMEM_SLOTS;
@@ -29,7 +30,10 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   }
   if (threadIdx.x == 0) {
     *claims = 0;
-    for (int s = 0; s < JIT_STAGES; s++) mbarInit(&bars[s], 1);
+    for (int s = 0; s < JIT_STAGES; s++) {
+      mbarInit(&bars[s], 1);
+      mbarInit(&empty[s], JIT_THREADS / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -46,6 +50,17 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   uint32_t it = 0;
   for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
     const uint32_t s = it % JIT_STAGES, parity = (it / JIT_STAGES) & 1;
+    if (threadIdx.x == 0 && it >= 1) {
+      // refill the stage the previous tile lived in, once every warp has released it; only this
+      // one thread ever waits for the slowest warp, nobody else is held at a CTA barrier
+      const uint32_t ps = (it - 1) % JIT_STAGES;
+      const uint32_t nt = t + (JIT_STAGES - 1) * step;
+      if (nt < P.numFullTiles) {
+        mbarWait(&empty[ps], ((it - 1) / JIT_STAGES) & 1);
+        jitIssueTile(P, nt, stages + (size_t)ps * JIT_STAGE_BYTES, &bars[ps]);
+      }
+    }
+    __syncwarp();
     mbarWait(&bars[s], parity);
     const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
     const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
@@ -70,11 +85,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) globalUpdate(P.G, op, k, roww, meas[r]);
       }
     }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      uint32_t nt = t + JIT_STAGES * step;
-      if (nt < P.numFullTiles) jitIssueTile(P, nt, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
-    }
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
   }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
