@@ -921,15 +921,9 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   int grid = smCount();
   const uint32_t work = P.staged ? P.numFullTiles : (P.numRows + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
   if ((uint32_t)grid > work) grid = work ? (int)work : 1;
-  if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) {
-    // the specialised kernel covered the staged tiles; the interpreter only sees the tail rows
-    const uint32_t done = P.numFullTiles * P.tileRows;
-    if (done >= P.numRows) return;
-    P.staged = 0;
-    P.tailBegin = done;
-    const uint32_t tailWork = (P.numRows - done + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
-    grid = (int)(tailWork < (uint32_t)smCount() ? tailWork : (uint32_t)smCount());
-  }
+  // the specialised kernel covers the staged tiles AND the tail; the interpreter below is the
+  // generic fallback (unaligned / RLE columns, NVRTC unavailable or disabled)
+  if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) return;
   if (st->keyMode == KEY_HASHED) fusedBatchKernel<true><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
   else fusedBatchKernel<false><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
   checkLastError("ExecuteBatchPlan");

@@ -22,6 +22,7 @@ struct JitParams {
   unsigned long long accNeutral;
   DevTable G;
   uint32_t numFullTiles;
+  uint32_t numRows;                       // rows of the batch (tail = numRows - numFullTiles * JIT_TILE_ROWS)
 };
 
 // rows 4q .. 4q+3 of a staged value column of W bytes per value

@@ -88,6 +88,49 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     __syncwarp();
     if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
   }
+  // ---- tail: the rows after the last full tile (< JIT_TILE_ROWS + 128) are copied into stage 0 by
+  // the threads themselves, byte-exact (nothing beyond a column's last byte is touched), and go
+  // through the same rowEval.  One CTA does it; rows past the end are masked dead.
+  if (blockIdx.x == gridDim.x - 1) {
+    uint32_t done = P.numFullTiles * JIT_TILE_ROWS;
+    while (done < P.numRows) {
+      __syncthreads();  // every warp has left the ring / the previous tail tile
+      const uint32_t rows = P.numRows - done < JIT_TILE_ROWS ? P.numRows - done : JIT_TILE_ROWS;
+#pragma unroll
+      for (int p = 0; p < JIT_NUM_PARTS; p++) {
+        // bytes of this part that exist for `rows` rows: values rows*width; bit-packed parts cover
+        // bits [startBit, startBit + rows)
+        const uint32_t per = kPartTileStride[p];                       // bytes per full tile
+        const uint32_t valid = kPartIsBits[p] ? (rows + kPartStartBit[p] + 7) / 8 : (uint32_t)((size_t)per * rows / JIT_TILE_ROWS);
+        const uint8_t *src = P.partSrc[p] + (size_t)(done / JIT_TILE_ROWS) * per;
+        uint8_t *dst = stages + kPartSmemOff[p];
+        for (uint32_t i = threadIdx.x; i < kPartBytes[p]; i += JIT_THREADS) dst[i] = i < valid ? src[i] : (uint8_t)0;
+      }
+      __syncthreads();
+      for (uint32_t q = threadIdx.x; q * 4 < rows; q += JIT_THREADS) {
+        uint64_t key[4][JIT_KW];
+        uint64_t meas[4];
+        uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
+        const uint32_t nvalid = rows - q * 4 < 4 ? rows - q * 4 : 4;
+        alive &= (1u << nvalid) - 1u;
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (!((alive >> r) & 1)) continue;
+          unsigned long long k;
+          const uint64_t *roww = nullptr;
+          if (JIT_KW == 1) {
+            k = key[r][0];
+          } else {
+            uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
+            k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+            roww = key[r];
+          }
+          if (!smemUpdate(T, P.G, op, k, roww, meas[r], true)) globalUpdate(P.G, op, k, roww, meas[r]);
+        }
+      }
+      done += rows;
+    }
+  }
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
