@@ -160,7 +160,7 @@ def gpu_run(args):
     import torch.distributed as dist
     from aresdb_b200 import cabi as A
     from aresdb_b200 import columns, synth
-    from aresdb_b200.executor import Batch, FusedBatchExecutor
+    from aresdb_b200.executor import Batch
     from aresdb_b200.memory import CudaSpace
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -194,43 +194,15 @@ def gpu_run(args):
             host_bufs.append(hb)
     torch.cuda.synchronize()
 
-    ex = FusedBatchExecutor(lib, space, q, expected_groups=1 << 16)
-    merged = FusedBatchExecutor(lib, space, q, expected_groups=1 << 16) if world > 1 else None
-
-    def merge_across_ranks():
-        """All-gather every rank's (dim block, measures) and fold them into `merged` on every rank."""
-        g, out = ex.finalize_into()
-        counts = torch.zeros(world, dtype=torch.int64, device=dev)
-        counts[rank] = g
-        dist.all_reduce(counts)
-        cap = int(counts.max().item())
-        from aresdb_b200.executor import _ResultBuffers, dim_offsets
-        pad = _ResultBuffers(space, q, max(cap, 1))
-        offs_s, nulls_s, widths, _ = dim_offsets(q.num_dims_per_width, out.capacity)
-        offs_d, nulls_d, _, _ = dim_offsets(q.num_dims_per_width, pad.capacity)
-        for p, w in enumerate(widths):
-            space.copy(pad.dims, offs_d[p], out.dims, offs_s[p], w * g)
-            space.copy(pad.dims, nulls_d[p], out.dims, nulls_s[p], g)
-        space.copy(pad.measures, 0, out.measures, 0, q.measure_bytes * g)
-        all_dims = [torch.empty_like(pad.dims.handle) for _ in range(world)]
-        all_meas = [torch.empty_like(pad.measures.handle) for _ in range(world)]
-        dist.all_gather(all_dims, pad.dims.handle)
-        dist.all_gather(all_meas, pad.measures.handle)
-        merged.reset()
-        for r in range(world):
-            n = int(counts[r].item())
-            if n:
-                dv = A.make_dimension_vector(all_dims[r].data_ptr(), None, None, q.num_dims_per_width, pad.capacity)
-                merged.merge(dv, all_meas[r].data_ptr(), n)
-        return merged.finalize_into()
+    from aresdb_b200.sharding import ShardedFusedQuery
+    # ExpectedGroups sizes the CTA-private shared table: a day-batch holds 24 hour buckets x 100 cities
+    ex = ShardedFusedQuery(lib, space, q, expected_groups=4096)
 
     def step_device():
         ex.reset()
         for b in batches:
             ex.process_batch(b)
-        if world > 1:
-            return merge_across_ranks()
-        return ex.finalize_into()
+        return ex.finalize()
 
     # e2e: host (pinned) columns -> H2D on a copy stream, double-buffered against the fused kernel
     copy_stream = torch.cuda.Stream(device=dev)
@@ -263,7 +235,7 @@ def gpu_run(args):
             ex.process_batch(Batch(cols, rows_per_batch))
             free_ev[slot] = torch.cuda.Event()
             free_ev[slot].record(main)
-        g, out = merge_across_ranks() if world > 1 else ex.finalize_into()
+        g, out = ex.finalize()
         dims_h = out.dims.handle[: max(out.dims.nbytes, 1)].cpu()
         meas_h = out.measures.handle[: g * q.measure_bytes].cpu()
         return g, h2d, dims_h.numel() + meas_h.numel()
