@@ -156,6 +156,9 @@ class ClockSampler:
 # the B200 arm
 # ---------------------------------------------------------------------------------------------------
 def gpu_run(args):
+    # keep stdout clean for the single JSON line: libraries (NCCL prints its version) write to fd 1
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from aresdb_b200 import cabi as A
@@ -195,8 +198,7 @@ def gpu_run(args):
     torch.cuda.synchronize()
 
     from aresdb_b200.sharding import ShardedFusedQuery
-    # ExpectedGroups sizes the CTA-private shared table: a day-batch holds 24 hour buckets x 100 cities
-    ex = ShardedFusedQuery(lib, space, q, expected_groups=4096)
+    ex = ShardedFusedQuery(lib, space, q)
 
     def step_device():
         ex.reset()
@@ -325,7 +327,7 @@ def gpu_run(args):
                      "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
         "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
     }
-    print(json.dumps(out))
+    os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -93,7 +93,8 @@ typedef struct {
   int32_t AggFunc;         /* enum AggregateFunction (SUM/MIN/MAX families) */
   int32_t MeasureDataType; /* enum DataType of one measure element: Int32/Uint32/Float32/Int64/Float64 */
   int32_t ReduceMode;      /* enum AresReduceMode */
-  uint32_t ExpectedGroups; /* capacity hint, 0 = default; the table grows when needed */
+  uint32_t ExpectedGroups; /* capacity hint: the group table holds max(2^21, 2 x ExpectedGroups) slots; exceeding it
+                            * is reported as an error by AggStateGroupCount / AggStateFinalize, never silently */
 } AggSpec;
 
 #ifdef __cplusplus
