@@ -395,8 +395,10 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);                       // kStages barriers
   uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);
   unsigned long long *tKeys = reinterpret_cast<unsigned long long *>(smem + 128);
-  unsigned long long *tAcc = tKeys + P.smemSlots;
-  uint8_t *stages = reinterpret_cast<uint8_t *>(tAcc + P.smemSlots);
+  // accumulators of the CTA's table live in an L2-resident private slice of global memory:
+  // fire-and-forget RED instead of shared-memory CAS loops, and 64 KB of shared memory back for the ring
+  unsigned long long *tAcc = P.ctaAcc + (size_t)blockIdx.x * P.smemSlots;
+  uint8_t *stages = reinterpret_cast<uint8_t *>(tKeys + P.smemSlots);
 
   SmemTable T;
   T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = P.smemSlots - 1;
@@ -454,7 +456,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   const AggOp op = (AggOp)P.aggOp;
   for (uint32_t i = threadIdx.x; i < P.smemSlots; i += blockDim.x) {
     unsigned long long k = tKeys[i];
-    if (k != kEmptyKey) globalUpdate(G, op, k, nullptr, tAcc[i]);
+    if (k != kEmptyKey) globalUpdate(G, op, k, nullptr, __ldcg(&tAcc[i]));
   }
 }
 
@@ -574,6 +576,7 @@ struct AggState {
   size_t capacity;
   DevTable table;
   void *mem;               // single allocation behind the table
+  unsigned long long *ctaAcc;  // [kMaxGridCtas][8192] private accumulator slices of the fused kernel's CTAs
 };
 
 static uint64_t neutralOf(AggOp op) {
@@ -602,7 +605,8 @@ static ValClass measureClassOf(int dt) {
 
 static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   const bool rows = st->keyMode == KEY_HASHED;
-  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256;
+  const size_t ctaAccBytes = (size_t)kMaxGridCtas * 8192 * sizeof(unsigned long long);
+  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes;
   void *mem = nullptr;
   CGoCallResHandle h = deviceMalloc(&mem, bytes);
   if (h.pStrErr) { std::string m(h.pStrErr); free((void *)h.pStrErr); throw EngineError(m); }
@@ -613,6 +617,7 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   st->table.keys = reinterpret_cast<unsigned long long *>(p + 256);
   st->table.acc = st->table.keys + cap;
   st->table.rows = rows ? reinterpret_cast<uint64_t *>(st->table.acc + cap) : nullptr;
+  st->ctaAcc = reinterpret_cast<unsigned long long *>(p + 256 + cap * 16 + (rows ? cap * 32 : 0));
   st->table.mask = (uint32_t)(cap - 1);
   ARES_CUDA(cudaMemsetAsync(p, 0, 256, s));
   fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, cap, st->accNeutral);
@@ -867,9 +872,12 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   };
   uint32_t tileRows = 0, stages = 0;
   if (canStage && rowBits > 0) {
+    uint32_t forceTile = 0;
+    if (const char *e = getenv("ARESDB_B200_TILE_ROWS")) forceTile = (uint32_t)atoi(e);  // tuning / experiments
     for (uint32_t sl : {slots, slots / 2, slots / 4}) {
       for (uint32_t tr : {4096u, 2048u, 1024u}) {
-        size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 16;
+        if (forceTile && tr != forceTile) continue;
+        size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8;
         uint32_t n = (uint32_t)(avail / stageBytesFor(tr));
         if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; break; }
       }
@@ -906,7 +914,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; P.numStages = 0; }
   P.stageBytes = (uint32_t)stageBytes;
   P.smemSlots = slots;
-  return 128 + (size_t)slots * 16 + stageBytes * P.numStages;
+  return 128 + (size_t)slots * 8 + stageBytes * P.numStages;
 }
 
 static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
@@ -915,6 +923,7 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   static thread_local DevPlan P;  // ~3 KB; passed by value as a __grid_constant__ parameter
   compilePlan(st, bp, P);
   P.tailBegin = 0;
+  P.ctaAcc = st->ctaAcc;
   const size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
   static bool attrSet[64] = {false};
   if (!attrSet[st->device & 63]) {
@@ -922,7 +931,7 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
     ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attrSet[st->device & 63] = true;
   }
-  int grid = smCount();
+  int grid = smCount() < kMaxGridCtas ? smCount() : kMaxGridCtas;
   const uint32_t work = P.staged ? P.numFullTiles : (P.numRows + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
   if ((uint32_t)grid > work) grid = work ? (int)work : 1;
   // the specialised kernel covers the staged tiles AND the tail; the interpreter below is the

@@ -21,6 +21,7 @@ struct JitParams {
   unsigned long long measureIdentity;
   unsigned long long accNeutral;
   DevTable G;
+  unsigned long long *ctaAcc;             // [grid][JIT_SMEM_SLOTS] accumulator slices in global memory
   uint32_t numFullTiles;
   uint32_t numRows;                       // rows of the batch (tail = numRows - numFullTiles * JIT_TILE_ROWS)
 };

@@ -19,8 +19,10 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   uint64_t *empty = bars + kMaxStages;                        // empty[JIT_STAGES]: every warp is done with the stage
   uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);
   unsigned long long *tKeys = reinterpret_cast<unsigned long long *>(smem + 128);
-  unsigned long long *tAcc = tKeys + JIT_SMEM_SLOTS;
-  uint8_t *stages = reinterpret_cast<uint8_t *>(tAcc + JIT_SMEM_SLOTS);
+  // keys of the CTA's table in shared memory (latency-critical, read-mostly); accumulators in an
+  // L2-resident private slice of global memory, updated with fire-and-forget RED
+  unsigned long long *tAcc = P.ctaAcc + (size_t)blockIdx.x * JIT_SMEM_SLOTS;
+  uint8_t *stages = reinterpret_cast<uint8_t *>(tKeys + JIT_SMEM_SLOTS);
 
   SmemTable T;
   T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = JIT_SMEM_SLOTS - 1;
@@ -134,7 +136,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
-    if (k != kEmptyKey) globalUpdate(P.G, op, k, nullptr, tAcc[i]);
+    if (k != kEmptyKey) globalUpdate(P.G, op, k, nullptr, __ldcg(&tAcc[i]));
   }
 }
 

@@ -10,6 +10,7 @@ constexpr int kFusedThreads = 512;
 constexpr int kMaxPlanCols = 16;
 constexpr int kSmemBudget = 232448;           // 227 KB: the most dynamic shared memory a CTA may opt into on sm_100
 constexpr int kJitThreads = 1024;
+constexpr int kMaxGridCtas = 160;             // persistent grid: one CTA per SM (148 on B200)
 
 enum KeyMode : uint8_t { KEY_PACKED = 0, KEY_HASHED = 1 };
 enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3 };
@@ -42,6 +43,7 @@ struct DevPlan {
   DevColumn cols[kMaxPlanCols];
   DevInst insts[ARES_MAX_PLAN_INSTS];
   const uint32_t *baseCounts;
+  unsigned long long *ctaAcc;   // [grid][smemSlots] accumulator slices (global, L2-resident)
   uint32_t startCount;
   uint32_t numRows;
   uint32_t tileRows;
