@@ -875,7 +875,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
     uint32_t forceTile = 0;
     if (const char *e = getenv("ARESDB_B200_TILE_ROWS")) forceTile = (uint32_t)atoi(e);  // tuning / experiments
     for (uint32_t sl : {slots, slots / 2, slots / 4}) {
-      for (uint32_t tr : {4096u, 2048u, 1024u}) {
+      for (uint32_t tr : {3968u, 1920u, 896u}) {  // 128 rows x (31 | 15 | 7) consumer warps
         if (forceTile && tr != forceTile) continue;
         size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8;
         uint32_t n = (uint32_t)(avail / stageBytesFor(tr));

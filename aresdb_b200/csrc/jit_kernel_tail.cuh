@@ -34,61 +34,58 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     *claims = 0;
     for (int s = 0; s < JIT_STAGES; s++) {
       mbarInit(&bars[s], 1);
-      mbarInit(&empty[s], JIT_THREADS / 32);
+      mbarInit(&empty[s], JIT_THREADS / 32 - 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
 
-  constexpr uint32_t kQuads = JIT_TILE_ROWS / 4;
+  // Warp specialisation: the last warp is the TMA producer (one lane issues the bulk copies as soon
+  // as a stage is released), the other JIT_THREADS/32 - 1 warps consume; a tile holds exactly one quad
+  // per consumer thread (JIT_TILE_ROWS = 128 x consumer warps).  No CTA-wide barrier in the loop.
+  constexpr uint32_t kConsumerThreads = JIT_THREADS - 32;
+  static_assert(JIT_TILE_ROWS == kConsumerThreads * 4, "one quad per consumer thread");
   constexpr AggOp op = (AggOp)JIT_AGG_OP;
   const uint32_t first = blockIdx.x, step = gridDim.x;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < JIT_STAGES; s++) {
-      uint32_t t = first + s * step;
-      if (t < P.numFullTiles) jitIssueTile(P, t, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
-    }
-  }
-  uint32_t it = 0;
-  for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
-    const uint32_t s = it % JIT_STAGES, parity = (it / JIT_STAGES) & 1;
-    if (threadIdx.x == 0 && it >= 1) {
-      // refill the stage the previous tile lived in, once every warp has released it; only this
-      // one thread ever waits for the slowest warp, nobody else is held at a CTA barrier
-      const uint32_t ps = (it - 1) % JIT_STAGES;
-      const uint32_t nt = t + (JIT_STAGES - 1) * step;
-      if (nt < P.numFullTiles) {
-        mbarWait(&empty[ps], ((it - 1) / JIT_STAGES) & 1);
-        jitIssueTile(P, nt, stages + (size_t)ps * JIT_STAGE_BYTES, &bars[ps]);
+  if (threadIdx.x >= kConsumerThreads) {
+    if (threadIdx.x == kConsumerThreads) {
+      uint32_t it = 0;
+      for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
+        const uint32_t s = it % JIT_STAGES;
+        if (it >= JIT_STAGES) mbarWait(&empty[s], ((it / JIT_STAGES) - 1) & 1);
+        jitIssueTile(P, t, stages + (size_t)s * JIT_STAGE_BYTES, &bars[s]);
       }
     }
-    __syncwarp();
-    mbarWait(&bars[s], parity);
-    const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
-    const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
-#pragma unroll 1
-    for (uint32_t q = threadIdx.x; q < kQuads; q += JIT_THREADS) {
-      uint64_t key[4][JIT_KW];
-      uint64_t meas[4];
-      const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
-      if (alive == 0) continue;
+  } else {
+    uint32_t it = 0;
+    for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
+      const uint32_t s = it % JIT_STAGES, parity = (it / JIT_STAGES) & 1;
+      mbarWait(&bars[s], parity);
+      const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
+      const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
+      {
+        const uint32_t q = threadIdx.x;
+        uint64_t key[4][JIT_KW];
+        uint64_t meas[4];
+        const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        if (!((alive >> r) & 1)) continue;
-        unsigned long long k;
-        const uint64_t *roww = nullptr;
-        if (JIT_KW == 1) {
-          k = key[r][0];
-        } else {
-          uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
-          k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
-          roww = key[r];
+        for (int r = 0; r < 4; r++) {
+          if (!((alive >> r) & 1)) continue;
+          unsigned long long k;
+          const uint64_t *roww = nullptr;
+          if (JIT_KW == 1) {
+            k = key[r][0];
+          } else {
+            uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
+            k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+            roww = key[r];
+          }
+          if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) globalUpdate(P.G, op, k, roww, meas[r]);
         }
-        if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) globalUpdate(P.G, op, k, roww, meas[r]);
       }
+      __syncwarp();
+      if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
     }
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
   }
   // ---- tail: the rows after the last full tile (< JIT_TILE_ROWS + 128) are copied into stage 0 by
   // the threads themselves, byte-exact (nothing beyond a column's last byte is touched), and go
