@@ -54,19 +54,25 @@ __device__ __forceinline__ uint32_t ldbits(const uint8_t *bits, uint32_t q) {
   if (START_BIT == 0) return (bits[q >> 1] >> ((q & 1) * 4)) & 0xF;
   const uint32_t bit = 4 * q + START_BIT;
   const uint32_t w = bits[bit >> 3] | ((uint32_t)bits[(bit >> 3) + 1] << 8);
-  return (w >> (bit & 7)) & 0xF;
+  return w >> (bit & 7);  // callers test bits 0..3
 }
 
-// x mod d for a runtime-constant divisor via one 64-bit multiply and one mul-hi (Lemire's fastmod):
-// M = floor((2^64 - 1) / d) + 1; exact for every 32-bit x and d >= 1.
-__device__ __forceinline__ uint32_t fastModU32(uint32_t x, uint32_t d, unsigned long long M) {
-  return (uint32_t)__umul64hi(M * x, (unsigned long long)d);
+// x / d for a runtime-constant divisor as the high word of a 64x32-bit product (Lemire's fastdiv):
+// M = floor((2^64 - 1) / d) + 1; exact for every 32-bit x and d >= 1.  Two IMAD.WIDE.
+__device__ __forceinline__ uint32_t fastDivU32(uint32_t x, unsigned long long M) {
+  const uint32_t carry = __umulhi((uint32_t)M, x);
+  const unsigned long long hi = (unsigned long long)(uint32_t)(M >> 32) * x + carry;
+  return (uint32_t)(hi >> 32);
 }
-// C-semantics remainder of a signed x by a positive d (sign follows the dividend)
-__device__ __forceinline__ int32_t fastModI32(int32_t x, uint32_t d, unsigned long long M) {
-  const uint32_t ux = x < 0 ? 0u - (uint32_t)x : (uint32_t)x;
-  const uint32_t m = fastModU32(ux, d, M);
-  return x < 0 ? -(int32_t)m : (int32_t)m;
+// Quotient / remainder / floor-to-multiple with C semantics (truncation, sign follows the dividend)
+// for a signed or unsigned 32-bit x and a positive literal d.  WHAT: 0 = x / d, 1 = x % d, 2 = x - x % d.
+template <int WHAT, bool SIGNED>
+__device__ __forceinline__ uint32_t fastDivOp(uint32_t x, uint32_t d, unsigned long long M) {
+  const bool neg = SIGNED && (int32_t)x < 0;
+  const uint32_t ux = neg ? 0u - x : x;
+  const uint32_t q = fastDivU32(ux, M);
+  const uint32_t res = WHAT == 0 ? q : WHAT == 1 ? ux - q * d : q * d;
+  return neg ? 0u - res : res;
 }
 
 __device__ __forceinline__ bool bitOf(const uint8_t *p, uint32_t bit) { return (p[bit >> 3] >> (bit & 7)) & 1; }
