@@ -29,6 +29,10 @@
 namespace aresb {
 
 // from sort_reduce.cu
+void gatherDims(const uint8_t *in, const DimLayout &Lin, const uint32_t *rows, int g, uint8_t *out,
+                const DimLayout &Lout, cudaStream_t s);
+int hllRegisterVectors(const uint64_t *hash, const uint32_t *values, uint32_t *index, int R, uint8_t **hllVectorPtr,
+                       size_t *hllVectorSizePtr, uint16_t **hllDimRegIDCountPtr, cudaStream_t s);
 int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *measures, int width, AggOp op, int n,
                  uint32_t *outIndex, uint8_t *outValues, cudaStream_t s, uint64_t *outHash = nullptr);
 
@@ -354,6 +358,7 @@ __device__ __forceinline__ void processQuad(const DevPlan &P, const DevTable &G,
     const uint64_t *roww = nullptr;
     if constexpr (WIDEKEY) {
       key = P.hashBits == 64 ? murmur3_128_lo(kw[r], P.rowBytes, 0) : (unsigned long long)murmur3_32(kw[r], P.rowBytes, 0);
+      if (P.hll) key = (key & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);
       roww = kw[r];
     } else {
       key = kw[r][0];
@@ -465,14 +470,16 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mergeRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint8_t *__restrict__ measures, int width,
-                AggOp op, int n, uint8_t keyMode, uint8_t hashBits, DevTable G) {
+                AggOp op, int n, uint8_t keyMode, uint8_t hashBits, bool hll, DevTable G) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride) {
     uint64_t w[4];
     packRow(block, L, i, w);
     unsigned long long key = keyMode == KEY_PACKED ? w[0]
                            : (hashBits == 64 ? murmur3_128_lo(w, L.rowBytes, 0) : (unsigned long long)murmur3_32(w, L.rowBytes, 0));
-    globalUpdate(G, op, key, keyMode == KEY_HASHED ? w : nullptr, loadMeasure(measures, i, width));
+    const uint64_t v = loadMeasure(measures, i, width);
+    if (hll) key = (key & 0xFFFFFFFFFFFF0000ull) | (v & 0x3FFFu);
+    globalUpdate(G, op, key, keyMode == KEY_HASHED ? w : nullptr, v);
   }
 }
 
@@ -573,6 +580,7 @@ struct AggState {
   int measWidth;
   ValClass measClass;
   uint64_t accNeutral;
+  bool hll;
   size_t capacity;
   DevTable table;
   void *mem;               // single allocation behind the table
@@ -632,9 +640,20 @@ static void describeState(AggState *st, const AggSpec &spec) {
   st->keyMode = st->rowLayout.rowBytes <= 8 ? KEY_PACKED : KEY_HASHED;
   st->measClass = measureClassOf(spec.MeasureDataType);
   int bytes = (st->measClass == VC_I64 || st->measClass == VC_F64) ? 8 : 4;
-  if (spec.AggFunc == AGGR_AVG_FLOAT || spec.AggFunc == AGGR_HLL)
-    throw EngineError("AVG / HLL aggregates are not available on the fused path; use the per-node entry points");
-  st->op = aggOpOf(spec.AggFunc, bytes, &st->measWidth);
+  if (spec.AggFunc == AGGR_AVG_FLOAT)
+    throw EngineError("the AVG aggregate is not available on the fused path; use the per-node entry points");
+  st->hll = spec.AggFunc == AGGR_HLL;
+  if (st->hll) {
+    // group identity = the reference's HLL key (dim-row hash with the register in its low 16 bits,
+    // query/functor.hpp:1299-1305); the table keeps the max value (rho << 16 | reg) per key
+    if (st->measClass != VC_U32) throw EngineError("an HLL measure is Uint32");
+    st->keyMode = KEY_HASHED;
+    st->hashBits = 64;
+    st->op = OP_MAX_U32;
+    st->measWidth = 4;
+  } else {
+    st->op = aggOpOf(spec.AggFunc, bytes, &st->measWidth);
+  }
   st->accNeutral = neutralOf(st->op);
 }
 
@@ -828,6 +847,7 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
   P.aggOp = st->op;
   P.measWidth = (uint8_t)st->measWidth;
   P.measClass = st->measClass;
+  P.hll = st->hll ? 1 : 0;
   const int agg = st->spec.AggFunc;
   P.skipCount = !((agg >= AGGR_SUM_UNSIGNED && agg <= AGGR_SUM_FLOAT) || agg == AGGR_AVG_FLOAT);
   P.measureIdentity = aggIdentity(agg, st->measClass);
@@ -950,7 +970,7 @@ static void mergeRows(AggState *st, const DimensionVector &in, const uint8_t *va
   int blocks = divUp(length, 256);
   if (blocks > smCount() * 8) blocks = smCount() * 8;
   mergeRowsKernel<<<blocks, 256, 0, s>>>(in.DimValues, L, values, st->measWidth, st->op, length, st->keyMode,
-                                        (uint8_t)st->hashBits, st->table);
+                                        (uint8_t)st->hashBits, st->hll, st->table);
   checkLastError("AggStateMerge");
 }
 
@@ -1008,6 +1028,46 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
   return g;
 }
 
+// HLL state -> the reference's final outputs.  AggStateFinalize on such a state already yields the
+// carried form (one row per (group, register) entry, key-ascending, value = max rho << 16 | reg);
+// this runs it into scratch buffers and then the shared register-vector stage of hll.cu.  The dim
+// block (VectorCapacity == number of groups) and the two vectors are allocated with deviceMalloc.
+static int64_t finalizeHLL(AggState *st, uint8_t **dimValuesPtr, uint8_t **hllVectorPtr, size_t *hllVectorSizePtr,
+                           uint16_t **hllDimRegIDCountPtr, cudaStream_t s) {
+  if (!st->hll) throw EngineError("AggStateFinalizeHLL needs a state created with AGGR_HLL");
+  if (!dimValuesPtr || !hllVectorPtr || !hllVectorSizePtr || !hllDimRegIDCountPtr) throw EngineError("null output pointer");
+  *dimValuesPtr = nullptr; *hllVectorPtr = nullptr; *hllVectorSizePtr = 0; *hllDimRegIDCountPtr = nullptr;
+  const int64_t entries = groupCount(st, s);
+  if (entries == 0) return 0;
+  const int n = (int)entries;
+  const int rowBytes = st->rowLayout.rowBytes;
+  Scratch block((size_t)rowBytes * n, s), hash(sizeof(uint64_t) * (size_t)n, s), index(sizeof(uint32_t) * (size_t)n, s);
+  Scratch values(sizeof(uint32_t) * (size_t)n, s);
+  DimensionVector carried;
+  carried.DimValues = block.as<uint8_t>();
+  carried.HashValues = hash.as<uint64_t>();
+  carried.IndexVector = index.as<uint32_t>();
+  carried.VectorCapacity = n;
+  for (int i = 0; i < NUM_DIM_WIDTH; i++) carried.NumDimsPerDimWidth[i] = st->spec.NumDimsPerDimWidth[i];
+  const int64_t g = finalize(st, carried, values.as<uint8_t>(), s);
+  if (g != entries) throw EngineError("HLL state: duplicate keys in the group table");
+  const int dims = hllRegisterVectors(hash.as<uint64_t>(), values.as<uint32_t>(), index.as<uint32_t>(), n, hllVectorPtr,
+                                      hllVectorSizePtr, hllDimRegIDCountPtr, s);
+  void *out = nullptr;
+  CGoCallResHandle h = deviceMalloc(&out, (size_t)rowBytes * dims);
+  if (h.pStrErr) {
+    std::string m(h.pStrErr); free((void *)h.pStrErr);
+    deviceFree(*hllVectorPtr); deviceFree(*hllDimRegIDCountPtr);
+    *hllVectorPtr = nullptr; *hllDimRegIDCountPtr = nullptr;
+    throw EngineError(m);
+  }
+  DimLayout Lin = makeDimLayout(carried.NumDimsPerDimWidth, n), Lout = makeDimLayout(carried.NumDimsPerDimWidth, dims);
+  gatherDims(block.as<uint8_t>(), Lin, index.as<uint32_t>(), dims, static_cast<uint8_t *>(out), Lout, s);
+  ARES_CUDA(cudaStreamSynchronize(s));
+  *dimValuesPtr = static_cast<uint8_t *>(out);
+  return dims;
+}
+
 }  // namespace aresb
 
 using namespace aresb;
@@ -1049,6 +1109,14 @@ CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8
                                   int device) {
   return guarded("AggStateFinalize", device, [&]() -> int64_t {
     return finalize(asState(state), outputKeys, outputValues, (cudaStream_t)cudaStream);
+  });
+}
+
+CGoCallResHandle AggStateFinalizeHLL(void *state, uint8_t **dimValuesPtr, uint8_t **hllVectorPtr, size_t *hllVectorSizePtr,
+                                     uint16_t **hllDimRegIDCountPtr, void *cudaStream, int device) {
+  return guarded("AggStateFinalizeHLL", device, [&]() -> int64_t {
+    return finalizeHLL(asState(state), dimValuesPtr, hllVectorPtr, hllVectorSizePtr, hllDimRegIDCountPtr,
+                       (cudaStream_t)cudaStream);
   });
 }
 

@@ -216,6 +216,50 @@ static void headCountScan(const uint64_t *hash, int n, int shift, uint32_t *out,
   checkLastError("headCountScan");
 }
 
+// Step 4 on merged rows sorted by (key asc, value desc): per-dim register counts, sparse / dense
+// vector offsets and the scatter.  `index[r]` is the dim-row index of entry r; on return
+// index[0..dims) holds the row of each dim's first entry.  Allocates the two outputs with
+// deviceMalloc (the caller adopts them) and returns the number of dims.
+int hllRegisterVectors(const uint64_t *hash, const uint32_t *values, uint32_t *index, int R, uint8_t **hllVectorPtr,
+                       size_t *hllVectorSizePtr, uint16_t **hllDimRegIDCountPtr, cudaStream_t s) {
+  Scratch dimOrd(sizeof(uint32_t) * (size_t)R, s), regCum(sizeof(uint32_t) * (size_t)R, s);
+  headCountScan(hash, R, 16, dimOrd.as<uint32_t>(), s);
+  headCountScan(hash, R, 0, regCum.as<uint32_t>(), s);
+  uint32_t totals[2];
+  ARES_CUDA(cudaMemcpyAsync(&totals[0], dimOrd.as<uint32_t>() + (R - 1), 4, cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaMemcpyAsync(&totals[1], regCum.as<uint32_t>() + (R - 1), 4, cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  const uint32_t dims = totals[0], regs = totals[1];
+  Scratch firstRow(sizeof(uint32_t) * (size_t)dims, s), regBefore(sizeof(uint32_t) * (size_t)dims, s);
+  Scratch offsets(sizeof(unsigned long long) * ((size_t)dims + 1), s);
+  dimHeadsKernel<<<divUp(R, 256), 256, 0, s>>>(dimOrd.as<uint32_t>(), regCum.as<uint32_t>(), index, R,
+                                               firstRow.as<uint32_t>(), regBefore.as<uint32_t>());
+  checkLastError("dimHeads");
+  void *regCountDev = nullptr;
+  CGoCallResHandle h = deviceMalloc(&regCountDev, sizeof(uint16_t) * (size_t)dims);
+  if (h.pStrErr) { std::string msg(h.pStrErr); free((void *)h.pStrErr); throw EngineError(msg); }
+  dimSizesKernel<<<1, 1024, 0, s>>>(regBefore.as<uint32_t>(), dims, regs, static_cast<uint16_t *>(regCountDev),
+                                    offsets.as<unsigned long long>());
+  checkLastError("dimSizes");
+  unsigned long long totalBytes = 0;
+  ARES_CUDA(cudaMemcpyAsync(&totalBytes, offsets.as<unsigned long long>() + dims, 8, cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  void *hllDev = nullptr;
+  h = deviceMalloc(&hllDev, totalBytes ? (size_t)totalBytes : 1);
+  if (h.pStrErr) { std::string msg(h.pStrErr); free((void *)h.pStrErr); deviceFree(regCountDev); throw EngineError(msg); }
+  ARES_CUDA(cudaMemsetAsync(hllDev, 0, (size_t)totalBytes, s));
+  hllScatterKernel<<<divUp(R, 256), 256, 0, s>>>(dimOrd.as<uint32_t>(), regCum.as<uint32_t>(), values, R,
+                                                 regBefore.as<uint32_t>(), static_cast<uint16_t *>(regCountDev),
+                                                 offsets.as<unsigned long long>(), static_cast<uint8_t *>(hllDev));
+  checkLastError("hllScatter");
+  // surviving rows: the first row of every dim, in order
+  ARES_CUDA(cudaMemcpyAsync(index, firstRow.ptr, sizeof(uint32_t) * (size_t)dims, cudaMemcpyDeviceToDevice, s));
+  *hllVectorPtr = static_cast<uint8_t *>(hllDev);
+  *hllVectorSizePtr = (size_t)totalBytes;
+  *hllDimRegIDCountPtr = static_cast<uint16_t *>(regCountDev);
+  return (int)dims;
+}
+
 static int64_t hyperloglog(DimensionVector prev, DimensionVector cur, uint32_t *prevValues, uint32_t *curValues,
                            int prevResultSize, int curBatchSize, bool isLastBatch, uint8_t **hllVectorPtr,
                            size_t *hllVectorSizePtr, uint16_t **hllDimRegIDCountPtr, cudaStream_t s) {
@@ -247,46 +291,9 @@ static int64_t hyperloglog(DimensionVector prev, DimensionVector cur, uint32_t *
                                                    curValues, cur.IndexVector);
     checkLastError("hllMerge");
   }
-  if (isLastBatch && resSize > 0) {
-    // 4. register vectors
-    const int R = resSize;
-    Scratch dimOrd(sizeof(uint32_t) * (size_t)R, s), regCum(sizeof(uint32_t) * (size_t)R, s);
-    headCountScan(cur.HashValues, R, 16, dimOrd.as<uint32_t>(), s);
-    headCountScan(cur.HashValues, R, 0, regCum.as<uint32_t>(), s);
-    uint32_t totals[2];
-    ARES_CUDA(cudaMemcpyAsync(&totals[0], dimOrd.as<uint32_t>() + (R - 1), 4, cudaMemcpyDeviceToHost, s));
-    ARES_CUDA(cudaMemcpyAsync(&totals[1], regCum.as<uint32_t>() + (R - 1), 4, cudaMemcpyDeviceToHost, s));
-    ARES_CUDA(cudaStreamSynchronize(s));
-    const uint32_t dims = totals[0], regs = totals[1];
-    Scratch firstRow(sizeof(uint32_t) * (size_t)dims, s), regBefore(sizeof(uint32_t) * (size_t)dims, s);
-    Scratch offsets(sizeof(unsigned long long) * ((size_t)dims + 1), s);
-    dimHeadsKernel<<<divUp(R, 256), 256, 0, s>>>(dimOrd.as<uint32_t>(), regCum.as<uint32_t>(), cur.IndexVector, R,
-                                                 firstRow.as<uint32_t>(), regBefore.as<uint32_t>());
-    checkLastError("dimHeads");
-    void *regCountDev = nullptr;
-    CGoCallResHandle h = deviceMalloc(&regCountDev, sizeof(uint16_t) * (size_t)dims);
-    if (h.pStrErr) { std::string msg(h.pStrErr); free((void *)h.pStrErr); throw EngineError(msg); }
-    dimSizesKernel<<<1, 1024, 0, s>>>(regBefore.as<uint32_t>(), dims, regs, static_cast<uint16_t *>(regCountDev),
-                                      offsets.as<unsigned long long>());
-    checkLastError("dimSizes");
-    unsigned long long totalBytes = 0;
-    ARES_CUDA(cudaMemcpyAsync(&totalBytes, offsets.as<unsigned long long>() + dims, 8, cudaMemcpyDeviceToHost, s));
-    ARES_CUDA(cudaStreamSynchronize(s));
-    void *hllDev = nullptr;
-    h = deviceMalloc(&hllDev, totalBytes ? (size_t)totalBytes : 1);
-    if (h.pStrErr) { std::string msg(h.pStrErr); free((void *)h.pStrErr); deviceFree(regCountDev); throw EngineError(msg); }
-    ARES_CUDA(cudaMemsetAsync(hllDev, 0, (size_t)totalBytes, s));
-    hllScatterKernel<<<divUp(R, 256), 256, 0, s>>>(dimOrd.as<uint32_t>(), regCum.as<uint32_t>(), curValues, R,
-                                                   regBefore.as<uint32_t>(), static_cast<uint16_t *>(regCountDev),
-                                                   offsets.as<unsigned long long>(), static_cast<uint8_t *>(hllDev));
-    checkLastError("hllScatter");
-    // surviving rows: the first row of every dim, in order
-    ARES_CUDA(cudaMemcpyAsync(cur.IndexVector, firstRow.ptr, sizeof(uint32_t) * (size_t)dims, cudaMemcpyDeviceToDevice, s));
-    *hllVectorPtr = static_cast<uint8_t *>(hllDev);
-    *hllVectorSizePtr = (size_t)totalBytes;
-    *hllDimRegIDCountPtr = static_cast<uint16_t *>(regCountDev);
-    resSize = (int)dims;
-  }
+  if (isLastBatch && resSize > 0)  // 4. register vectors
+    resSize = hllRegisterVectors(cur.HashValues, curValues, cur.IndexVector, resSize, hllVectorPtr, hllVectorSizePtr,
+                                 hllDimRegIDCountPtr, s);
   // 5. dims of the surviving rows (output block uses prev's capacity, query/hll.cu:169-187)
   DimLayout Lc = makeDimLayout(prev.NumDimsPerDimWidth, prev.VectorCapacity);
   gatherDims(prev.DimValues, Lc, cur.IndexVector, resSize, cur.DimValues, Lc, s);

@@ -78,6 +78,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
           } else {
             uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
             k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+            if (JIT_HLL) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
             roww = key[r];
           }
           if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) globalUpdate(P.G, op, k, roww, meas[r]);
@@ -122,6 +123,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
           } else {
             uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
             k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+            if (JIT_HLL) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
             roww = key[r];
           }
           if (!smemUpdate(T, P.G, op, k, roww, meas[r], true)) globalUpdate(P.G, op, k, roww, meas[r]);

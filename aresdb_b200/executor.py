@@ -20,7 +20,7 @@ import numpy as np
 from . import cabi as A
 from . import expr as E
 from .memory import Buf
-from .query import AggQuery, QueryResult
+from .query import AggQuery, HLLResult, QueryResult
 
 
 @dataclass
@@ -68,6 +68,7 @@ class LegacyBatchExecutor:
         self.result_size = 0
         self.out: _ResultBuffers | None = None   # results of the batches processed so far
         self.calls = 0                           # C-ABI calls issued (the reference's kernel-launch proxy)
+        self.hll: HLLResult | None = None        # set by the last batch of an hll query
 
     # -- processExpression (reference query/time_series_aggregate.go:493-593) ----------------------
     def _call(self, name, *args):
@@ -110,7 +111,10 @@ class LegacyBatchExecutor:
                            e.op, stream, dev)
         return A.scratch_input(frame.ptr, 4 * size, dt)
 
-    def process_batch(self, batch: Batch):
+    def process_batch(self, batch: Batch, is_last: bool = False):
+        """One batch through preExec -> filter -> project -> reduce -> postExec.  `is_last` only
+        matters for hll queries (HyperLogLog builds the register vectors on the last batch,
+        reference query/aql_batchexecutor.go:228-233)."""
         q, sp, stream, dev = self.q, self.space, self.space.stream, self.space.device
         bc = batch.base_counts.ptr if batch.base_counts else None
         size = batch.num_rows
@@ -140,6 +144,7 @@ class LegacyBatchExecutor:
         prev = self.result_size
         cap = max(prev + size, 1)
         inb = _ResultBuffers(sp, q, cap)
+        outb = _ResultBuffers(sp, q, cap)
         if prev > 0:
             self._copy_results(self.out, inb, prev)
         offs, nulls, widths, _ = dim_offsets(q.num_dims_per_width, cap)
@@ -162,7 +167,9 @@ class LegacyBatchExecutor:
         def measure_action(fn, inputs):
             if ctx["size"] <= 0:
                 return
-            ov = A.measure_output(inb.measures.at(prev * q.measure_bytes), q.measure_data_type, q.agg_func)
+            # hll: this batch's values go to measureVectorD[1] from row 0 (time_series_aggregate.go:405-408)
+            target = outb.measures.ptr if q.is_hll else inb.measures.at(prev * q.measure_bytes)
+            ov = A.measure_output(target, q.measure_data_type, q.agg_func)
             if len(inputs) == 1:
                 self._call("UnaryTransform", inputs[0], ov, ctx["index"].ptr, ctx["size"], bc, batch.start_count, fn, stream, dev)
             else:
@@ -174,9 +181,16 @@ class LegacyBatchExecutor:
 
         # reduce (aql_batchexecutor.go:219-253)
         length = prev + size
-        outb = _ResultBuffers(sp, q, cap)
         kin, kout = inb.dimension_vector(q), outb.dimension_vector(q)
-        if length > 0:
+        if q.is_hll:
+            self._call("InitIndexVector", inb.index.ptr, 0, prev, stream, dev)
+            self._call("InitIndexVector", outb.index.ptr, prev, prev + size, stream, dev)
+            vec, vec_size, counts = C.c_void_p(), C.c_size_t(), C.c_void_p()
+            self.result_size = self._call("HyperLogLog", kin, kout, inb.measures.ptr, outb.measures.ptr, prev, size,
+                                          bool(is_last), C.byref(vec), C.byref(vec_size), C.byref(counts), stream, dev)
+            if is_last:
+                self.hll = self._adopt_hll(outb, vec.value, vec_size.value, counts.value, self.result_size)
+        elif length > 0:
             if q.reduce_mode == A.ARES_REDUCE_HASH:
                 self.result_size = self._call("HashReduce", kin, inb.measures.ptr, kout, outb.measures.ptr,
                                               q.measure_bytes, length, q.agg_func, stream, dev)
@@ -188,6 +202,30 @@ class LegacyBatchExecutor:
         # postExec: swapResultBufferForNextBatch (aql_processor.go:718-723)
         self.out = outb
 
+    def _adopt_hll(self, outb: _ResultBuffers, vec: int, vec_size: int, counts: int, num_dims: int):
+        """Copies the two library-allocated outputs to the host and frees them (the Go side adopts
+        them as devicePointers, reference query/time_series_aggregate.go:661-681)."""
+        lib, sp = self.lib, self.space
+        if num_dims <= 0 or not vec:
+            return HLLResult(self.q, 0, np.zeros(0, np.uint8), 1, np.zeros(0, np.uint8), np.zeros(0, np.uint16))
+
+        def read(ptr, nbytes):
+            if not sp.is_cuda:
+                return np.frombuffer(C.string_at(ptr, nbytes), dtype=np.uint8).copy()
+            host = np.zeros(max(nbytes, 1), np.uint8)
+            lib.AsyncCopyDeviceToHost(host.ctypes.data, ptr, nbytes, sp.stream, sp.device)
+            lib.WaitForCudaStream(sp.stream, sp.device)
+            return host[:nbytes]
+
+        regs = read(vec, vec_size)
+        cnt = read(counts, 2 * num_dims).view(np.uint16).copy()
+        for p in (vec, counts):
+            if sp.is_cuda:
+                lib.DeviceFree(p, sp.device)
+            else:
+                C.CDLL(None).free(C.c_void_p(p))
+        return HLLResult(self.q, num_dims, outb.dims.get(np.uint8), outb.capacity, regs, cnt)
+
     def _copy_results(self, src: _ResultBuffers, dst: _ResultBuffers, rows: int):
         q, sp = self.q, self.space
         so, sn, widths, _ = dim_offsets(q.num_dims_per_width, src.capacity)
@@ -196,6 +234,8 @@ class LegacyBatchExecutor:
             sp.copy(dst.dims, do[p], src.dims, so[p], w * rows)
             sp.copy(dst.dims, dn[p], src.dims, sn[p], rows)
         sp.copy(dst.measures, 0, src.measures, 0, q.measure_bytes * rows)
+        if q.is_hll:  # the carried keys travel with the rows (aql_processor.go:763-768)
+            sp.copy(dst.hash, 0, src.hash, 0, 8 * rows)
 
     def result(self) -> QueryResult:
         if self.out is None or self.result_size == 0:
@@ -250,6 +290,27 @@ class FusedBatchExecutor:
         if g == 0:
             return QueryResult(self.q, np.zeros(0, np.uint8), 1, np.zeros(0, np.uint8), 0)
         return QueryResult(self.q, out.dims.get(np.uint8), out.capacity, out.measures.get(np.uint8), g)
+
+    def hll_result(self) -> HLLResult:
+        """hll queries: the register vectors of every dimension group (AggStateFinalizeHLL)."""
+        lib, sp = self.lib, self.space
+        dims, vec, counts, size = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_size_t()
+        g = lib.AggStateFinalizeHLL(self.state, C.byref(dims), C.byref(vec), C.byref(size), C.byref(counts), sp.stream, sp.device)
+        if g == 0:
+            return HLLResult(self.q, 0, np.zeros(0, np.uint8), 1, np.zeros(0, np.uint8), np.zeros(0, np.uint16))
+
+        def read(ptr, nbytes):
+            host = np.zeros(max(nbytes, 1), np.uint8)
+            lib.AsyncCopyDeviceToHost(host.ctypes.data, ptr, nbytes, sp.stream, sp.device)
+            lib.WaitForCudaStream(sp.stream, sp.device)
+            return host[:nbytes]
+
+        block = read(dims.value, self.q.row_bytes * g)
+        regs = read(vec.value, size.value)
+        cnt = read(counts.value, 2 * g).view(np.uint16).copy()
+        for p in (dims, vec, counts):
+            lib.DeviceFree(p, sp.device)
+        return HLLResult(self.q, g, block, g, regs, cnt)
 
     def reset(self):
         self.lib.AggStateReset(self.state, self.space.stream, self.space.device)

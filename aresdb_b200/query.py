@@ -18,7 +18,7 @@ from . import expr as E
 
 @dataclass
 class Measure:
-    kind: str                 # "count" | "sum" | "min" | "max"
+    kind: str                 # "count" | "sum" | "min" | "max" | "hll" | "countdistincthll"
     expr: E.Expr | None = None
 
 
@@ -40,6 +40,16 @@ class AggQuery:
         if measure.kind == "count":
             self.measure = E.Lit(1, E.Type.Unsigned)
             self.agg_func, self.measure_bytes = A.AGGR_SUM_UNSIGNED, 4
+        elif measure.kind in ("hll", "countdistincthll"):
+            # hll(col): col already holds rho << 16 | reg; countdistincthll(col) computes it on the fly
+            # (reference query/context/query_context_helper.go:540-575, aql_compiler.go:1243)
+            col = E.resolve(measure.expr)
+            if not isinstance(col, E.Col):
+                raise ValueError(f"expect 1 argument to be a column for {measure.kind}")
+            if measure.kind == "hll" and col.data_type != A.Uint32:
+                raise ValueError("expect 1 argument to be a valid hll column")
+            self.measure = col if measure.kind == "hll" else E.resolve(E.Unary(A.GetHLLValue, col))
+            self.agg_func, self.measure_bytes = A.AGGR_HLL, 4
         else:
             self.measure = E.resolve(measure.expr)
             t = self.measure.type
@@ -50,7 +60,12 @@ class AggQuery:
                 raise ValueError(f"unsupported input type for {measure.kind}")
             self.agg_func = fam[{E.Type.Unsigned: 0, E.Type.Signed: 1, E.Type.Float: 2}[t]]
             self.measure_bytes = 8 if measure.kind == "sum" else 4
-        self.measure_data_type = self._output_data_type(self.measure.type, self.measure_bytes)
+        self.measure_data_type = A.Uint32 if self.agg_func == A.AGGR_HLL else \
+            self._output_data_type(self.measure.type, self.measure_bytes)
+
+    @property
+    def is_hll(self) -> bool:
+        return self.agg_func == A.AGGR_HLL
 
     @staticmethod
     def _output_data_type(t: E.Type, width: int) -> int:
@@ -164,4 +179,40 @@ class QueryResult:
             else:
                 col = vals.reshape(-1).view(npdt).tolist()
             out.append([c if v else None for c, v in zip(col, self.dim_valid[qi])])
+        return out
+
+
+HLL_REGISTERS = 1 << 14          # p = 14 (reference query/common/hll.go:786)
+HLL_DENSE_THRESHOLD = HLL_REGISTERS // 4
+
+
+class HLLResult:
+    """Output of an hll query: one register set per dimension group.
+
+    `regs` is the library's register vector: for every group, in output order, either
+    `count` 4-byte little-endian entries `(rho+1) << 16 | reg` (count < 4096) or 16384 bytes of
+    `rho+1` per register (reference query/functor.hpp:1351-1374); `counts[g]` = number of non-zero
+    registers of group g.  `block` is the DimensionVector block holding the groups' dim rows."""
+
+    def __init__(self, query: AggQuery, groups: int, block: np.ndarray, capacity: int, regs: np.ndarray,
+                 counts: np.ndarray):
+        self.query, self.groups, self.regs, self.counts = query, groups, regs, counts
+        self.dims = QueryResult(query, block, capacity, np.zeros(groups * query.measure_bytes, np.uint8), groups)
+
+    def dense_registers(self) -> dict:
+        """packed dim row (bytes) -> uint8[16384] of rho+1 (0 = register never hit)."""
+        out, pos = {}, 0
+        for g in range(self.groups):
+            c = int(self.counts[g])
+            dense = np.zeros(HLL_REGISTERS, np.uint8)
+            if c < HLL_DENSE_THRESHOLD:
+                e = self.regs[pos:pos + 4 * c].view(np.uint32)
+                dense[e & 0xFFFF] = (e >> 16).astype(np.uint8)
+                pos += 4 * c
+            else:
+                dense[:] = self.regs[pos:pos + HLL_REGISTERS]
+                pos += HLL_REGISTERS
+            out[self.dims.rows[g]] = dense
+        if pos != self.regs.size:
+            raise ValueError("register vector size does not match the per-group counts")
         return out

@@ -51,10 +51,10 @@ class ShardedFusedQuery:
     def process_batch(self, batch, stream=None):
         self.local.process_batch(batch, stream)
 
-    def finalize(self):
-        """(groups, result buffers) of the WHOLE query, identical on every rank."""
-        if self.world == 1:
-            return self.local.finalize_into()
+    def _exchange(self):
+        """All-gathers every rank's finalized rows and folds them into `self.merged`; returns the
+        total number of rows gathered (an upper bound of the merged group count).  For hll queries
+        the rows are the carried (group, register) entries."""
         import torch
         q, sp, dist = self.q, self.space, self.dist
         g, out = self.local.finalize_into()
@@ -73,7 +73,20 @@ class ShardedFusedQuery:
             if n:
                 dv = A.make_dimension_vector(all_dims[r].data_ptr(), None, None, q.num_dims_per_width, pad.capacity)
                 self.merged.merge(dv, all_meas[r].data_ptr(), n)
-        return self.merged.finalize_into(int(counts.sum().item()))
+        return int(counts.sum().item())
+
+    def finalize(self):
+        """(groups, result buffers) of the WHOLE query, identical on every rank."""
+        if self.world == 1:
+            return self.local.finalize_into()
+        return self.merged.finalize_into(self._exchange())
+
+    def finalize_hll(self):
+        """hll queries: the HLLResult of the WHOLE query, identical on every rank."""
+        if self.world == 1:
+            return self.local.hll_result()
+        self._exchange()
+        return self.merged.hll_result()
 
     def close(self):
         self.local.close()

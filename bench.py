@@ -27,20 +27,87 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
-WORKLOAD = ("cfg3: 1e9-row fact table as 8 day-batches; filters status==1, fare>5.0, city_id!=0, "
-            "request_at in [t0+1800, t0+8d-1800); dims floor(request_at,3600) x city_id; SUM(fare) in f64")
 NUM_BATCHES = 8
-ALGO_BYTES_PER_ROW = 4 + 2 + 1 + 4 + 4 / 8.0  # request_at + city_id + status + fare + 4 null bitmaps (11.5)
 
 
-def build_query():
+def _columns():
+    from aresdb_b200 import expr as E, synth
+    return tuple(E.Col(i, t, n) for i, (t, n) in enumerate(zip(synth.COLUMN_TYPES, synth.COLUMN_NAMES)))
+
+
+def _q_cfg3():
     from aresdb_b200 import expr as E, synth
     from aresdb_b200.query import AggQuery, Measure
-    TS, CITY, STATUS, FARE = (E.Col(i, t, n) for i, (t, n) in enumerate(zip(synth.COLUMN_TYPES, synth.COLUMN_NAMES)))
+    TS, CITY, STATUS, FARE = _columns()
     t0 = synth.BASE_TS
     return AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0)), E.ne(CITY, E.Lit(0)),
                      E.ge(TS, E.Lit(t0 + 1800)), E.lt(TS, E.Lit(t0 + NUM_BATCHES * 86400 - 1800))],
                     [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE))
+
+
+def _q_cfg3_count():
+    from aresdb_b200 import expr as E
+    from aresdb_b200.query import AggQuery, Measure
+    TS, CITY, STATUS, FARE = _columns()
+    return AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0)), E.ne(CITY, E.Lit(0))],
+                    [E.floor(TS, E.Lit(3600)), CITY], Measure("count"))
+
+
+def _q_cfg2():
+    from aresdb_b200 import expr as E
+    from aresdb_b200.query import AggQuery, Measure
+    TS, CITY, STATUS, FARE = _columns()
+    return AggQuery([E.eq(STATUS, E.Lit(1))], [CITY], Measure("sum", FARE))
+
+
+def _q_cfg4():
+    from aresdb_b200 import cabi as A, expr as E
+    from aresdb_b200.query import AggQuery, Measure
+    TS, CITY, STATUS, FARE = _columns()
+    return AggQuery([], [CITY, E.floor(TS, E.Lit(60))], Measure("sum", FARE), reduce_mode=A.ARES_REDUCE_HASH)
+
+
+def _q_cfg4_hll():
+    from aresdb_b200 import expr as E
+    from aresdb_b200.query import AggQuery, Measure
+    TS, CITY, STATUS, FARE = _columns()
+    return AggQuery([E.eq(STATUS, E.Lit(1))], [E.floor(TS, E.Lit(86400)), CITY], Measure("countdistincthll", TS))
+
+
+# name -> description, query, algorithmic bytes per row (value widths of the referenced
+# columns + 1 bit per referenced null bitmap), default rows, batches, group-table hint, arithmetic
+WORKLOADS = {
+    "cfg3": dict(desc="cfg3: 1e9-row fact table as 8 day-batches; filters status==1, fare>5.0, city_id!=0, "
+                      "request_at in [t0+1800, t0+8d-1800); dims floor(request_at,3600) x city_id; SUM(fare) in f64",
+                 query=_q_cfg3, bytes_per_row=4 + 2 + 1 + 4 + 4 / 8.0, rows=1_000_000_000, batches=8, expected_groups=0,
+                 dtype="u32/u16/u8 filters, f32->f64 sum", metric="rows/s, 1e9-row time-bucketed SUM group-by (cfg3)"),
+    "cfg3_count": dict(desc="cfg3 count(*) variant: filters status==1, fare>5.0, city_id!=0; dims floor(request_at,3600) x "
+                            "city_id; COUNT in u32", query=_q_cfg3_count, bytes_per_row=4 + 2 + 1 + 4 + 4 / 8.0,
+                       rows=1_000_000_000, batches=8, expected_groups=0, dtype="u32 count",
+                       metric="rows/s, 1e9-row time-bucketed COUNT group-by (cfg3)"),
+    "cfg2": dict(desc="cfg2: 1e8-row fact table, one batch; filter status==1; dim city_id; SUM(fare) in f64",
+                 query=_q_cfg2, bytes_per_row=1 + 2 + 4 + 3 / 8.0, rows=100_000_000, batches=1, expected_groups=0,
+                 dtype="u8 filter, f32->f64 sum", metric="rows/s, 1e8-row SUM group-by 1 dim (cfg2)"),
+    "cfg4": dict(desc="cfg4: 1e9 rows as 8 day-batches, no filter; dims city_id x floor(request_at,60) (1.15e6 groups); "
+                      "SUM(fare) in f64, hash-reduce semantics", query=_q_cfg4, bytes_per_row=4 + 2 + 4 + 3 / 8.0,
+                 rows=1_000_000_000, batches=8, expected_groups=1_300_000, dtype="f32->f64 sum, 32-bit hash identity",
+                 metric="rows/s, 1e9-row high-cardinality SUM group-by (cfg4)"),
+    "cfg4_hll": dict(desc="cfg4 HLL: 1e9 rows as 8 day-batches; filter status==1; dims floor(request_at,86400) x city_id "
+                          "(800 groups); countdistincthll(request_at), p=14 registers",
+                     query=_q_cfg4_hll, bytes_per_row=4 + 2 + 1 + 3 / 8.0, rows=1_000_000_000, batches=8,
+                     expected_groups=14_000_000, dtype="u32 murmur3 -> rho/register max",
+                     metric="rows/s, 1e9-row HLL distinct-count group-by (cfg4)"),
+}
+WL = WORKLOADS["cfg3"]
+
+
+def select_workload(name: str):
+    global WL
+    WL = WORKLOADS[name]
+
+
+def build_query():
+    return WL["query"]()
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -48,7 +115,8 @@ def build_query():
 # ---------------------------------------------------------------------------------------------------
 def _cpu_worker(args):
     """One worker process = one table shard slice: runs the reference call sequence over its rows."""
-    kind, day, rows, reps = args
+    kind, day, rows, reps, wl_name = args
+    select_workload(wl_name)
     sys.path.insert(0, str(ROOT))
     from aresdb_b200 import cabi, columns, synth
     from aresdb_b200.executor import Batch, LegacyBatchExecutor
@@ -59,13 +127,17 @@ def _cpu_worker(args):
     else:
         lib = cabi.Library(ROOT / "oracle" / "build" / "liboracle.so", None, has_plan_api=False, name="oracle")
     sp = HostSpace()
-    hb = synth.generate_batch(day % NUM_BATCHES, rows, seed=777 + day)
+    hb = synth.generate_batch(day % WL["batches"], rows, seed=777 + day)
     cols, keep = [], []
     for dt, v, ok in zip(synth.COLUMN_TYPES, hb.values, hb.valid):
         buf, vp = columns.make_column(sp, dt, v, valid=ok)
         cols.append(vp)
         keep.append(buf)
     q = build_query()
+    if wl_name == "cfg4":
+        # the HOST HashReduce extracts its result in O(g^2) (std::next over the map per slot,
+        # reference query/hash_reduction.cu:143-156): time the same grouping through Sort + Reduce
+        q.reduce_mode = cabi.ARES_REDUCE_SORT
     devnull = os.open(os.devnull, os.O_WRONLY)
     saved = os.dup(1)
     os.dup2(devnull, 1)  # the reference's HOST build prints a line per call (utils.cu:41-57)
@@ -74,7 +146,7 @@ def _cpu_worker(args):
         for _ in range(reps):
             t = time.perf_counter()
             ex = LegacyBatchExecutor(lib, sp, q)
-            ex.process_batch(Batch(cols, rows))
+            ex.process_batch(Batch(cols, rows), is_last=True)
             groups = ex.result_size
             times.append(time.perf_counter() - t)
     finally:
@@ -83,7 +155,7 @@ def _cpu_worker(args):
     return times, groups
 
 
-def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: int | None = None):
+def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: int | None = None, wl_name: str = "cfg3"):
     """Times the reference CPU path: `workers` processes, each running the reference's
     single-threaded batch executor over its own slice (the reference's unit of parallelism is the
     table shard / batch).  A step = every worker processing its slice once, concurrently."""
@@ -98,7 +170,7 @@ def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: in
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
         t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(kind, d, rows_per_worker, steps + warmup) for d in range(workers)])
+        res = pool.map(_cpu_worker, [(kind, d, rows_per_worker, steps + warmup, wl_name) for d in range(workers)])
         wall = time.perf_counter() - t0
     # per step, the job time is the slowest worker (they run concurrently)
     per_step = [max(r[0][i] for r in res) for i in range(warmup, warmup + steps)]
@@ -106,7 +178,7 @@ def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: in
     sample_rows = rows_per_worker * workers
     return {"value": sample_rows / (ms / 1e3), "ms_per_step": ms, "kind": kind, "cores": workers,
             "host_cores": cores, "sample": f"{workers} concurrent single-threaded workers x {rows_per_worker} rows of the "
-                                          f"cfg3 query per step (reference HOST path is single-threaded per batch)",
+                                          f"{wl_name} query per step (reference HOST path is single-threaded per batch)",
             "groups": int(res[0][1]), "wall_s": wall}
 
 
@@ -177,9 +249,11 @@ def gpu_run(args):
     stream = torch.cuda.current_stream().cuda_stream
     space = CudaSpace(local, stream)
     q = build_query()
-    rows_total = args.rows
-    rows_per_batch = rows_total // NUM_BATCHES
-    my_days = [d for d in range(NUM_BATCHES) if d % world == rank]
+    num_batches = WL["batches"]
+    rows_total = args.rows or WL["rows"]
+    rows_per_batch = rows_total // num_batches
+    my_days = [d for d in range(num_batches) if d % world == rank]
+    is_hll = q.is_hll
 
     # ---- data: generated on the GPU, mirrored into pinned host memory for the e2e leg -------------
     dev_bufs, batches, host_bufs = [], [], []
@@ -198,13 +272,22 @@ def gpu_run(args):
     torch.cuda.synchronize()
 
     from aresdb_b200.sharding import ShardedFusedQuery
-    ex = ShardedFusedQuery(lib, space, q)
+    ex = ShardedFusedQuery(lib, space, q, expected_groups=WL["expected_groups"],
+                           merged_groups=max(WL["expected_groups"], 1 << 16))
+
+    def finish():
+        """(groups, d2h bytes): the query result lands in host memory."""
+        if is_hll:
+            r = ex.finalize_hll()
+            return r.groups, int(r.regs.size + r.counts.size * 2 + r.groups * q.row_bytes)
+        g, out = ex.finalize()
+        return g, out
 
     def step_device():
         ex.reset()
         for b in batches:
             ex.process_batch(b)
-        return ex.finalize()
+        return finish()
 
     # e2e: host (pinned) columns -> H2D on a copy stream, double-buffered against the fused kernel
     copy_stream = torch.cuda.Stream(device=dev)
@@ -237,7 +320,9 @@ def gpu_run(args):
             ex.process_batch(Batch(cols, rows_per_batch))
             free_ev[slot] = torch.cuda.Event()
             free_ev[slot].record(main)
-        g, out = ex.finalize()
+        g, out = finish()
+        if is_hll:
+            return g, h2d, out
         dims_h = out.dims.handle[: max(out.dims.nbytes, 1)].cpu()
         meas_h = out.measures.handle[: g * q.measure_bytes].cpu()
         return g, h2d, dims_h.numel() + meas_h.numel()
@@ -305,23 +390,23 @@ def gpu_run(args):
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    algo_bytes = ALGO_BYTES_PER_ROW * rows_per_batch
+    algo_bytes = WL["bytes_per_row"] * rows_per_batch
     achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_reference_run(steps=2, warmup=1, rows_per_worker=args.cpu_rows)
+        cpu = cpu_reference_run(steps=2, warmup=1, rows_per_worker=args.cpu_rows, wl_name=args.workload)
         cpu = {k: cpu[k] for k in ("value", "kind", "cores", "host_cores", "sample")}
         cpu["unit"] = "rows/s"
     out = {
-        "metric": "rows/s, 1e9-row time-bucketed SUM group-by (cfg3)", "value": rows_total / (ms / 1e3), "unit": "rows/s",
+        "metric": WL["metric"], "value": rows_total / (ms / 1e3), "unit": "rows/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "p50_query_ms": ms,
-        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32/u16/u8 filters, f32->f64 sum",
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": WL["dtype"],
         "data": "synthetic", "groups": int(groups),
-        "config": {"workload": WORKLOAD, "rows": rows_total, "batches": NUM_BATCHES, "rows_per_batch": rows_per_batch,
+        "config": {"workload": WL["desc"], "rows": rows_total, "batches": num_batches, "rows_per_batch": rows_per_batch,
                    "parallelism": f"batches round-robin over {world} GPU(s), NCCL all-gather merge" if world > 1 else "1 GPU",
-                   "l2": "inputs (1.44 GB per batch) larger than L2; no flush needed"},
+                   "l2": f"inputs ({algo_bytes / 1e9:.2f} GB per batch) larger than the 126 MB L2; no flush needed"},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "fusedBatchKernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "roofline": {"bound": "hbm", "kernel": "aresFusedJit (NVRTC-specialised fused scan-filter-aggregate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None, "traffic": None,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
@@ -336,11 +421,11 @@ def reference_run(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    r = cpu_reference_run(args.steps, args.warmup, rows_per_worker=args.cpu_rows)
-    out = {"impl": "reference", "metric": "rows/s, 1e9-row time-bucketed SUM group-by (cfg3)", "value": r["value"],
+    r = cpu_reference_run(args.steps, args.warmup, rows_per_worker=args.cpu_rows, wl_name=args.workload)
+    out = {"impl": "reference", "metric": WL["metric"], "value": r["value"],
            "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
-           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32/u16/u8 filters, f32->f64 sum",
-           "data": "synthetic", "config": {"workload": WORKLOAD, "rows": r["cores"] * args.cpu_rows,
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": WL["dtype"],
+           "data": "synthetic", "config": {"workload": WL["desc"], "rows": r["cores"] * args.cpu_rows,
                                            "note": "bounded sample of the workload; CPU throughput is size-independent"},
            "cpu_baseline": {"value": r["value"], "unit": "rows/s", "kind": r["kind"], "cores": r["cores"],
                             "host_cores": r["host_cores"], "sample": r["sample"]},
@@ -355,11 +440,14 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--rows", type=int, default=1_000_000_000)
+    ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
+                    help="cfg3 (default) is the headline; the others are the remaining BASELINE configs")
+    ap.add_argument("--rows", type=int, default=0, help="override the workload's table size")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows per CPU worker per step (baseline sample)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
+    select_workload(args.workload)
     if args.impl == "reference":
         reference_run(args)
     else:

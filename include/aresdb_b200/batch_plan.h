@@ -90,7 +90,9 @@ enum AresReduceMode {
 typedef struct {
   uint8_t NumDimsPerDimWidth[NUM_DIM_WIDTH]; /* as DimensionVector */
   uint8_t Reserved[3];
-  int32_t AggFunc;         /* enum AggregateFunction (SUM/MIN/MAX families) */
+  int32_t AggFunc;         /* enum AggregateFunction: SUM/MIN/MAX families, or AGGR_HLL (measure = Uint32
+                            * rho << 16 | reg values; group identity and results as HyperLogLog's,
+                            * query/hll.cu:21-290; read the result with AggStateFinalizeHLL) */
   int32_t MeasureDataType; /* enum DataType of one measure element: Int32/Uint32/Float32/Int64/Float64 */
   int32_t ReduceMode;      /* enum AresReduceMode */
   uint32_t ExpectedGroups; /* capacity hint: the group table holds max(2^21, 2 x ExpectedGroups) slots; exceeding it
@@ -122,6 +124,18 @@ CGoCallResHandle AggStateGroupCount(void *state, void *cudaStream, int device);
  * Synchronises cudaStream.  The state stays valid (it can be finalized again or reset). */
 CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8_t *outputValues,
                                   void *cudaStream, int device);
+
+/* AGGR_HLL states: the final outputs of the reference's last-batch HyperLogLog call
+ * (query/hll.cu:262-290, adopted by query/time_series_aggregate.go:661-681).  res = number of dimension
+ * groups g.  *dimValuesPtr = a DimensionVector block of VectorCapacity g (groups in key order),
+ * *hllDimRegIDCountPtr = g register counts, *hllVectorPtr / *hllVectorSizePtr = per group either
+ * count x 4 bytes ((rho+1) << 16 | reg, count < 4096) or 16384 dense bytes.  All three are allocated
+ * with deviceMalloc; the caller frees them with DeviceFree.  On such a state AggStateGroupCount
+ * counts (group, register) entries and AggStateFinalize / AggStateMerge exchange the carried form
+ * (one row per entry, Uint32 value) — which is how several GPUs combine HLL states.  Synchronises. */
+CGoCallResHandle AggStateFinalizeHLL(void *state, uint8_t **dimValuesPtr, uint8_t **hllVectorPtr,
+                                     size_t *hllVectorSizePtr, uint16_t **hllDimRegIDCountPtr,
+                                     void *cudaStream, int device);
 
 /* Empties the table, keeping its memory. */
 CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device);

@@ -46,3 +46,13 @@ def test_literals_are_runtime_parameters():
     q1 = AggQuery([E.ge(T.TS, E.Lit(1000)), E.gt(T.FARE, E.Lit(5.0))], [T.CITY], Measure("count"))
     q2 = AggQuery([E.ge(T.TS, E.Lit(2000)), E.gt(T.FARE, E.Lit(7.5))], [T.CITY], Measure("count"))
     assert _dry_run(lib, q1)[1] == _dry_run(lib, q2)[1]
+
+
+def test_hll_queries_specialise_with_the_reference_key():
+    """AGGR_HLL plans compile too; the kernel keys its table by (dim-row hash & ~0xFFFF) | register."""
+    import test_hll_pipeline as HP
+    lib = A.load_engine()
+    for name, q in HP.hll_queries().items():
+        size, src = _dry_run(lib, q)
+        assert size > 0, name
+        assert "#define JIT_HLL 1" in src and "#define JIT_KW 4" in src
