@@ -327,6 +327,7 @@ _PLAN_SIGS = {
     "AggStateMerge": [_VP, DimensionVector, _VP, C.c_int, _VP, C.c_int],
     "AggStateGroupCount": [_VP, _VP, C.c_int],
     "AggStateFinalize": [_VP, DimensionVector, _VP, _VP, C.c_int],
+    "AggStateExport": [_VP, DimensionVector, _VP, _VP, C.c_int],
     "AggStateFinalizeHLL": [_VP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_void_p),
                             _VP, C.c_int],
     "AggStateReset": [_VP, _VP, C.c_int],

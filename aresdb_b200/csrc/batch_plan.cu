@@ -874,8 +874,10 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   // The shared table takes 8192 slots (128 KB) whenever a ring of >= 2 stages still fits beside
   // it: measured on cfg3 (2,400 groups per batch) 8192 slots beat 4096 by 1.5x because fewer
   // probe iterations are paid per warp; a plan with very wide rows falls back to fewer slots.
-  (void)expectedGroups;
   uint32_t slots = 8192;
+  // The caller expects far more groups than the shared table holds (or HLL, whose entries are
+  // (group, register) pairs): compile the kernel with the direct-to-global mode it can switch to.
+  P.bypassOk = (P.hll || expectedGroups > 4 * slots) ? 1 : 0;
   if (const char *e = getenv("ARESDB_B200_SMEM_SLOTS")) {  // tuning / experiments
     uint32_t v = (uint32_t)atoi(e);
     if (v >= 256 && v <= 8192 && (v & (v - 1)) == 0) slots = v;
@@ -988,7 +990,7 @@ static int64_t groupCount(AggState *st, cudaStream_t s) {
   return c[0];
 }
 
-static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outValues, cudaStream_t s) {
+static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outValues, cudaStream_t s, bool ordered = true) {
   for (int i = 0; i < NUM_DIM_WIDTH; i++)
     if (out.NumDimsPerDimWidth[i] != st->spec.NumDimsPerDimWidth[i]) throw EngineError("dimension layout differs from AggSpec");
   const int64_t occupied = groupCount(st, s);
@@ -1009,6 +1011,18 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
   // 2. sort the groups by hash (stable), 3. merge equal hashes (reference group identity)
   Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
   iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);
+  if (!ordered) {
+    // exchange form: the occupied slots as they are (no hash order, no merge of colliding hashes —
+    // the receiving state's own finalize does both)
+    if (n > out.VectorCapacity) throw EngineError("output DimensionVector capacity is smaller than the number of groups");
+    DimLayout Lx = makeDimLayout(out.NumDimsPerDimWidth, out.VectorCapacity);
+    emitGroupsKernel<<<divUp(n, 256), 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), order.as<uint32_t>(), (uint32_t)n,
+                                                   out.DimValues, Lx, out.IndexVector);
+    checkLastError("emitGroups");
+    ARES_CUDA(cudaMemcpyAsync(outValues, vals.ptr, (size_t)width * n, cudaMemcpyDeviceToDevice, s));
+    ARES_CUDA(cudaStreamSynchronize(s));
+    return n;
+  }
   radixSortPairs<uint32_t>(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 0,
                            st->hashBits, s);
   Scratch rep(sizeof(uint32_t) * (size_t)n, s);
@@ -1109,6 +1123,13 @@ CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8
                                   int device) {
   return guarded("AggStateFinalize", device, [&]() -> int64_t {
     return finalize(asState(state), outputKeys, outputValues, (cudaStream_t)cudaStream);
+  });
+}
+
+CGoCallResHandle AggStateExport(void *state, DimensionVector outputKeys, uint8_t *outputValues, void *cudaStream,
+                                int device) {
+  return guarded("AggStateExport", device, [&]() -> int64_t {
+    return finalize(asState(state), outputKeys, outputValues, (cudaStream_t)cudaStream, false);
   });
 }
 

@@ -63,8 +63,12 @@ __device__ __forceinline__ uint32_t mixKey(unsigned long long key) {
   return x ^ (x >> 15);
 }
 
+__device__ __forceinline__ uint32_t globalHome(const DevTable &G, unsigned long long key) {
+  return (mixKey(key) >> 3) & G.mask;
+}
+
 static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
-  uint32_t slot = (mixKey(key) >> 3) & G.mask;
+  uint32_t slot = globalHome(G, key);
 #pragma unroll 1
   for (uint32_t probe = 0; probe < kGlobalProbeLimit; probe++) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&G.keys[slot]);

@@ -13,11 +13,60 @@ __device__ __forceinline__ void jitIssueTile(const JitParams &P, uint32_t tile, 
     tmaLoad1D(stage + kPartSmemOff[p], P.partSrc[p] + (size_t)tile * kPartTileStride[p], kPartBytes[p], bar);
 }
 
+// Group identity of row r of a quad: the packed row itself, or the reference's hash of it.
+__device__ __forceinline__ unsigned long long jitKeyOf(const uint64_t (&key)[4][JIT_KW], const uint64_t (&meas)[4], int r) {
+  if (JIT_KW == 1) return key[r][0];
+  uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
+  unsigned long long k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+  if (JIT_HLL) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
+  return k;
+}
+
+// Folds the surviving rows of one quad.  Normal mode: the CTA's shared table first, the global table
+// for rows it cannot take (counted in *misses).  Bypass mode (the batch has far more groups than the
+// shared table holds, so looking there is wasted work): straight to the L2-resident global table,
+// with the four home-slot key loads issued back to back so that their latencies overlap.  The mode
+// is compiled in (JIT_BYPASS) only when AggSpec.ExpectedGroups announces such a batch, or for HLL.
+__device__ __forceinline__ void jitAggregate(const SmemTable &T, const JitParams &P, uint32_t alive,
+                                             const uint64_t (&key)[4][JIT_KW], const uint64_t (&meas)[4], bool allowClaim,
+                                             bool bypass, uint32_t *misses) {
+  constexpr AggOp op = (AggOp)JIT_AGG_OP;
+  if (JIT_BYPASS && bypass) {
+    unsigned long long k[4], seen[4];
+    uint32_t slot[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (!((alive >> r) & 1)) continue;
+      k[r] = jitKeyOf(key, meas, r);
+      slot[r] = globalHome(P.G, k[r]);
+      asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(seen[r]) : "l"(P.G.keys + slot[r]));
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (!((alive >> r) & 1)) continue;
+      if (seen[r] == k[r]) aggAtomic(op, &P.G.acc[slot[r]], meas[r]);
+      else globalUpdate(P.G, op, k[r], JIT_KW == 1 ? nullptr : key[r], meas[r]);
+    }
+    return;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    if (!((alive >> r) & 1)) continue;
+    const unsigned long long k = jitKeyOf(key, meas, r);
+    const uint64_t *roww = JIT_KW == 1 ? nullptr : key[r];
+    if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) {
+      if (JIT_BYPASS) atomicAdd(misses, 1u);
+      globalUpdate(P.G, op, k, roww, meas[r]);
+    }
+  }
+}
+
 extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const __grid_constant__ JitParams P) {
   extern __shared__ __align__(128) uint8_t smem[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem);        // full[JIT_STAGES]: bytes of a tile have landed
   uint64_t *empty = bars + kMaxStages;                        // empty[JIT_STAGES]: every warp is done with the stage
-  uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);
+  uint32_t *claims = reinterpret_cast<uint32_t *>(smem + 64);   // occupied slots of the shared table
+  uint32_t *misses = claims + 1;                                // rows the shared table turned away
   unsigned long long *tKeys = reinterpret_cast<unsigned long long *>(smem + 128);
   // keys of the CTA's table in shared memory (latency-critical, read-mostly); accumulators in an
   // L2-resident private slice of global memory, updated with fire-and-forget RED
@@ -32,6 +81,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   }
   if (threadIdx.x == 0) {
     *claims = 0;
+    *misses = 0;
     for (int s = 0; s < JIT_STAGES; s++) {
       mbarInit(&bars[s], 1);
       mbarInit(&empty[s], JIT_THREADS / 32 - 1);
@@ -45,7 +95,6 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   // per consumer thread (JIT_TILE_ROWS = 128 x consumer warps).  No CTA-wide barrier in the loop.
   constexpr uint32_t kConsumerThreads = JIT_THREADS - 32;
   static_assert(JIT_TILE_ROWS == kConsumerThreads * 4, "one quad per consumer thread");
-  constexpr AggOp op = (AggOp)JIT_AGG_OP;
   const uint32_t first = blockIdx.x, step = gridDim.x;
   if (threadIdx.x >= kConsumerThreads) {
     if (threadIdx.x == kConsumerThreads) {
@@ -63,26 +112,14 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
       mbarWait(&bars[s], parity);
       const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
       const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
+      // the shared table is full and has turned away several times its size in rows: stop consulting it
+      const bool bypass = JIT_BYPASS && !allowClaim && *reinterpret_cast<volatile uint32_t *>(misses) > 4u * JIT_SMEM_SLOTS;
       {
         const uint32_t q = threadIdx.x;
         uint64_t key[4][JIT_KW];
         uint64_t meas[4];
         const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          if (!((alive >> r) & 1)) continue;
-          unsigned long long k;
-          const uint64_t *roww = nullptr;
-          if (JIT_KW == 1) {
-            k = key[r][0];
-          } else {
-            uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
-            k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
-            if (JIT_HLL) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
-            roww = key[r];
-          }
-          if (!smemUpdate(T, P.G, op, k, roww, meas[r], allowClaim)) globalUpdate(P.G, op, k, roww, meas[r]);
-        }
+        jitAggregate(T, P, alive, key, meas, allowClaim, bypass, misses);
       }
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
@@ -113,21 +150,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
         const uint32_t nvalid = rows - q * 4 < 4 ? rows - q * 4 : 4;
         alive &= (1u << nvalid) - 1u;
-#pragma unroll
-        for (int r = 0; r < 4; r++) {
-          if (!((alive >> r) & 1)) continue;
-          unsigned long long k;
-          const uint64_t *roww = nullptr;
-          if (JIT_KW == 1) {
-            k = key[r][0];
-          } else {
-            uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
-            k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
-            if (JIT_HLL) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
-            roww = key[r];
-          }
-          if (!smemUpdate(T, P.G, op, k, roww, meas[r], true)) globalUpdate(P.G, op, k, roww, meas[r]);
-        }
+        jitAggregate(T, P, alive, key, meas, true, false, misses);
       }
       done += rows;
     }
@@ -135,7 +158,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   __syncthreads();
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
-    if (k != kEmptyKey) globalUpdate(P.G, op, k, nullptr, __ldcg(&tAcc[i]));
+    if (k != kEmptyKey) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, nullptr, __ldcg(&tAcc[i]));
   }
 }
 

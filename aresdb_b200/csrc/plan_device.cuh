@@ -57,7 +57,7 @@ struct DevPlan {
   uint64_t accNeutral;       // neutral element of the combine op
   uint8_t keyMode, rowBytes, valueBytes, hashBits;
   uint8_t aggOp, measWidth, measClass, skipCount;
-  uint8_t hasMeasure, staged, hll, pad1;
+  uint8_t hasMeasure, staged, hll, bypassOk;
 };
 
 // jit.cu: runs the staged tiles of `P` with a kernel specialised for the plan's shape.  Returns false

@@ -52,28 +52,35 @@ class ShardedFusedQuery:
         self.local.process_batch(batch, stream)
 
     def _exchange(self):
-        """All-gathers every rank's finalized rows and folds them into `self.merged`; returns the
-        total number of rows gathered (an upper bound of the merged group count).  For hll queries
-        the rows are the carried (group, register) entries."""
+        """The one exchange step: every rank exports its table (AggStateExport: unordered rows, no
+        sort), ONE all-gather moves [dim block | measure vector] of every rank, and every rank folds
+        all of them into `self.merged`.  Returns the number of rows gathered (an upper bound of the
+        merged group count).  For hll queries the rows are the carried (group, register) entries."""
         import torch
-        q, sp, dist = self.q, self.space, self.dist
-        g, out = self.local.finalize_into()
+        q, sp, dist, lib = self.q, self.space, self.dist, self.lib
+        n = self.local.group_count()
         counts = torch.zeros(self.world, dtype=torch.int64, device=sp.dev)
-        counts[self.rank] = g
+        counts[self.rank] = n
         dist.all_reduce(counts)
-        cap = int(counts.max().item())
-        pad = pad_result(sp, q, out, g, cap)
-        all_dims = [torch.empty_like(pad.dims.handle) for _ in range(self.world)]
-        all_meas = [torch.empty_like(pad.measures.handle) for _ in range(self.world)]
-        dist.all_gather(all_dims, pad.dims.handle)
-        dist.all_gather(all_meas, pad.measures.handle)
+        counts = counts.tolist()
+        cap = max(max(counts), 1)
+        _, _, _, dim_bytes = dim_offsets(q.num_dims_per_width, cap)
+        dim_bytes = (dim_bytes + 15) // 16 * 16
+        part = dim_bytes + q.measure_bytes * cap
+        gathered = torch.empty(self.world * part, dtype=torch.uint8, device=sp.dev)
+        mine = gathered[self.rank * part:(self.rank + 1) * part]
+        if n:
+            dv = A.make_dimension_vector(mine.data_ptr(), None, None, q.num_dims_per_width, cap)
+            lib.AggStateExport(self.local.state, dv, mine.data_ptr() + dim_bytes, sp.stream, sp.device)
+        dist.all_gather_into_tensor(gathered, mine.clone())
         self.merged.reset()
+        base = gathered.data_ptr()
         for r in range(self.world):
-            n = int(counts[r].item())
-            if n:
-                dv = A.make_dimension_vector(all_dims[r].data_ptr(), None, None, q.num_dims_per_width, pad.capacity)
-                self.merged.merge(dv, all_meas[r].data_ptr(), n)
-        return int(counts.sum().item())
+            if counts[r]:
+                dv = A.make_dimension_vector(base + r * part, None, None, q.num_dims_per_width, cap)
+                self.merged.merge(dv, base + r * part + dim_bytes, counts[r])
+        self._keep = gathered   # merge is asynchronous: keep the gathered rows alive until finalize
+        return int(sum(counts))
 
     def finalize(self):
         """(groups, result buffers) of the WHOLE query, identical on every rank."""

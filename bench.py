@@ -166,7 +166,7 @@ def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: in
         import build_oracle
         build_oracle.build()
     cores = os.cpu_count() or 1
-    workers = workers or max(1, min(cores, 64))
+    workers = workers or max(1, min(cores, 128))
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
         t0 = time.perf_counter()
@@ -355,7 +355,12 @@ def gpu_run(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+    if args.profile_range:  # `ncu --profile-from-start off`: only the timed steps are captured
+        torch.cuda.profiler.start()
     ms, launches, last = timed(step_device, args.steps, args.warmup)
+    if args.profile_range:
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
     groups = last[0]
 
     # dominant kernel (fusedBatchKernel) timed alone, L2 cold because each batch (1.4 GB) >> L2
@@ -391,6 +396,13 @@ def gpu_run(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     algo_bytes = WL["bytes_per_row"] * rows_per_batch
+    traffic = None
+    try:  # DRAM bytes per launch from the committed ncu capture of this workload's kernel, scaled to this batch size
+        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(args.workload)
+        if t:
+            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * rows_per_batch / t["rows_per_launch"]
+    except Exception:
+        pass
     achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -407,7 +419,7 @@ def gpu_run(args):
                    "l2": f"inputs ({algo_bytes / 1e9:.2f} GB per batch) larger than the 126 MB L2; no flush needed"},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "aresFusedJit (NVRTC-specialised fused scan-filter-aggregate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": None,
+                     "frac": achieved / peak if achieved else None, "traffic": traffic,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
                      "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
         "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
@@ -444,6 +456,8 @@ def main():
                     help="cfg3 (default) is the headline; the others are the remaining BASELINE configs")
     ap.add_argument("--rows", type=int, default=0, help="override the workload's table size")
     ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows per CPU worker per step (baseline sample)")
+    ap.add_argument("--profile-range", action="store_true",
+                    help="bracket the device-resident steps (warm-up included) with cudaProfilerStart/Stop for ncu")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()

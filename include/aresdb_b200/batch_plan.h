@@ -125,6 +125,12 @@ CGoCallResHandle AggStateGroupCount(void *state, void *cudaStream, int device);
 CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8_t *outputValues,
                                   void *cudaStream, int device);
 
+/* Exchange form of AggStateFinalize: the occupied table slots as (dim row, partial measure) pairs in
+ * no particular order and without merging equal hashes — what another state's AggStateMerge consumes.
+ * Cheaper than AggStateFinalize (no sort); res = number of rows (== AggStateGroupCount). Synchronises. */
+CGoCallResHandle AggStateExport(void *state, DimensionVector outputKeys, uint8_t *outputValues,
+                                void *cudaStream, int device);
+
 /* AGGR_HLL states: the final outputs of the reference's last-batch HyperLogLog call
  * (query/hll.cu:262-290, adopted by query/time_series_aggregate.go:661-681).  res = number of dimension
  * groups g.  *dimValuesPtr = a DimensionVector block of VectorCapacity g (groups in key order),
