@@ -358,10 +358,14 @@ __device__ __forceinline__ void processQuad(const DevPlan &P, const DevTable &G,
     const uint64_t *roww = nullptr;
     if constexpr (WIDEKEY) {
       key = P.hashBits == 64 ? murmur3_128_lo(kw[r], P.rowBytes, 0) : (unsigned long long)murmur3_32(kw[r], P.rowBytes, 0);
-      if (P.hll) key = (key & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);
+      if (P.hll == 1) key = (key & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);
       roww = kw[r];
     } else {
       key = kw[r][0];
+    }
+    if (P.hll == 2) {  // dense registers (no shared mirror on this generic path)
+      hllDenseUpdate(G, nullptr, key, roww, (uint32_t)meas[r]);
+      continue;
     }
     if (!useSmem || !smemUpdate(T, G, op, key, roww, meas[r], allowClaim)) globalUpdate(G, op, key, roww, meas[r]);
   }
@@ -458,6 +462,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   }
   // ---- flush the shared table into the global one ---------------------------------------------
   __syncthreads();
+  if (P.hll == 2) return;
   const AggOp op = (AggOp)P.aggOp;
   for (uint32_t i = threadIdx.x; i < P.smemSlots; i += blockDim.x) {
     unsigned long long k = tKeys[i];
@@ -470,7 +475,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 mergeRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint8_t *__restrict__ measures, int width,
-                AggOp op, int n, uint8_t keyMode, uint8_t hashBits, bool hll, DevTable G) {
+                AggOp op, int n, uint8_t keyMode, uint8_t hashBits, int hll, DevTable G) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride) {
     uint64_t w[4];
@@ -478,10 +483,72 @@ mergeRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint8_t *_
     unsigned long long key = keyMode == KEY_PACKED ? w[0]
                            : (hashBits == 64 ? murmur3_128_lo(w, L.rowBytes, 0) : (unsigned long long)murmur3_32(w, L.rowBytes, 0));
     const uint64_t v = loadMeasure(measures, i, width);
-    if (hll) key = (key & 0xFFFFFFFFFFFF0000ull) | (v & 0x3FFFu);
+    if (hll == 2) { hllDenseUpdate(G, nullptr, key, keyMode == KEY_HASHED ? w : nullptr, (uint32_t)v); continue; }
+    if (hll == 1) key = (key & 0xFFFFFFFFFFFF0000ull) | (v & 0x3FFFu);
     globalUpdate(G, op, key, keyMode == KEY_HASHED ? w : nullptr, v);
   }
 }
+
+// ---------------------------------------------------------------------------------------
+// dense HLL mode: registers -> the carried (key, value) rows of query/hll.cu, already in key order
+// ---------------------------------------------------------------------------------------
+// one CTA per group (d-th in hash order): number of registers that were hit
+__global__ void __launch_bounds__(256)
+hllDenseCountKernel(const uint32_t *__restrict__ regs, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ order,
+                    uint32_t *__restrict__ counts) {
+  __shared__ uint32_t sWarp[256 / 32 + 1];
+  const uint32_t *r = regs + (size_t)slotOf[order[blockIdx.x]] * kHllRegisters;
+  uint32_t c = 0;
+  for (uint32_t i = threadIdx.x; i < kHllRegisters; i += 256) c += r[i] != 0;
+  uint32_t total;
+  blockExclusiveScan<256>(c, sWarp, &total);
+  if (threadIdx.x == 0) counts[blockIdx.x] = total;
+}
+
+// exclusive prefix of n <= 8192 counts by one CTA; offsets[n] = total
+__global__ void __launch_bounds__(1024) hllDenseOffsetsKernel(const uint32_t *__restrict__ counts, int n, uint32_t *__restrict__ offsets) {
+  __shared__ uint32_t sWarp[1024 / 32 + 1];
+  __shared__ uint32_t sCarry;
+  if (threadIdx.x == 0) sCarry = 0;
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t x = i < n ? counts[i] : 0;
+    uint32_t total;
+    const uint32_t excl = blockExclusiveScan<1024>(x, sWarp, &total);
+    if (i < n) offsets[i] = sCarry + excl;
+    __syncthreads();
+    if (threadIdx.x == 0) sCarry += total;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[n] = sCarry;
+}
+
+// one CTA per group: its hit registers in ascending register order -> (key, value, group ordinal)
+__global__ void __launch_bounds__(256)
+hllDenseEmitKernel(const uint32_t *__restrict__ regs, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ order,
+                   const uint64_t *__restrict__ sortedHash, const uint32_t *__restrict__ offsets,
+                   uint64_t *__restrict__ outHash, uint32_t *__restrict__ outVals, uint32_t *__restrict__ outIndex) {
+  __shared__ uint32_t sWarp[256 / 32 + 1];
+  const uint32_t d = blockIdx.x;
+  const uint32_t *r = regs + (size_t)slotOf[order[d]] * kHllRegisters;
+  const uint64_t hi = sortedHash[d] & 0xFFFFFFFFFFFF0000ull;
+  uint32_t pos = offsets[d];
+  for (uint32_t base = 0; base < kHllRegisters; base += 256) {
+    const uint32_t reg = base + threadIdx.x;
+    const uint32_t v = r[reg];
+    uint32_t total;
+    const uint32_t excl = blockExclusiveScan<256>(v != 0, sWarp, &total);
+    if (v != 0) {
+      outHash[pos + excl] = hi | reg;
+      outVals[pos + excl] = v - 1u;
+      outIndex[pos + excl] = d;
+    }
+    pos += total;
+    __syncthreads();
+  }
+}
+
 
 constexpr int kCmpThreads = 256;
 constexpr int kCmpItems = 8;
@@ -581,11 +648,15 @@ struct AggState {
   ValClass measClass;
   uint64_t accNeutral;
   bool hll;
+  bool hllDense;           // HLL with one dense register array per group (few groups) instead of (group, register) entries
   size_t capacity;
   DevTable table;
   void *mem;               // single allocation behind the table
   unsigned long long *ctaAcc;  // [kMaxGridCtas][8192] private accumulator slices of the fused kernel's CTAs
 };
+
+constexpr uint32_t kHllDenseMaxGroups = 4096;   // dense HLL: directory of 8192 slots, 64 KB of registers per slot
+constexpr size_t kHllDenseSlots = 8192;
 
 static uint64_t neutralOf(AggOp op) {
   switch (op) {
@@ -614,7 +685,8 @@ static ValClass measureClassOf(int dt) {
 static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   const bool rows = st->keyMode == KEY_HASHED;
   const size_t ctaAccBytes = (size_t)kMaxGridCtas * 8192 * sizeof(unsigned long long);
-  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes;
+  const size_t regBytes = st->hllDense ? cap * kHllRegisters * sizeof(uint32_t) : 0;
+  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes + regBytes;
   void *mem = nullptr;
   CGoCallResHandle h = deviceMalloc(&mem, bytes);
   if (h.pStrErr) { std::string m(h.pStrErr); free((void *)h.pStrErr); throw EngineError(m); }
@@ -627,6 +699,8 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   st->table.rows = rows ? reinterpret_cast<uint64_t *>(st->table.acc + cap) : nullptr;
   st->ctaAcc = reinterpret_cast<unsigned long long *>(p + 256 + cap * 16 + (rows ? cap * 32 : 0));
   st->table.mask = (uint32_t)(cap - 1);
+  st->table.regs = st->hllDense ? reinterpret_cast<uint32_t *>(p + 256 + cap * 16 + (rows ? cap * 32 : 0) + ctaAccBytes) : nullptr;
+  if (st->hllDense) ARES_CUDA(cudaMemsetAsync(st->table.regs, 0, regBytes, s));
   ARES_CUDA(cudaMemsetAsync(p, 0, 256, s));
   fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, cap, st->accNeutral);
   checkLastError("fillTable");
@@ -643,14 +717,17 @@ static void describeState(AggState *st, const AggSpec &spec) {
   if (spec.AggFunc == AGGR_AVG_FLOAT)
     throw EngineError("the AVG aggregate is not available on the fused path; use the per-node entry points");
   st->hll = spec.AggFunc == AGGR_HLL;
+  st->hllDense = st->hll && spec.ExpectedGroups <= kHllDenseMaxGroups;
   if (st->hll) {
-    // group identity = the reference's HLL key (dim-row hash with the register in its low 16 bits,
-    // query/functor.hpp:1299-1305); the table keeps the max value (rho << 16 | reg) per key
     if (st->measClass != VC_U32) throw EngineError("an HLL measure is Uint32");
-    st->keyMode = KEY_HASHED;
     st->hashBits = 64;
     st->op = OP_MAX_U32;
     st->measWidth = 4;
+    // entry mode: group identity = the reference's HLL key (dim-row hash with the register in its low
+    // 16 bits, query/functor.hpp:1299-1305), the table keeps the max value (rho << 16 | reg) per key.
+    // dense mode (ExpectedGroups <= 4096 groups): the table is the directory of dimension rows and
+    // every group owns 16384 registers in DevTable::regs.
+    if (!st->hllDense) st->keyMode = KEY_HASHED;
   } else {
     st->op = aggOpOf(spec.AggFunc, bytes, &st->measWidth);
   }
@@ -666,6 +743,7 @@ static AggState *createState(const AggSpec &spec, cudaStream_t s, int device) {
     size_t want = (size_t)spec.ExpectedGroups * 2;
     size_t cap = (size_t)1 << 21;
     while (cap < want) cap <<= 1;
+    if (st->hllDense) cap = kHllDenseSlots;
     allocTable(st, cap, s);
   } catch (...) {
     delete st;
@@ -847,7 +925,8 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
   P.aggOp = st->op;
   P.measWidth = (uint8_t)st->measWidth;
   P.measClass = st->measClass;
-  P.hll = st->hll ? 1 : 0;
+  P.hll = st->hll ? (st->hllDense ? 2 : 1) : 0;
+  P.denseSlots = st->hllDense ? (uint32_t)st->capacity : 0;
   const int agg = st->spec.AggFunc;
   P.skipCount = !((agg >= AGGR_SUM_UNSIGNED && agg <= AGGR_SUM_FLOAT) || agg == AGGR_AVG_FLOAT);
   P.measureIdentity = aggIdentity(agg, st->measClass);
@@ -972,11 +1051,14 @@ static void mergeRows(AggState *st, const DimensionVector &in, const uint8_t *va
   int blocks = divUp(length, 256);
   if (blocks > smCount() * 8) blocks = smCount() * 8;
   mergeRowsKernel<<<blocks, 256, 0, s>>>(in.DimValues, L, values, st->measWidth, st->op, length, st->keyMode,
-                                        (uint8_t)st->hashBits, st->hll, st->table);
+                                        (uint8_t)st->hashBits, st->hll ? (st->hllDense ? 2 : 1) : 0, st->table);
   checkLastError("AggStateMerge");
 }
 
 static void checkOverflow(AggState *st, const uint32_t counters[2]) {
+  if (counters[1] && st->hllDense)
+    throw EngineError("dense HLL state: more than " + std::to_string(st->capacity) +
+                      " dimension groups; recreate the AggState with AggSpec.ExpectedGroups > 4096 (entry mode) and replay the batches");
   if (counters[1])
     throw EngineError("group table overflow: more than " + std::to_string(st->capacity) +
                       " slots needed; recreate the AggState with a larger AggSpec.ExpectedGroups and replay the batches");
@@ -990,9 +1072,78 @@ static int64_t groupCount(AggState *st, cudaStream_t s) {
   return c[0];
 }
 
+// Dense HLL state -> carried rows.  Fills `block` (one dim row per group, capacity = groups, hash
+// order) and, per hit register in (group, register) order, key / value / group ordinal.
+struct DenseCarried {
+  int groups = 0;
+  int64_t entries = 0;
+  Scratch block, hash, values, index;
+};
+
+static void denseCarried(AggState *st, cudaStream_t s, DenseCarried &out, bool countOnly) {
+  uint32_t c[2];
+  ARES_CUDA(cudaMemcpyAsync(c, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  checkOverflow(st, c);
+  const int n = (int)c[0];
+  out.groups = n;
+  out.entries = 0;
+  if (n == 0) return;
+  // groups in the order of the reference hash of their dim row
+  const int tiles = divUp((int64_t)st->capacity, kCmpTile);
+  Scratch state(scanStateBytes(tiles) + sizeof(uint32_t), s);
+  ARES_CUDA(cudaMemsetAsync(state.ptr, 0, state.bytes, s));
+  ScanTileState sst = makeScanState(state.ptr, tiles);
+  uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
+  Scratch slotOf(sizeof(uint32_t) * (size_t)n, s), hash(sizeof(uint64_t) * (size_t)n, s), vals(sizeof(uint32_t) * (size_t)n, s);
+  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, 64, st->rowLayout.rowBytes, 4, sst,
+                                                   slotOf.as<uint32_t>(), hash.as<uint64_t>(), vals.as<uint8_t>(), dCount);
+  checkLastError("compactGroups");
+  Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
+  iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);
+  radixSortPairs<uint32_t>(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 0, 64, s);
+  Scratch counts(sizeof(uint32_t) * (size_t)n, s), offsets(sizeof(uint32_t) * ((size_t)n + 1), s);
+  hllDenseCountKernel<<<n, 256, 0, s>>>(st->table.regs, slotOf.as<uint32_t>(), order.as<uint32_t>(), counts.as<uint32_t>());
+  checkLastError("hllDenseCount");
+  hllDenseOffsetsKernel<<<1, 1024, 0, s>>>(counts.as<uint32_t>(), n, offsets.as<uint32_t>());
+  checkLastError("hllDenseOffsets");
+  uint32_t total = 0;
+  ARES_CUDA(cudaMemcpyAsync(&total, offsets.as<uint32_t>() + n, 4, cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  out.entries = total;
+  if (countOnly || total == 0) return;
+  out.block.reset((size_t)st->rowLayout.rowBytes * n, s);
+  out.hash.reset(sizeof(uint64_t) * (size_t)total, s);
+  out.values.reset(sizeof(uint32_t) * (size_t)total, s);
+  out.index.reset(sizeof(uint32_t) * (size_t)total, s);
+  DimLayout L = makeDimLayout(st->spec.NumDimsPerDimWidth, n);
+  emitGroupsKernel<<<divUp(n, 256), 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), order.as<uint32_t>(), (uint32_t)n,
+                                                 out.block.as<uint8_t>(), L, nullptr);
+  checkLastError("emitGroups");
+  hllDenseEmitKernel<<<n, 256, 0, s>>>(st->table.regs, slotOf.as<uint32_t>(), order.as<uint32_t>(), hash.as<uint64_t>(),
+                                       offsets.as<uint32_t>(), out.hash.as<uint64_t>(), out.values.as<uint32_t>(),
+                                       out.index.as<uint32_t>());
+  checkLastError("hllDenseEmit");
+  ARES_CUDA(cudaStreamSynchronize(s));  // the locals above are released in stream order; keep it simple
+}
+
 static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outValues, cudaStream_t s, bool ordered = true) {
   for (int i = 0; i < NUM_DIM_WIDTH; i++)
     if (out.NumDimsPerDimWidth[i] != st->spec.NumDimsPerDimWidth[i]) throw EngineError("dimension layout differs from AggSpec");
+  if (st->hllDense) {  // carried rows straight from the register arrays (already in key order)
+    DenseCarried dc;
+    denseCarried(st, s, dc, false);
+    if (dc.entries == 0) return 0;
+    if (dc.entries > out.VectorCapacity) throw EngineError("output DimensionVector capacity is smaller than the number of rows");
+    DimLayout Lin = makeDimLayout(out.NumDimsPerDimWidth, dc.groups), Lout = makeDimLayout(out.NumDimsPerDimWidth, out.VectorCapacity);
+    gatherDims(dc.block.as<uint8_t>(), Lin, dc.index.as<uint32_t>(), (int)dc.entries, out.DimValues, Lout, s);
+    ARES_CUDA(cudaMemcpyAsync(outValues, dc.values.ptr, sizeof(uint32_t) * (size_t)dc.entries, cudaMemcpyDeviceToDevice, s));
+    if (out.HashValues)
+      ARES_CUDA(cudaMemcpyAsync(out.HashValues, dc.hash.ptr, sizeof(uint64_t) * (size_t)dc.entries, cudaMemcpyDeviceToDevice, s));
+    if (out.IndexVector) iotaKernel<<<divUp(dc.entries, 256), 256, 0, s>>>(out.IndexVector, (int)dc.entries);
+    ARES_CUDA(cudaStreamSynchronize(s));
+    return dc.entries;
+  }
   const int64_t occupied = groupCount(st, s);
   if (occupied == 0) return 0;
   const int n = (int)occupied;
@@ -1051,6 +1202,26 @@ static int64_t finalizeHLL(AggState *st, uint8_t **dimValuesPtr, uint8_t **hllVe
   if (!st->hll) throw EngineError("AggStateFinalizeHLL needs a state created with AGGR_HLL");
   if (!dimValuesPtr || !hllVectorPtr || !hllVectorSizePtr || !hllDimRegIDCountPtr) throw EngineError("null output pointer");
   *dimValuesPtr = nullptr; *hllVectorPtr = nullptr; *hllVectorSizePtr = 0; *hllDimRegIDCountPtr = nullptr;
+  if (st->hllDense) {
+    DenseCarried dc;
+    denseCarried(st, s, dc, false);
+    if (dc.entries == 0) return 0;
+    const int dims = hllRegisterVectors(dc.hash.as<uint64_t>(), dc.values.as<uint32_t>(), dc.index.as<uint32_t>(), (int)dc.entries,
+                                        hllVectorPtr, hllVectorSizePtr, hllDimRegIDCountPtr, s);
+    void *out = nullptr;
+    CGoCallResHandle h = deviceMalloc(&out, (size_t)st->rowLayout.rowBytes * dims);
+    if (h.pStrErr) {
+      std::string m(h.pStrErr); free((void *)h.pStrErr);
+      deviceFree(*hllVectorPtr); deviceFree(*hllDimRegIDCountPtr);
+      *hllVectorPtr = nullptr; *hllDimRegIDCountPtr = nullptr;
+      throw EngineError(m);
+    }
+    DimLayout Lin = makeDimLayout(st->spec.NumDimsPerDimWidth, dc.groups), Lout = makeDimLayout(st->spec.NumDimsPerDimWidth, dims);
+    gatherDims(dc.block.as<uint8_t>(), Lin, dc.index.as<uint32_t>(), dims, static_cast<uint8_t *>(out), Lout, s);
+    ARES_CUDA(cudaStreamSynchronize(s));
+    *dimValuesPtr = static_cast<uint8_t *>(out);
+    return dims;
+  }
   const int64_t entries = groupCount(st, s);
   if (entries == 0) return 0;
   const int n = (int)entries;
@@ -1116,7 +1287,15 @@ CGoCallResHandle AggStateMerge(void *state, DimensionVector inputKeys, uint8_t *
 }
 
 CGoCallResHandle AggStateGroupCount(void *state, void *cudaStream, int device) {
-  return guarded("AggStateGroupCount", device, [&]() -> int64_t { return groupCount(asState(state), (cudaStream_t)cudaStream); });
+  return guarded("AggStateGroupCount", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    if (st->hllDense) {  // rows of the carried form = registers that were hit
+      DenseCarried dc;
+      denseCarried(st, (cudaStream_t)cudaStream, dc, true);
+      return dc.entries;
+    }
+    return groupCount(st, (cudaStream_t)cudaStream);
+  });
 }
 
 CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8_t *outputValues, void *cudaStream,
@@ -1146,6 +1325,7 @@ CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device) {
     AggState *st = asState(state);
     cudaStream_t s = (cudaStream_t)cudaStream;
     ARES_CUDA(cudaMemsetAsync(st->table.counters, 0, 256, s));
+    if (st->hllDense) ARES_CUDA(cudaMemsetAsync(st->table.regs, 0, st->capacity * kHllRegisters * sizeof(uint32_t), s));
     fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, st->capacity, st->accNeutral);
     checkLastError("AggStateReset");
     return 0;
@@ -1161,6 +1341,7 @@ CGoCallResHandle AresJitDryRun(AggSpec spec, const BatchPlan *plan, char **sourc
     AggState st;
     memset(&st.table, 0, sizeof(st.table));
     describeState(&st, spec);
+    st.capacity = st.hllDense ? kHllDenseSlots : 0;
     static thread_local DevPlan P;
     compilePlan(&st, *plan, P);
     P.tailBegin = 0;

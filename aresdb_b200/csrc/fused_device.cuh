@@ -19,7 +19,10 @@ struct DevTable {
   uint64_t *rows;        // [capacity][4] packed rows, wide (hashed) keys only
   uint32_t *counters;    // [0] occupied slots, [1] overflow flag
   uint32_t mask;
+  uint32_t *regs;        // dense HLL mode: [capacity][16384] registers, value + 1 (0 = never hit); else null
 };
+
+constexpr uint32_t kHllRegisters = 1u << 14;   // p = 14
 
 // ---------------------------------------------------------------------------------------
 // device helpers: TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
@@ -95,6 +98,40 @@ __device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsign
                                              uint64_t val) {
   uint32_t slot = globalFindOrClaim(G, key, roww);
   if (slot != 0xFFFFFFFFu) aggAtomic(op, &G.acc[slot], val);
+}
+
+// ---------------------------------------------------------------------------------------
+// dense HLL mode: the table is only the directory of dimension groups; each group owns 16384
+// registers in G.regs.  `mirror` (optional) is a shared-memory copy of G.keys with the same
+// geometry, filled on demand, so that steady-state lookups never leave the SM.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void hllDenseUpdate(const DevTable &G, unsigned long long *mirror, unsigned long long key,
+                                               const uint64_t *roww, uint32_t value) {
+  uint32_t slot = globalHome(G, key);
+  bool found = false;
+  if (mirror != nullptr) {
+#pragma unroll 1
+    for (uint32_t probe = 0; probe < kSmemProbeLimit; probe++) {
+      const unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&mirror[slot]);
+      if (k == key) { found = true; break; }
+      if (k == kEmptyKey) break;          // unknown here: ask the global directory
+      slot = (slot + 1) & G.mask;
+    }
+  }
+  if (!found) {
+    const uint32_t home = globalHome(G, key);
+    slot = globalFindOrClaim(G, key, roww);
+    if (slot == 0xFFFFFFFFu) return;      // directory full: flagged in G.counters[1], reported at finalize
+    if (mirror != nullptr) {
+      // every directory slot from the key's home up to where it lives is occupied (linear probing):
+      // copy them so that the next probe sequence reaches the key without leaving shared memory
+      for (uint32_t s2 = home;; s2 = (s2 + 1) & G.mask) {
+        mirror[s2] = *reinterpret_cast<volatile unsigned long long *>(&G.keys[s2]);
+        if (s2 == slot) break;
+      }
+    }
+  }
+  atomicMax(&G.regs[(size_t)slot * kHllRegisters + (value & (kHllRegisters - 1))], value + 1u);
 }
 
 // ---------------------------------------------------------------------------------------

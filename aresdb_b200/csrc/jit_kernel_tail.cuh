@@ -18,7 +18,7 @@ __device__ __forceinline__ unsigned long long jitKeyOf(const uint64_t (&key)[4][
   if (JIT_KW == 1) return key[r][0];
   uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
   unsigned long long k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
-  if (JIT_HLL) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
+  if (JIT_HLL == 1) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
   return k;
 }
 
@@ -31,6 +31,15 @@ __device__ __forceinline__ void jitAggregate(const SmemTable &T, const JitParams
                                              const uint64_t (&key)[4][JIT_KW], const uint64_t (&meas)[4], bool allowClaim,
                                              bool bypass, uint32_t *misses) {
   constexpr AggOp op = (AggOp)JIT_AGG_OP;
+  if (JIT_HLL == 2) {  // dense registers: the shared table mirrors the directory of groups
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (!((alive >> r) & 1)) continue;
+      hllDenseUpdate(P.G, JIT_SMEM_SLOTS == JIT_DENSE_SLOTS ? T.keys : nullptr, jitKeyOf(key, meas, r),
+                     JIT_KW == 1 ? nullptr : key[r], (uint32_t)meas[r]);
+    }
+    return;
+  }
   if (JIT_BYPASS && bypass) {
     unsigned long long k[4], seen[4];
     uint32_t slot[4];
@@ -77,7 +86,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = JIT_SMEM_SLOTS - 1;
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     tKeys[i] = kEmptyKey;
-    tAcc[i] = P.accNeutral;
+    if (JIT_HLL != 2) tAcc[i] = P.accNeutral;
   }
   if (threadIdx.x == 0) {
     *claims = 0;
@@ -156,6 +165,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     }
   }
   __syncthreads();
+  if (JIT_HLL == 2) return;  // nothing CTA-private to fold: registers are updated in place
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
     if (k != kEmptyKey) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, nullptr, __ldcg(&tAcc[i]));

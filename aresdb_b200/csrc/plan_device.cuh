@@ -52,6 +52,7 @@ struct DevPlan {
   uint32_t smemSlots;      // shared table slots (power of two)
   uint32_t tailBegin;      // first row of the direct (non-staged) pass
   uint32_t numStages;      // depth of the TMA ring (2..kMaxStages)
+  uint32_t denseSlots;     // dense HLL mode: slots of the group directory (0 otherwise)
   int32_t ncols, ninsts, lastFilter;
   uint64_t measureIdentity;  // NULL measure -> this (sink class bits)
   uint64_t accNeutral;       // neutral element of the combine op

@@ -149,9 +149,12 @@ def test_hll_value_device_shift_semantics_on_b200():
 
 
 # ---- the fused path: ExecuteBatchPlan into an AGGR_HLL state, AggStateFinalizeHLL --------------------
-def run_hll_fused(be, q, host_batches):
+ENTRY_MODE, DENSE_MODE = 100000, 0   # AggSpec.ExpectedGroups: > 4096 -> (group, register) entries; else dense registers
+
+
+def run_hll_fused(be, q, host_batches, expected_groups=DENSE_MODE):
     from aresdb_b200.executor import FusedBatchExecutor
-    ex = FusedBatchExecutor(be.lib, be.space, q)
+    ex = FusedBatchExecutor(be.lib, be.space, q, expected_groups)
     keep = []
     for hb in host_batches:
         b = upload(be, hb)
@@ -172,29 +175,34 @@ def _device_oracle(q, host_batches):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("mode", [ENTRY_MODE, DENSE_MODE], ids=["entries", "dense"])
 @pytest.mark.parametrize("name", list(hll_queries()))
-def test_hll_fused_plan_on_b200(name, host_batches):
+def test_hll_fused_plan_on_b200(name, mode, host_batches):
     """One fused kernel per batch + AggStateFinalizeHLL == the reference's per-batch HyperLogLog
-    sequence, byte for byte (dims, order, register counts, sparse/dense vectors)."""
+    sequence, byte for byte (dims, order, register counts, sparse/dense vectors), in both table modes."""
     eng = H.get_backend("b200")
     q = hll_queries()[name]
-    assert_same_hll(run_hll_fused(eng, q, host_batches), _device_oracle(q, host_batches), name)
+    assert_same_hll(run_hll_fused(eng, q, host_batches, mode), _device_oracle(q, host_batches), f"{name}/{mode}")
 
 
 @pytest.mark.gpu
-def test_hll_fused_states_merge_through_carried_rows(host_batches):
+@pytest.mark.parametrize("mode", [ENTRY_MODE, DENSE_MODE], ids=["entries", "dense"])
+def test_hll_fused_states_merge_through_carried_rows(mode, host_batches):
     """Two HLL states (two GPUs' worth of batches) combine through AggStateFinalize (carried rows:
     one per (group, register) entry) + AggStateMerge — the multi-GPU exchange step for hll queries."""
     from aresdb_b200.executor import FusedBatchExecutor, _ResultBuffers
     eng = H.get_backend("b200")
     q = hll_queries()["two_dims"]
-    a, b = FusedBatchExecutor(eng.lib, eng.space, q), FusedBatchExecutor(eng.lib, eng.space, q)
+    a, b = FusedBatchExecutor(eng.lib, eng.space, q, mode), FusedBatchExecutor(eng.lib, eng.space, q, mode)
     keep = [upload(eng, hb) for hb in host_batches]
     a.process_batch(keep[0])
     a.process_batch(keep[1])
     b.process_batch(keep[2])
     n, carried = b.finalize_into()
     assert n == b.group_count() and n > 0
+    values = carried.measures.get(np.uint32, n)
+    assert (np.diff(carried.hash.get(np.uint64, n).astype(np.uint64)) > 0).all()      # key-ascending, one row per key
+    assert ((carried.hash.get(np.uint64, n) & 0x3FFF) == (values & 0x3FFF)).all()    # key carries the register
     a.merge(carried.dimension_vector(q), carried.measures.ptr, n)
     assert_same_hll(a.hll_result(), _device_oracle(q, host_batches), "merged")
     a.close()

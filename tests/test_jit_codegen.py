@@ -10,7 +10,7 @@ from aresdb_b200 import columns, synth
 import test_pipeline_parity as T
 
 
-def _dry_run(lib, q, rows=100000, start_bit=0):
+def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0):
     fn = lib.alg.AresJitDryRun
     fn.argtypes = [A.AggSpec, C.POINTER(A.BatchPlan), C.POINTER(C.c_char_p)]
     fn.restype = A.CGoCallResHandle
@@ -24,7 +24,7 @@ def _dry_run(lib, q, rows=100000, start_bit=0):
         p.Columns[i] = columns.slice_of(0x7F0000000000 + i * (1 << 30), dt, rows, 0, 64 * 200, 2, start_bit)
     p.NumRows = rows
     src = C.c_char_p()
-    h = fn(q.agg_spec(), C.byref(p), C.byref(src))
+    h = fn(q.agg_spec(expected_groups), C.byref(p), C.byref(src))
     if h.pStrErr:
         raise A.AresError(C.string_at(h.pStrErr).decode())
     return int(h.res or 0), (src.value or b"").decode()
@@ -48,11 +48,16 @@ def test_literals_are_runtime_parameters():
     assert _dry_run(lib, q1)[1] == _dry_run(lib, q2)[1]
 
 
-def test_hll_queries_specialise_with_the_reference_key():
-    """AGGR_HLL plans compile too; the kernel keys its table by (dim-row hash & ~0xFFFF) | register."""
+def test_hll_queries_specialise_in_both_modes():
+    """AGGR_HLL plans compile too.  Entry mode (many groups expected) keys the table by
+    (dim-row hash & ~0xFFFF) | register; dense mode keeps one register array per dimension row and
+    mirrors the directory of rows in shared memory."""
     import test_hll_pipeline as HP
     lib = A.load_engine()
     for name, q in HP.hll_queries().items():
-        size, src = _dry_run(lib, q)
+        size, src = _dry_run(lib, q, expected_groups=100000)
         assert size > 0, name
         assert "#define JIT_HLL 1" in src and "#define JIT_KW 4" in src
+        size, src = _dry_run(lib, q)
+        assert size > 0, name
+        assert "#define JIT_HLL 2" in src and "#define JIT_DENSE_SLOTS 8192" in src
