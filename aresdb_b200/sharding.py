@@ -35,7 +35,7 @@ def pad_result(space, q: AggQuery, src: _ResultBuffers, groups: int, capacity: i
 class ShardedFusedQuery:
     """One rank's half of a sharded query on the B200 engine (torch.distributed / NCCL plumbing)."""
 
-    def __init__(self, lib, space, q: AggQuery, expected_groups: int = 0, merged_groups: int = 1 << 16):
+    def __init__(self, lib, space, q: AggQuery, expected_groups: int = 0, merged_groups: int | None = None):
         from .executor import FusedBatchExecutor
         import torch.distributed as dist
         self.dist = dist
@@ -43,6 +43,8 @@ class ShardedFusedQuery:
         self.rank = dist.get_rank() if dist.is_initialized() else 0
         self.lib, self.space, self.q = lib, space, q
         self.local = FusedBatchExecutor(lib, space, q, expected_groups)
+        # the merged state sees every rank's groups: same table hint (and, for hll, the same table mode)
+        merged_groups = expected_groups if merged_groups is None else merged_groups
         self.merged = FusedBatchExecutor(lib, space, q, merged_groups) if self.world > 1 else None
 
     def reset(self):

@@ -272,8 +272,7 @@ def gpu_run(args):
     torch.cuda.synchronize()
 
     from aresdb_b200.sharding import ShardedFusedQuery
-    ex = ShardedFusedQuery(lib, space, q, expected_groups=WL["expected_groups"],
-                           merged_groups=max(WL["expected_groups"], 1 << 16))
+    ex = ShardedFusedQuery(lib, space, q, expected_groups=WL["expected_groups"])
 
     def finish():
         """(groups, d2h bytes): the query result lands in host memory."""
