@@ -168,32 +168,52 @@ __device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, u
   }
 }
 
+// Out-of-line tail of smemUpdate: `slot` is the first empty slot of the key's probe sequence (seen
+// `probe` steps from its home).  Claims it (or follows the winner of a lost race further down the
+// sequence).  Returns the key's slot, or 0xFFFFFFFF when the row has to go to the global table.
+static __device__ __noinline__ uint32_t smemClaim(unsigned long long *keys, uint32_t *claims, uint32_t mask, const DevTable &G,
+                                                  unsigned long long key, const uint64_t *roww, uint32_t slot, uint32_t probe) {
+#pragma unroll 1
+  while (true) {
+    unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&keys[slot]);
+    if (k == kEmptyKey) {
+      k = atomicCAS(&keys[slot], kEmptyKey, key);
+      if (k == kEmptyKey) {
+        atomicAdd(claims, 1u);
+        // wide keys: the packed row is recorded in the global table once, by whoever claims first
+        if (roww != nullptr) globalFindOrClaim(G, key, roww);
+        return slot;
+      }
+    }
+    if (k == key) return slot;
+    if (++probe >= kSmemProbeLimit) return 0xFFFFFFFFu;
+    slot = (slot + 1) & mask;
+  }
+}
+
 // Returns false when the row has to go to the global table (shared table full around its home).
 // Common case first: the key already sits in its home slot -> one LDS.64, one compare, one atomic.
+// Displaced keys (19 % at load 0.3) take a tight linear search; only an empty slot — a key this CTA
+// has not seen yet — leaves the inlined code.
 __device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
                                            const uint64_t *roww, uint64_t val, bool allowClaim) {
   uint32_t slot = mixKey(key) & T.mask;
   unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
   if (k != key) {
     uint32_t probe = 0;
+    if (k != kEmptyKey) {
 #pragma unroll 1
-    while (true) {
-      if (k == kEmptyKey) {
-        if (!allowClaim) return false;
-        unsigned long long old = atomicCAS(&T.keys[slot], kEmptyKey, key);
-        if (old == kEmptyKey) {
-          atomicAdd(T.claims, 1u);
-          // wide keys: the packed row is recorded in the global table once, by whoever claims first
-          if (roww != nullptr) globalFindOrClaim(G, key, roww);
-          break;
-        }
-        k = old;
-        if (k == key) break;
+      for (;;) {
+        probe++;
+        slot = (slot + 1) & T.mask;
+        k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+        if (k == key || k == kEmptyKey || probe >= kSmemProbeLimit - 1) break;
       }
-      if (++probe >= kSmemProbeLimit) return false;
-      slot = (slot + 1) & T.mask;
-      k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
-      if (k == key) break;
+    }
+    if (k != key) {
+      if (k != kEmptyKey || !allowClaim) return false;   // probe limit reached inside a long run / table closed
+      slot = smemClaim(T.keys, T.claims, T.mask, G, key, roww, slot, probe);
+      if (slot == 0xFFFFFFFFu) return false;
     }
   }
   smemAtomic(op, &T.acc[slot], val);
