@@ -1,0 +1,425 @@
+"""AQL front-end subset: a JSON AQL query (the form of the reference's examples/1k_trips/queries/*.aql)
+-> `AggQuery`, i.e. the part of the reference's query compiler that produces what the hot path consumes
+(SURVEY.md §8 f1).  Mirrors, for UTC and a single fact table:
+
+* time filters            query/common/time_filter.go:100-420 (calendar-aligned relative / absolute
+                          expressions -> `col >= from AND col < to`)
+* time bucketizers        query/time_bucketizer.go:36-299, query/common/time_bucketizer.go:60-140
+                          (regular -> FLOOR, recurring -> FLOOR(MOD) [/ unit], irregular -> calendar functors)
+* measures                query/aql_compiler.go:1139-1250 (count -> sum(1), sum widening, hll) and
+                          query/context/query_context_helper.go:540-575 (countdistincthll)
+* row / common filters    SQL-ish boolean expressions over columns and literals, enum literals translated
+                          through the column's dictionary (query/aql_compiler.go:540-600)
+
+Not covered (they raise): joins, non-UTC timezones, geo, array functions, non-aggregate queries.
+"""
+from __future__ import annotations
+
+import calendar
+import datetime as _dt
+import re
+from dataclasses import dataclass, field
+
+from . import cabi as A
+from . import expr as E
+from .query import AggQuery, Measure
+
+SECONDS = {"m": 60, "h": 3600, "d": 86400}
+SECONDS_PER_WEEK = 7 * 86400
+SECONDS_PER_4_DAYS = 4 * 86400
+
+_TIME_UNIT = {"year": "y", "quarter": "q", "month": "M", "week": "w", "day": "d", "hour": "h", "quarter-hour": "15m",
+              "minute": "m", "second": "s"}
+_REGULAR_UNIT = {"minutes": "m", "minute": "m", "day": "d", "hours": "h", "hour": "h"}
+_RECURRING = {"time of day": (1, 86400), "hour of day": (3600, 86400), "hour of week": (3600, SECONDS_PER_WEEK),
+              "day of week": (86400, SECONDS_PER_WEEK)}
+_IRREGULAR = {"month": A.GetMonthStart, "quarter": A.GetQuarterStart, "year": A.GetYearStart, "week": A.GetWeekStart}
+_IRREGULAR_RECURRING = {"day of month": A.GetDayOfMonth, "day of year": A.GetDayOfYear,
+                        "month of year": A.GetMonthOfYear, "quarter of year": A.GetQuarterOfYear}
+
+
+class AQLError(ValueError):
+    pass
+
+
+@dataclass
+class Column:
+    name: str
+    data_type: int                       # cabi data type of the stored values (SmallEnum -> Uint8, BigEnum -> Uint16)
+    enum: dict | None = None             # enum columns: literal -> dictionary id
+    hll: bool = False                    # Uint32 column that already holds rho << 16 | reg values
+
+
+@dataclass
+class Table:
+    name: str
+    columns: list = field(default_factory=list)
+
+    def index_of(self, name: str) -> int:
+        for i, c in enumerate(self.columns):
+            if c.name == name:
+                return i
+        raise AQLError(f"unknown column {name}")
+
+    def ref(self, name: str) -> E.Col:
+        i = self.index_of(name)
+        return E.Col(i, self.columns[i].data_type, name)
+
+
+# ---- time filter -----------------------------------------------------------------------------------
+def _utc(*a) -> _dt.datetime:
+    return _dt.datetime(*a, tzinfo=_dt.timezone.utc)
+
+
+def _add_months(t: _dt.datetime, months: int) -> _dt.datetime:
+    m = t.month - 1 + months
+    return t.replace(year=t.year + m // 12, month=m % 12 + 1)
+
+
+def _apply_offset(base: _dt.datetime, amount: int, unit: str):
+    """start / end of the calendar unit `amount` units away from the one containing `base`."""
+    day = _utc(base.year, base.month, base.day)
+    month = _utc(base.year, base.month, 1)
+    if unit == "y":
+        return _utc(base.year + amount, 1, 1), _utc(base.year + 1 + amount, 1, 1)
+    if unit == "q":
+        start = _add_months(month, -((base.month - 1) % 3) + 3 * amount)
+        return start, _add_months(start, 3)
+    if unit == "M":
+        start = _add_months(month, amount)
+        return start, _add_months(start, 1)
+    if unit == "w":  # weeks start on Monday
+        start = day - _dt.timedelta(days=base.weekday()) + _dt.timedelta(days=7 * amount)
+        return start, start + _dt.timedelta(days=7)
+    if unit == "d":
+        start = day + _dt.timedelta(days=amount)
+        return start, start + _dt.timedelta(days=1)
+    if unit == "h":
+        start = _utc(base.year, base.month, base.day, base.hour) + _dt.timedelta(hours=amount)
+        return start, start + _dt.timedelta(hours=1)
+    if unit == "15m":
+        start = _utc(base.year, base.month, base.day, base.hour, base.minute - base.minute % 15) + _dt.timedelta(minutes=15 * amount)
+        return start, start + _dt.timedelta(minutes=15)
+    if unit == "m":
+        start = _utc(base.year, base.month, base.day, base.hour, base.minute) + _dt.timedelta(minutes=amount)
+        return start, start + _dt.timedelta(minutes=1)
+    raise AQLError(f"Unknown time filter unit: {unit}")
+
+
+def _absolute(date_expr: str, time_expr: str):
+    seg = date_expr.split("-")
+    if len(seg) > 3:
+        raise AQLError(f"Unknown time expression: {date_expr} {time_expr}")
+    year, month, day, hour, minute, unit = int(seg[0]), 1, 1, 0, 0, "y"
+    if len(seg) >= 2:
+        if seg[1].startswith("Q"):
+            if len(seg) == 3:
+                raise AQLError(f"Unknown time expression: {date_expr} {time_expr}")
+            month, unit = 1 + (int(seg[1][1:]) - 1) * 3, "q"
+        else:
+            month, unit = int(seg[1]), "M"
+    if len(seg) == 3:
+        day, unit = int(seg[2]), "d"
+    elif time_expr:
+        raise AQLError(f"Unknown time expression: {date_expr} {time_expr}")
+    if time_expr:
+        ts = time_expr.split(":")
+        if len(ts) > 2:
+            raise AQLError(f"Unknown time expression: {date_expr} {time_expr}")
+        hour, unit = int(ts[0]), "h"
+        if len(ts) == 2:
+            minute = int(ts[1])
+            unit = "15m" if minute % 15 == 0 else "m"
+    start, end = _apply_offset(_utc(year, month, day, hour, minute), 0, unit)
+    return start, end, unit
+
+
+def _time_expression(expression: str, now: _dt.datetime):
+    """(start, end, unit) of the calendar unit an expression names."""
+    if expression == "now":
+        return now, now, "s"
+    expression = {"today": "this day", "yesterday": "last day"}.get(expression, expression)
+    seg = expression.split(" ")
+    if seg[0] in ("this", "last"):
+        if len(seg) != 2 or seg[1] not in _TIME_UNIT:
+            raise AQLError(f"Unknown time filter expression: {expression}")
+        unit = _TIME_UNIT[seg[1]]
+        return (*_apply_offset(now, 0 if seg[0] == "this" else -1, unit), unit)
+    if seg[-1] == "ago":
+        if len(seg) != 3 or seg[1][:-1] not in _TIME_UNIT:
+            raise AQLError(f"Unknown time filter expression: {expression}")
+        unit = _TIME_UNIT[seg[1][:-1]]
+        return (*_apply_offset(now, -int(seg[0]), unit), unit)
+    if len(seg) == 1:
+        m = re.fullmatch(r"(-?\d+)([yqMwdhm])", expression)
+        if m:
+            return (*_apply_offset(now, int(m.group(1)), m.group(2)), m.group(2))
+        if re.fullmatch(r"\d+", expression):
+            seconds = int(expression)
+            if seconds > 99999999999:      # milliseconds
+                seconds //= 1000
+            if seconds > 9999999:
+                t = _dt.datetime.fromtimestamp(seconds, _dt.timezone.utc)
+                return t, t, "m" if seconds % 60 == 0 else "s"
+    if len(seg) > 2:
+        raise AQLError(f"Unknown time filter expression: {expression}")
+    return _absolute(seg[0], seg[1] if len(seg) == 2 else "")
+
+
+def parse_time_filter(time_filter: dict, now: int):
+    """-> (from_ts | None, to_ts | None) in epoch seconds; `to` defaults to now when only `from` is given."""
+    now_t = _dt.datetime.fromtimestamp(int(now), _dt.timezone.utc)
+    frm = to = None
+    if time_filter.get("from"):
+        frm = int(_time_expression(time_filter["from"], now_t)[0].timestamp())
+    if time_filter.get("to"):
+        to = int(_time_expression(time_filter["to"], now_t)[1].timestamp())
+    elif frm is not None:
+        to = int(now)
+    return frm, to
+
+
+# ---- time bucketizer -------------------------------------------------------------------------------
+def _bucket_size(text: str, unit: str) -> int:
+    if unit in ("m", "h") and text.isdigit():
+        n = int(text)
+        if 0 < n < 60 and ((unit == "m" and 60 % n == 0) or (unit == "h" and 24 % n == 0)):
+            return n
+    raise AQLError(f"failed to parse time bucketizer: {text}: invalid bucket size for {unit}")
+
+
+def _regular_bucket_seconds(s: str) -> int:
+    """"3m", "4 hours", "hour", "day", "quarter-hour" ... -> seconds (ParseRegularTimeBucketizer)."""
+    s = "15m" if s == "quarter-hour" else s.lower()
+    seg = s.split(" ", 1)
+    if len(seg) == 2:
+        if seg[1] not in _REGULAR_UNIT:
+            raise AQLError(f"failed to parse time bucketizer: {s}")
+        unit = _REGULAR_UNIT[seg[1]]
+        return _bucket_size(seg[0], unit) * SECONDS[unit]
+    s = _REGULAR_UNIT.get(s, s)
+    unit = s[-1:]
+    if unit not in SECONDS:
+        raise AQLError(f"failed to parse time bucketizer: {s}")
+    return (_bucket_size(s[:-1], unit) if len(s) > 1 else 1) * SECONDS[unit]
+
+
+def time_dimension_expr(bucketizer: str, time_col: E.Expr) -> E.Expr:
+    """The expression a time dimension with `timeBucketizer` evaluates (UTC)."""
+    unsigned = E.Type.Unsigned
+    rec = None
+    if bucketizer.endswith("minutes of day"):
+        comps = bucketizer.split()
+        if len(comps) < 4 or not comps[0].isdigit():
+            raise AQLError(f"Must put number before minutes of day: got {bucketizer}")
+        n = int(comps[0])
+        if n < 2 or n > 30 or 30 % n:
+            raise AQLError(f"Only {{2,3,4,5,6,10,15,20,30}} minutes of day are allowed: got {bucketizer}")
+        rec = (60 * n, 86400)
+    elif bucketizer in _RECURRING:
+        rec = _RECURRING[bucketizer]
+    if rec:
+        base_unit, bucket = rec
+        if base_unit > 1:
+            t = time_col
+            if bucket == SECONDS_PER_WEEK:   # 1970-01-01 is a Thursday: shift to Monday-based weeks
+                t = E.Binary(A.Minus, t, E.Lit(SECONDS_PER_4_DAYS, unsigned))
+            e = E.Binary(A.Floor, E.Binary(A.Mod, t, E.Lit(bucket, unsigned)), E.Lit(base_unit, unsigned))
+        else:
+            e = E.Binary(A.Mod, time_col, E.Lit(bucket, unsigned))
+        if base_unit >= 86400:
+            e = E.Binary(A.Divide, e, E.Lit(float(base_unit), E.Type.Float))
+        return e
+    if bucketizer in _IRREGULAR_RECURRING:
+        return E.Unary(_IRREGULAR_RECURRING[bucketizer], time_col)
+    if bucketizer in _IRREGULAR:
+        return E.Unary(_IRREGULAR[bucketizer], time_col)
+    return E.Binary(A.Floor, time_col, E.Lit(_regular_bucket_seconds(bucketizer), unsigned))
+
+
+# ---- SQL-ish expressions ---------------------------------------------------------------------------
+_TOKEN = re.compile(r"\s*(?:(\d+\.\d*|\.\d+|\d+)|'((?:[^']|'')*)'|([A-Za-z_][A-Za-z_0-9.]*)|(<>|!=|<=|>=|[-+*/%()=<>,]))")
+_BINARY = {"or": (1, A.Or), "and": (2, A.And), "=": (4, A.Equal), "!=": (4, A.NotEqual), "<>": (4, A.NotEqual),
+           "<": (4, A.LessThan), "<=": (4, A.LessThanOrEqual), ">": (4, A.GreaterThan), ">=": (4, A.GreaterThanOrEqual),
+           "+": (5, A.Plus), "-": (5, A.Minus), "*": (6, A.Multiply), "/": (6, A.Divide), "%": (6, A.Mod)}
+AGGREGATES = ("count", "sum", "min", "max", "hll", "countdistincthll")
+
+
+@dataclass
+class _Call:
+    name: str
+    args: list
+
+
+@dataclass
+class _Str:
+    value: str
+
+
+class _Parser:
+    def __init__(self, text: str, table: Table):
+        self.table, self.toks, pos = table, [], 0
+        while pos < len(text):
+            if text[pos:].strip() == "":
+                break
+            m = _TOKEN.match(text, pos)
+            if not m:
+                raise AQLError(f"cannot parse expression near: {text[pos:]}")
+            num, s, ident, op = m.groups()
+            if num is not None:
+                self.toks.append(("num", num))
+            elif s is not None:
+                self.toks.append(("str", s.replace("''", "'")))
+            elif ident is not None:
+                self.toks.append(("id", ident))
+            else:
+                self.toks.append(("op", op))
+            pos = m.end()
+        self.i = 0
+
+    def peek(self):
+        return self.toks[self.i] if self.i < len(self.toks) else (None, None)
+
+    def take(self):
+        t = self.peek()
+        self.i += 1
+        return t
+
+    def expect(self, op):
+        if self.take() != ("op", op):
+            raise AQLError(f"expected {op}")
+
+    def parse(self):
+        e = self.expression(0)
+        if self.i != len(self.toks):
+            raise AQLError(f"unexpected token {self.peek()[1]}")
+        return e
+
+    def expression(self, min_prec: int):
+        lhs = self.unary()
+        while True:
+            kind, v = self.peek()
+            key = v.lower() if kind == "id" else v
+            if kind not in ("op", "id") or key not in _BINARY or _BINARY[key][0] < min_prec:
+                return lhs
+            prec, op = _BINARY[key]
+            self.take()
+            rhs = self.expression(prec + 1)
+            lhs = self.binary(op, lhs, rhs)
+
+    def binary(self, op, lhs, rhs):
+        # enum literal against an enum column -> its dictionary id (unknown literal: matches nothing, id -1)
+        for a, b in ((lhs, rhs), (rhs, lhs)):
+            if isinstance(b, _Str):
+                if not isinstance(a, E.Col) or self.table.columns[a.index].enum is None:
+                    raise AQLError("string literals are only comparable with enum columns")
+                lit = E.Lit(self.table.columns[a.index].enum.get(b.value, -1))
+                lhs, rhs = (a, lit) if b is rhs else (lit, a)
+        return E.Binary(op, lhs, rhs)
+
+    def unary(self):
+        kind, v = self.take()
+        if kind == "num":
+            return E.Lit(float(v)) if "." in v else E.Lit(int(v))
+        if kind == "str":
+            return _Str(v)
+        if kind == "op" and v == "(":
+            e = self.expression(0)
+            self.expect(")")
+            return e
+        if kind == "op" and v == "-":
+            e = self.unary()
+            return E.Lit(-e.value) if isinstance(e, E.Lit) else E.Unary(A.Negate, e)
+        if kind == "id" and v.lower() == "not":
+            return E.Unary(A.Not, self.expression(3))
+        if kind == "id":
+            if self.peek() == ("op", "("):
+                self.take()
+                args = []
+                if self.peek() == ("op", "*"):
+                    self.take()
+                    args.append("*")
+                elif self.peek() != ("op", ")"):
+                    args.append(self.expression(0))
+                    while self.peek() == ("op", ","):
+                        self.take()
+                        args.append(self.expression(0))
+                self.expect(")")
+                return self.call(v.lower(), args)
+            if v.lower() in ("true", "false"):
+                return E.Lit(1 if v.lower() == "true" else 0, E.Type.Boolean)
+            name = v.split(".", 1)[1] if v.startswith(self.table.name + ".") else v
+            return self.table.ref(name)
+        raise AQLError(f"unexpected token {v}")
+
+    def call(self, name, args):
+        if name in AGGREGATES:
+            return _Call(name, args)
+        if name == "floor" and len(args) == 2:
+            return E.Binary(A.Floor, args[0], args[1])
+        raise AQLError(f"unsupported function {name}")
+
+
+def parse_expression(text: str, table: Table):
+    return _Parser(text, table).parse()
+
+
+# ---- query -----------------------------------------------------------------------------------------
+def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES_REDUCE_SORT) -> AggQuery:
+    """One element of the AQL `queries` array -> AggQuery.  `now` (epoch seconds) anchors relative time filters."""
+    if query.get("table") != table.name:
+        raise AQLError(f"unknown table {query.get('table')}")
+    if query.get("joins"):
+        raise AQLError("joins are outside this engine")
+    if query.get("timezone", "UTC") not in ("UTC", ""):
+        raise AQLError("only UTC is supported")
+    measures = query.get("measures") or []
+    if len(measures) != 1:
+        raise AQLError("expect one measure per query")   # aql_compiler.go:1140-1146
+    m = measures[0]
+    agg = parse_expression(m.get("sqlExpression") or m.get("expr"), table)
+    if not isinstance(agg, _Call):
+        raise AQLError("expect aggregate function")
+    if agg.name == "count":
+        measure = Measure("count")
+    elif len(agg.args) != 1 or agg.args[0] == "*":
+        raise AQLError(f"expect one parameter for {agg.name}")
+    else:
+        arg = agg.args[0]
+        if agg.name == "countdistincthll" and isinstance(arg, E.Col) and table.columns[arg.index].hll:
+            measure = Measure("hll", arg)      # noop when the column itself is an hll column
+        else:
+            measure = Measure(agg.name, arg)
+
+    filters = [parse_expression(f, table) for f in (m.get("rowFilters") or []) + (query.get("rowFilters") or [])]
+    tf = query.get("timeFilter") or {}
+    time_col = None
+    if tf.get("column"):
+        time_col = table.ref(tf["column"])
+        frm, to = parse_time_filter(tf, now)
+        if frm is not None:
+            filters.append(E.Binary(A.GreaterThanOrEqual, time_col, E.Lit(frm, E.Type.Unsigned)))
+        if to is not None:
+            filters.append(E.Binary(A.LessThan, time_col, E.Lit(to, E.Type.Unsigned)))
+
+    dims = []
+    for d in query.get("dimensions") or []:
+        e = parse_expression(d.get("sqlExpression") or d.get("expr"), table)
+        if d.get("timeBucketizer"):
+            e = time_dimension_expr(d["timeBucketizer"], e)
+        dims.append(e)
+    return AggQuery(filters, dims, measure, reduce_mode)
+
+
+def time_bucket_start(ts: int, bucketizer: str) -> int:
+    """Host-side statement of the irregular bucket starts (tests / result formatting)."""
+    t = _dt.datetime.fromtimestamp(ts, _dt.timezone.utc)
+    if bucketizer == "month":
+        return calendar.timegm((t.year, t.month, 1, 0, 0, 0))
+    if bucketizer == "year":
+        return calendar.timegm((t.year, 1, 1, 0, 0, 0))
+    if bucketizer == "quarter":
+        return calendar.timegm((t.year, 1 + (t.month - 1) // 3 * 3, 1, 0, 0, 0))
+    if bucketizer == "week":   # Monday 00:00 (reference query/functor.cu:207-212)
+        return ts - (ts - SECONDS_PER_4_DAYS) % SECONDS_PER_WEEK
+    return ts - ts % _regular_bucket_seconds(bucketizer)

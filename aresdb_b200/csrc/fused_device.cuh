@@ -191,32 +191,42 @@ static __device__ __noinline__ uint32_t smemClaim(unsigned long long *keys, uint
   }
 }
 
+// Byte offset of a key's home slot: multiplicative hash, top bits (table positions only, never group
+// identity).  With a compile-time table size this is IMAD, LOP3, IMAD, SHF, LOP3.
+__device__ __forceinline__ uint32_t smemHomeOffset(const SmemTable &T, unsigned long long key) {
+  const uint32_t x = ((uint32_t)key ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
+  return (x >> (29 - __popc(T.mask))) & (T.mask << 3);
+}
+
 // Returns false when the row has to go to the global table (shared table full around its home).
 // Common case first: the key already sits in its home slot -> one LDS.64, one compare, one atomic.
 // Displaced keys (19 % at load 0.3) take a tight linear search; only an empty slot — a key this CTA
-// has not seen yet — leaves the inlined code.
+// has not seen yet — leaves the inlined code.  Slots are addressed by byte offset throughout.
 __device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
                                            const uint64_t *roww, uint64_t val, bool allowClaim) {
-  uint32_t slot = mixKey(key) & T.mask;
-  unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+  const uint8_t *kb = reinterpret_cast<const uint8_t *>(T.keys);
+  const uint32_t offMask = T.mask << 3;
+  uint32_t off = smemHomeOffset(T, key);
+  unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
   if (k != key) {
     uint32_t probe = 0;
     if (k != kEmptyKey) {
 #pragma unroll 1
       for (;;) {
         probe++;
-        slot = (slot + 1) & T.mask;
-        k = *reinterpret_cast<volatile unsigned long long *>(&T.keys[slot]);
+        off = (off + 8) & offMask;
+        k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
         if (k == key || k == kEmptyKey || probe >= kSmemProbeLimit - 1) break;
       }
     }
     if (k != key) {
       if (k != kEmptyKey || !allowClaim) return false;   // probe limit reached inside a long run / table closed
-      slot = smemClaim(T.keys, T.claims, T.mask, G, key, roww, slot, probe);
+      const uint32_t slot = smemClaim(T.keys, T.claims, T.mask, G, key, roww, off >> 3, probe);
       if (slot == 0xFFFFFFFFu) return false;
+      off = slot << 3;
     }
   }
-  smemAtomic(op, &T.acc[slot], val);
+  smemAtomic(op, reinterpret_cast<unsigned long long *>(reinterpret_cast<uint8_t *>(T.acc) + off), val);
   return true;
 }
 

@@ -1,0 +1,176 @@
+"""The AQL front-end subset (aresdb_b200/aql.py) and BASELINE config 1: the reference's
+examples/1k_trips data set and its two example queries (count(*) / sum(fare) of completed trips
+by hour over the last 24 hours).  The expectation in tests/golden/trips_1k.npz was produced by the
+reference's HOST build (tests/golden/make_trips_fixture.py); a numpy restatement of the query
+cross-checks the fixture itself."""
+import datetime as dt
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+import harness as H
+from aresdb_b200 import aql, cabi as A, columns, expr as E
+from aresdb_b200.executor import Batch, FusedBatchExecutor, LegacyBatchExecutor
+
+GOLDEN = Path(__file__).resolve().parent / "golden" / "trips_1k.npz"
+
+
+def _queries():
+    def q(measure):
+        return {"table": "trips",
+                "measures": [{"alias": "value", "sqlExpression": measure, "rowFilters": ["status='completed'"]}],
+                "timeFilter": {"column": "request_at", "from": "24 hours ago", "to": "this quarter-hour"},
+                "dimensions": [{"alias": "ts", "sqlExpression": "request_at", "timeBucketizer": "hour"}],
+                "joins": []}
+    return {"total_trips": q("count(*)"), "total_fare": q("sum(fare)")}
+
+
+@pytest.fixture(scope="module")
+def trips():
+    z = np.load(GOLDEN)
+    names = [str(s) for s in z["status_names"]]
+    table = aql.Table("trips", [aql.Column("request_at", A.Uint32), aql.Column("city_id", A.Uint16),
+                                aql.Column("status", A.Uint8, enum={n: i for i, n in enumerate(names)}),
+                                aql.Column("fare", A.Float32)])
+    return z, table, int(z["now"])
+
+
+def _upload(be, z, table):
+    vps, keep = [], []
+    for c in table.columns:
+        buf, vp = columns.make_column(be.space, c.data_type, z[c.name])
+        vps.append(vp)
+        keep.append(buf)
+    return Batch(vps, len(z["fare"]), keep=keep)
+
+
+def _check(res, z, name):
+    hours = np.array(res.decoded_dims()[0], np.uint32)
+    got = dict(zip(hours.tolist(), res.measures.tolist()))
+    exp = dict(zip(z[f"{name}_hours"].tolist(), z[f"{name}_values"].tolist()))
+    assert got == exp
+
+
+def test_fixture_agrees_with_numpy(trips):
+    """The stored reference results equal an independent numpy evaluation of the two queries."""
+    z, table, now = trips
+    frm, to = aql.parse_time_filter({"from": "24 hours ago", "to": "this quarter-hour"}, now)
+    ts, fare = z["request_at"].astype(np.int64), z["fare"].astype(np.float64)
+    keep = (z["status"] == table.columns[2].enum["completed"]) & (ts >= frm) & (ts < to)
+    hours = ts[keep] - ts[keep] % 3600
+    for name, weights in (("total_trips", None), ("total_fare", fare[keep])):
+        uniq = np.unique(hours)
+        vals = [(weights[hours == h].sum() if weights is not None else int((hours == h).sum())) for h in uniq]
+        exp = dict(zip(z[f"{name}_hours"].tolist(), z[f"{name}_values"].tolist()))
+        assert exp == dict(zip(uniq.tolist(), vals))
+
+
+@pytest.mark.parametrize("name", ["total_trips", "total_fare"])
+def test_example_queries_on_cpu_checkers(name, trips, impl):
+    if impl.is_gpu:
+        pytest.skip("covered by the gpu tests below")
+    z, table, now = trips
+    ex = LegacyBatchExecutor(impl.lib, impl.space, aql.compile_query(_queries()[name], table, now))
+    ex.process_batch(_upload(impl, z, table))
+    _check(ex.result(), z, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["total_trips", "total_fare"])
+def test_example_queries_on_b200(name, trips):
+    """config 1 through both forms of the engine: per-node entry points and the fused plan."""
+    z, table, now = trips
+    eng = H.get_backend("b200")
+    q = aql.compile_query(_queries()[name], table, now)
+    batch = _upload(eng, z, table)
+    legacy = LegacyBatchExecutor(eng.lib, eng.space, q)
+    legacy.process_batch(batch)
+    _check(legacy.result(), z, name)
+    fused = FusedBatchExecutor(eng.lib, eng.space, q)
+    fused.process_batch(batch)
+    _check(fused.result(), z, name)
+    fused.close()
+
+
+# ---- front-end unit tests (reference behaviour cited per case) -------------------------------------------
+NOW = int(dt.datetime(2023, 11, 15, 1, 39, 5, tzinfo=dt.timezone.utc).timestamp())   # a Wednesday
+
+
+def _ts(*a):
+    return int(dt.datetime(*a, tzinfo=dt.timezone.utc).timestamp())
+
+
+@pytest.mark.parametrize("frm,to,exp", [
+    ("24 hours ago", "this quarter-hour", (_ts(2023, 11, 14, 1), _ts(2023, 11, 15, 1, 45))),
+    ("today", "", (_ts(2023, 11, 15), NOW)),                       # `to` defaults to now (time_filter.go:357-360)
+    ("yesterday", "yesterday", (_ts(2023, 11, 14), _ts(2023, 11, 15))),
+    ("last week", "this week", (_ts(2023, 11, 6), _ts(2023, 11, 20))),   # weeks start on Monday
+    ("this month", "this month", (_ts(2023, 11, 1), _ts(2023, 12, 1))),
+    ("this quarter", "this quarter", (_ts(2023, 10, 1), _ts(2024, 1, 1))),
+    ("2 years ago", "last year", (_ts(2021, 1, 1), _ts(2023, 1, 1))),
+    ("-3d", "-1d", (_ts(2023, 11, 12), _ts(2023, 11, 15))),
+    ("2023-Q2", "2023-Q2", (_ts(2023, 4, 1), _ts(2023, 7, 1))),
+    ("2023-02", "2023-02-28 13:30", (_ts(2023, 2, 1), _ts(2023, 2, 28, 13, 45))),  # :30 aligns to the quarter-hour
+    ("2023-02-28 13:31", "2023-02-28 13", (_ts(2023, 2, 28, 13, 31), _ts(2023, 2, 28, 14))),
+    ("1700000000", "1700000060000", (1700000000, 1700000060)),   # epoch seconds / milliseconds
+])
+def test_time_filter_expressions(frm, to, exp):
+    assert aql.parse_time_filter({"from": frm, "to": to}, NOW) == exp
+
+
+def test_time_bucketizers():
+    t = aql.Table("t", [aql.Column("ts", A.Uint32)])
+    col = t.ref("ts")
+
+    def floor(e, n):
+        return isinstance(e, E.Binary) and e.op == A.Floor and e.rhs.value == n
+
+    for s, n in (("hour", 3600), ("day", 86400), ("minute", 60), ("3m", 180), ("4 hours", 14400), ("quarter-hour", 900),
+                 ("30 minutes", 1800), ("12h", 43200)):
+        assert floor(aql.time_dimension_expr(s, col), n), s
+    for bad in ("7m", "5h", "2d", "fortnight", "61 minutes"):
+        with pytest.raises(aql.AQLError):
+            aql.time_dimension_expr(bad, col)
+    e = aql.time_dimension_expr("hour of day", col)            # floor(ts % 86400, 3600)
+    assert floor(e, 3600) and e.lhs.op == A.Mod and e.lhs.rhs.value == 86400
+    e = aql.time_dimension_expr("day of week", col)            # floor((ts - 4d) % 7d, 1d) / 86400.0
+    assert e.op == A.Divide and e.rhs.value == 86400.0 and e.lhs.lhs.lhs.op == A.Minus and e.lhs.lhs.lhs.rhs.value == 345600
+    assert aql.time_dimension_expr("time of day", col).op == A.Mod
+    assert aql.time_dimension_expr("week", col).op == A.GetWeekStart
+    assert aql.time_dimension_expr("quarter of year", col).op == A.GetQuarterOfYear
+    assert floor(aql.time_dimension_expr("10 minutes of day", col), 600)
+    with pytest.raises(aql.AQLError):
+        aql.time_dimension_expr("7 minutes of day", col)
+
+
+def test_expression_parser_and_measures():
+    t = aql.Table("trips", [aql.Column("request_at", A.Uint32), aql.Column("city_id", A.Uint16),
+                            aql.Column("status", A.Uint8, enum={"completed": 0, "canceled": 1}),
+                            aql.Column("fare", A.Float32), aql.Column("driver_hll", A.Uint32, hll=True)])
+    e = aql.parse_expression("fare > 5.5 and (trips.city_id != 0 or not status = 'canceled')", t)
+    assert e.op == A.And and e.lhs.op == A.GreaterThan and e.rhs.op == A.Or and e.rhs.rhs.op == A.Not
+    assert e.rhs.rhs.expr.rhs.value == 1                       # enum literal -> dictionary id
+    assert aql.parse_expression("status = 'never seen'", t).rhs.value == -1
+    assert aql.parse_expression("1 + 2 * 3", t).op == A.Plus   # precedence
+    with pytest.raises(aql.AQLError):
+        aql.parse_expression("fare = 'completed'", t)
+
+    def q(measure, **kw):
+        return aql.compile_query(dict({"table": "trips", "measures": [{"sqlExpression": measure}]}, **kw), t, NOW)
+
+    assert q("count(*)").agg_func == A.AGGR_SUM_UNSIGNED and q("count(*)").measure_bytes == 4
+    assert q("sum(fare)").agg_func == A.AGGR_SUM_FLOAT and q("sum(fare)").measure_bytes == 8
+    assert q("sum(city_id + 1)").agg_func == A.AGGR_SUM_UNSIGNED
+    assert q("min(fare)").agg_func == A.AGGR_MIN_FLOAT and q("max(city_id)").agg_func == A.AGGR_MAX_UNSIGNED
+    h = q("countdistincthll(city_id)")
+    assert h.is_hll and isinstance(h.measure, E.Unary) and h.measure.op == A.GetHLLValue
+    assert isinstance(q("countdistincthll(driver_hll)").measure, E.Col)    # already an hll column: no functor
+    assert isinstance(q("hll(driver_hll)").measure, E.Col)
+    for bad in ("fare", "sum(fare, 1)", "median(fare)", "hll(city_id)"):
+        with pytest.raises(ValueError):
+            q(bad)
+    with pytest.raises(aql.AQLError):
+        q("count(*)", joins=[{"table": "cities"}])
+    two_dims = q("count(*)", dimensions=[{"sqlExpression": "request_at", "timeBucketizer": "day"}, {"sqlExpression": "city_id"}])
+    assert two_dims.num_dims_per_width == [0, 0, 1, 1, 0]
