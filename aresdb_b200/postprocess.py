@@ -1,0 +1,165 @@
+"""Result post-processing: the binary dimension / measure vectors of an aggregate
+query -> the nested `{dim0: {dim1: value}}` result the reference returns as JSON
+(query/aql_postprocessor.go:34-170 flushResultBuffer + readMeasure :232-264, query/common/dimval.go:36-212
+ReadDimension / formatTimeDimension, query/common/aql_query_result.go:45-68 Set), and the HyperLogLog
+estimate of an hll query's register sets (query/common/hll.go:735-775 Compute).  UTC only.
+"""
+from __future__ import annotations
+
+import datetime as _dt
+import math
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import cabi as A
+from .aql import _regular_bucket_seconds, AQLError, SECONDS_PER_4_DAYS
+from .query import HLL_REGISTERS, HLLResult, QueryResult
+
+NULL_STRING = "NULL"
+
+
+@dataclass
+class DimensionMeta:
+    """What the reference keeps per query dimension: enum reverse dictionary and time formatting."""
+    enum_names: list | None = None
+    time_bucketizer: str | None = None     # set for time dimensions
+    time_unit: str = ""                    # "", "second", "minute", "hour", "day", "millisecond"
+
+
+def format_float32(x) -> str:
+    """strconv.FormatFloat(float64(float32), 'g', -1, 32): shortest digits that round-trip a float32;
+    exponent form when the decimal exponent is < -4 or >= 6 (strconv's rule for the shortest precision)."""
+    f = np.float32(x)
+    if np.isnan(f):
+        return "NaN"
+    if np.isinf(f):
+        return "+Inf" if f > 0 else "-Inf"
+    if f == 0:
+        return "-0" if np.signbit(f) else "0"
+    sci = np.format_float_scientific(f, unique=True, trim="-", exp_digits=2)   # d.ddde+XX
+    mant, exp = sci.split("e")
+    e = int(exp)
+    if e < -4 or e >= 6:
+        return f"{mant}e{'+' if e >= 0 else '-'}{abs(e):02d}"
+    return np.format_float_positional(f, unique=True, trim="-")
+
+
+def _utc(ts: int) -> _dt.datetime:
+    return _dt.datetime.fromtimestamp(ts, _dt.timezone.utc)
+
+
+def format_time_dimension(val: int, meta: DimensionMeta) -> str:
+    if meta.time_unit:
+        div = {"day": 86400, "hour": 3600, "minute": 60}.get(meta.time_unit)
+        if div:
+            val = int(val / div) if val < 0 else val // div   # Go integer division truncates
+        elif meta.time_unit == "millisecond":
+            val *= 1000
+        return str(val)
+    b = meta.time_bucketizer
+    if b == "time of day":
+        return _utc(val).strftime("%H:%M")
+    if b == "hour of day":
+        return _utc(val - val % 3600).strftime("%H:%M")
+    if b == "hour of week":
+        return _utc(val + SECONDS_PER_4_DAYS).strftime("%A %H:%M")
+    if b == "day of week":     # 1970-01-01 was a Thursday
+        return _utc(((val + 4) % 7) * 86400).strftime("%A")
+    try:
+        seconds = _regular_bucket_seconds(b)
+    except (AQLError, TypeError, AttributeError):
+        return str(val)
+    if seconds % 86400 == 0:
+        return _utc(val - val % 86400).strftime("%Y-%m-%d")
+    if seconds % 3600 == 0:
+        return _utc(val - val % 3600).strftime("%Y-%m-%d %H:00")
+    return _utc(val).strftime("%Y-%m-%d %H:%M")
+
+
+def read_dimension(raw, valid, data_type: int, meta: DimensionMeta | None) -> str | None:
+    """One dimension value of one result row -> its string form (None for NULL)."""
+    if not valid:
+        return None
+    is_time = meta is not None and meta.time_bucketizer is not None
+    if data_type == A.Float32:
+        if not is_time:
+            return format_float32(raw)
+        val = int(raw)                       # a time dimension that went through a float division
+    elif data_type in (A.Int64, A.Int32, A.Int16, A.Int8, A.Bool):
+        return str(int(raw))
+    elif data_type in (A.Uint32, A.Uint16, A.Uint8):
+        val = int(raw)
+    elif data_type == A.UUID:
+        h = bytes(raw).hex()
+        return f"{h[0:8]}-{h[8:12]}-{h[12:16]}-{h[16:20]}-{h[20:32]}"
+    else:
+        return None
+    names = meta.enum_names if meta else None
+    if names is not None and 0 <= val < len(names):
+        return names[val]
+    if is_time:
+        return format_time_dimension(val, meta)
+    return str(val)
+
+
+def nested_result(result: QueryResult, metas: list | None = None) -> dict:
+    """QueryResult -> nested dict keyed by the formatted dimension values, leaves = float measures."""
+    q = result.query
+    metas = metas or [None] * len(q.dimensions)
+    cols = result.decoded_dims()
+    out: dict = {}
+    for g in range(result.groups):
+        cur = out
+        for d in range(len(q.dimensions)):
+            v = cols[d][g]
+            key = read_dimension(v, v is not None, q.dim_types[d], metas[d])
+            key = NULL_STRING if key is None else key
+            if d == len(q.dimensions) - 1:
+                cur[key] = float(result.measures[g])
+            else:
+                cur = cur.setdefault(key, {})
+    return out
+
+
+# ---- HyperLogLog estimate ----------------------------------------------------------------------------
+HLL_THRESHOLD = 15500.0
+
+
+def hll_estimate(dense: np.ndarray) -> float:
+    """HLL.Compute on one register set (uint8[16384] of rho+1, 0 = empty).
+
+    The reference corrects the raw estimate with Google's empirical bias table when it lies in
+    (15500, 5 * 16384]; that table is data of the reference and is not reproduced here — in that range the
+    uncorrected estimate is returned (within ~1 % of the corrected one).  Below the threshold (linear
+    counting) and above 5m the value is exactly the reference's."""
+    m = float(HLL_REGISTERS)
+    nonzero = float(np.count_nonzero(dense))
+    rho = dense[dense != 0].astype(np.float64)          # registers store rho + 1 ... as the reference's Rho field
+    s = float(np.sum(np.exp2(-rho))) + (m - nonzero)
+    estimate = 0.7213 / (1 + 1.079 / m) * m * m / s
+    estimate_h = estimate
+    if nonzero < m:
+        estimate_h = m * math.log(m / (m - nonzero))
+    if estimate_h <= HLL_THRESHOLD:
+        estimate = estimate_h
+    return float(int(estimate))
+
+
+def hll_nested_result(result: HLLResult, metas: list | None = None) -> dict:
+    q = result.query
+    metas = metas or [None] * len(q.dimensions)
+    cols = result.dims.decoded_dims()
+    dense = result.dense_registers()
+    out: dict = {}
+    for g in range(result.groups):
+        cur = out
+        for d in range(len(q.dimensions)):
+            v = cols[d][g]
+            key = read_dimension(v, v is not None, q.dim_types[d], metas[d])
+            key = NULL_STRING if key is None else key
+            if d == len(q.dimensions) - 1:
+                cur[key] = hll_estimate(dense[result.dims.rows[g]])
+            else:
+                cur = cur.setdefault(key, {})
+    return out

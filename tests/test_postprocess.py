@@ -1,0 +1,95 @@
+"""Result post-processing rules (aresdb_b200/postprocess.py) against hand-derived expectations from the
+reference's formatting code (query/common/dimval.go:36-212, query/aql_postprocessor.go:232-264,
+query/common/hll.go:735-775)."""
+import math
+
+import numpy as np
+import pytest
+
+from aresdb_b200 import cabi as A, expr as E, postprocess as PP
+from aresdb_b200.postprocess import DimensionMeta as M
+from aresdb_b200.query import AggQuery, HLLResult, Measure, QueryResult
+
+TS = 1700012345   # 2023-11-15 01:39:05 UTC, a Wednesday
+
+
+@pytest.mark.parametrize("x,s", [(1.5, "1.5"), (100.0, "100"), (0.1, "0.1"), (1e6, "1e+06"), (123456.0, "123456"),
+                                 (1.0e-5, "1e-05"), (0.0001, "0.0001"), (3.4028235e38, "3.4028235e+38"), (0.0, "0"),
+                                 (86.074904, "86.074905"), (-2.5, "-2.5"), (1e21, "1e+21")])
+def test_float32_formatting_matches_go_shortest_g(x, s):
+    assert PP.format_float32(x) == s
+
+
+@pytest.mark.parametrize("bucketizer,val,exp", [
+    ("hour", TS - TS % 3600, "2023-11-15 01:00"),
+    ("day", TS - TS % 86400, "2023-11-15"),
+    ("minute", TS - TS % 60, "2023-11-15 01:39"),
+    ("15m", TS - TS % 900, "2023-11-15 01:30"),
+    ("4 hours", TS - TS % 14400, "2023-11-15 00:00"),
+    ("time of day", TS % 86400, "01:39"),
+    ("hour of day", (TS % 86400) // 3600 * 3600, "01:00"),
+    ("hour of week", ((TS - 345600) % 604800) // 3600 * 3600, "Wednesday 01:00"),
+    ("day of week", ((TS - 345600) % 604800) // 86400, "Wednesday"),
+    ("month", 1698796800, "1698796800"),           # irregular buckets stay epoch seconds
+])
+def test_time_dimension_formatting(bucketizer, val, exp):
+    assert PP.format_time_dimension(val, M(time_bucketizer=bucketizer)) == exp
+
+
+def test_time_unit_overrides_bucketizer():
+    assert PP.format_time_dimension(7200, M(time_bucketizer="hour", time_unit="hour")) == "2"
+    assert PP.format_time_dimension(7200, M(time_bucketizer="hour", time_unit="millisecond")) == "7200000"
+    assert PP.format_time_dimension(7200, M(time_bucketizer="hour", time_unit="second")) == "7200"
+
+
+def _result(q, dims, valid, measures):
+    """Builds the binary block of a QueryResult (capacity == groups) from per-dimension arrays."""
+    g = len(measures)
+    parts = []
+    for p, qi in enumerate(q.dim_order):
+        parts.append(np.ascontiguousarray(dims[qi]).view(np.uint8).reshape(-1))
+    for p, qi in enumerate(q.dim_order):
+        parts.append(np.asarray(valid[qi], np.uint8))
+    block = np.concatenate(parts)
+    return QueryResult(q, block, g, np.ascontiguousarray(measures).view(np.uint8).reshape(-1), g)
+
+
+def test_nested_result_with_enum_null_and_time_dims():
+    ts, city, status = E.Col(0, A.Uint32, "ts"), E.Col(1, A.Uint16, "city"), E.Col(2, A.Uint8, "status")
+    q = AggQuery([], [E.floor(ts, E.Lit(3600)), status, city], Measure("count"))
+    hours = np.array([TS - TS % 3600, TS - TS % 3600, TS - TS % 3600 + 3600], np.uint32)
+    res = _result(q, [hours, np.array([0, 1, 5], np.uint8), np.array([7, 7, 0], np.uint16)],
+                  [[1, 1, 1], [1, 1, 1], [1, 1, 0]], np.array([5, 4, 9], np.uint32))
+    out = PP.nested_result(res, [M(time_bucketizer="hour"), M(enum_names=["completed", "canceled"]), None])
+    assert out == {"2023-11-15 01:00": {"completed": {"7": 5.0}, "canceled": {"7": 4.0}},
+                   "2023-11-15 02:00": {"5": {"NULL": 9.0}}}     # id outside the dictionary prints as a number
+
+
+def test_measure_types_become_float64():
+    city, fare = E.Col(0, A.Uint16, "city"), E.Col(1, A.Float32, "fare")
+    q = AggQuery([], [city], Measure("sum", fare))
+    res = _result(q, [np.array([3], np.uint16)], [[1]], np.array([12.625], np.float64))
+    assert PP.nested_result(res) == {"3": 12.625}
+    q = AggQuery([], [city], Measure("max", E.Unary(A.Negate, city)))       # signed 4-byte measure
+    res = _result(q, [np.array([3], np.uint16)], [[1]], np.array([-3], np.int32))
+    assert PP.nested_result(res) == {"3": -3.0}
+
+
+def test_hll_estimate_linear_counting_and_large_range():
+    m = 16384.0
+    dense = np.zeros(16384, np.uint8)
+    assert PP.hll_estimate(dense) == 0.0
+    dense[:100] = 1                               # 100 registers hit: linear counting m * ln(m / (m - 100))
+    assert PP.hll_estimate(dense) == float(int(m * math.log(m / (m - 100))))
+    dense[:] = 12                                 # all registers rho+1 = 12: raw estimate, far above 5m
+    assert PP.hll_estimate(dense) == float(int(0.7213 / (1 + 1.079 / m) * m * m / (m * 2.0 ** -12)))
+
+
+def test_hll_nested_result():
+    city = E.Col(0, A.Uint16, "city")
+    q = AggQuery([], [city], Measure("countdistincthll", E.Col(1, A.Uint32, "x")))
+    block = np.concatenate([np.array([7, 9], np.uint16).view(np.uint8), np.array([1, 1], np.uint8)])
+    regs = np.concatenate([np.array([(3 << 16) | 5, (1 << 16) | 9], np.uint32).view(np.uint8),     # group 7: 2 registers
+                           np.array([(2 << 16) | 1], np.uint32).view(np.uint8)])                    # group 9: 1 register
+    r = HLLResult(q, 2, block, 2, regs, np.array([2, 1], np.uint16))
+    assert PP.hll_nested_result(r) == {"7": 2.0, "9": 1.0}
