@@ -168,13 +168,28 @@ __device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, u
   }
 }
 
-// Out-of-line tail of smemUpdate: `slot` is the first empty slot of the key's probe sequence (seen
-// `probe` steps from its home).  Claims it (or follows the winner of a lost race further down the
-// sequence).  Returns the key's slot, or 0xFFFFFFFF when the row has to go to the global table.
-static __device__ __noinline__ uint32_t smemClaim(unsigned long long *keys, uint32_t *claims, uint32_t mask, const DevTable &G,
-                                                  unsigned long long key, const uint64_t *roww, uint32_t slot, uint32_t probe) {
+// Two-choice placement.  A key lives in its first home slot h1 if that was free when the key arrived, else
+// in its second home h2, else (both taken: ~2 % of the keys at load 0.3) on the linear run that starts at
+// h2.  A lookup therefore costs one probe for ~85 % of the rows and exactly two for nearly all others —
+// what matters is that the SECOND step is a fixed short sequence, because with 18 live lanes some lane of
+// the warp needs it almost every time.  Slots are addressed by byte offset throughout.
+__device__ __forceinline__ uint32_t smemHome1(const SmemTable &T, unsigned long long key) {
+  const uint32_t x = ((uint32_t)key ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
+  return (x >> (29 - __popc(T.mask))) & (T.mask << 3);
+}
+__device__ __forceinline__ uint32_t smemHome2(const SmemTable &T, unsigned long long key, uint32_t off1) {
+  const uint32_t x = ((uint32_t)(key >> 32) ^ (uint32_t)key * 0xC2B2AE35u) * 0x27D4EB2Fu;
+  const uint32_t off2 = (x >> (29 - __popc(T.mask))) & (T.mask << 3);
+  return off2 != off1 ? off2 : (off1 + 8) & (T.mask << 3);
+}
+
+// Out-of-line insertion of a key the inlined lookup did not find: replays the placement rule with CAS.
+// Returns the key's slot, or 0xFFFFFFFF when the row has to go to the global table.
+static __device__ __noinline__ uint32_t smemInsert(unsigned long long *keys, uint32_t *claims, uint32_t mask, const DevTable &G,
+                                                   unsigned long long key, const uint64_t *roww, uint32_t off1, uint32_t off2) {
+  uint32_t slot = off1 >> 3;
 #pragma unroll 1
-  while (true) {
+  for (uint32_t step = 0; step < kSmemProbeLimit + 1; step++) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&keys[slot]);
     if (k == kEmptyKey) {
       k = atomicCAS(&keys[slot], kEmptyKey, key);
@@ -186,42 +201,37 @@ static __device__ __noinline__ uint32_t smemClaim(unsigned long long *keys, uint
       }
     }
     if (k == key) return slot;
-    if (++probe >= kSmemProbeLimit) return 0xFFFFFFFFu;
-    slot = (slot + 1) & mask;
+    slot = step == 0 ? off2 >> 3 : (slot + 1) & mask;
   }
+  return 0xFFFFFFFFu;
 }
 
-// Byte offset of a key's home slot: multiplicative hash, top bits (table positions only, never group
-// identity).  With a compile-time table size this is IMAD, LOP3, IMAD, SHF, LOP3.
-__device__ __forceinline__ uint32_t smemHomeOffset(const SmemTable &T, unsigned long long key) {
-  const uint32_t x = ((uint32_t)key ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
-  return (x >> (29 - __popc(T.mask))) & (T.mask << 3);
-}
-
-// Returns false when the row has to go to the global table (shared table full around its home).
-// Common case first: the key already sits in its home slot -> one LDS.64, one compare, one atomic.
-// Displaced keys (19 % at load 0.3) take a tight linear search; only an empty slot — a key this CTA
-// has not seen yet — leaves the inlined code.  Slots are addressed by byte offset throughout.
+// Returns false when the row has to go to the global table (no room on the key's probe sequence, or the
+// table is closed for new keys).
 __device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
                                            const uint64_t *roww, uint64_t val, bool allowClaim) {
   const uint8_t *kb = reinterpret_cast<const uint8_t *>(T.keys);
-  const uint32_t offMask = T.mask << 3;
-  uint32_t off = smemHomeOffset(T, key);
+  const uint32_t off1 = smemHome1(T, key);
+  uint32_t off = off1;
   unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
   if (k != key) {
-    uint32_t probe = 0;
+    const uint32_t off2 = smemHome2(T, key, off1);
     if (k != kEmptyKey) {
+      off = off2;
+      k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
+      if (k != key && k != kEmptyKey) {   // both homes taken by other keys: the run behind h2
+        uint32_t probe = 1;
 #pragma unroll 1
-      for (;;) {
-        probe++;
-        off = (off + 8) & offMask;
-        k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
-        if (k == key || k == kEmptyKey || probe >= kSmemProbeLimit - 1) break;
+        for (;;) {
+          off = (off + 8) & (T.mask << 3);
+          k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
+          if (k == key || k == kEmptyKey || ++probe >= kSmemProbeLimit) break;
+        }
       }
     }
     if (k != key) {
-      if (k != kEmptyKey || !allowClaim) return false;   // probe limit reached inside a long run / table closed
-      const uint32_t slot = smemClaim(T.keys, T.claims, T.mask, G, key, roww, off >> 3, probe);
+      if (k != kEmptyKey || !allowClaim) return false;
+      const uint32_t slot = smemInsert(T.keys, T.claims, T.mask, G, key, roww, off1, off2);
       if (slot == 0xFFFFFFFFu) return false;
       off = slot << 3;
     }
