@@ -145,3 +145,57 @@ def test_fused_small_and_empty_batches():
     q0 = AggQuery([E.eq(STATUS, E.Lit(99))], [CITY], Measure("count"))
     hbs = [synth.generate_batch(0, 5000)]
     assert run_fused(eng, q0, hbs).groups == 0
+
+
+# ---- archive-style batch: run-length encoded sort columns, index space = runs of the first one ----------
+def _archive_batch(be, seed, runs=6000):
+    """An archive batch as the reference lays it out: the first sort column is RLE (mode 3) and its
+    cumulative counts are the batch's base counts — one index position per run; a second, finer sort
+    column is RLE with its own counts; unsorted columns carry one value per index position.  SUM / COUNT
+    measures are multiplied by the run length (query/iterator.hpp:626-645)."""
+    rng = np.random.default_rng(seed)
+    lens = rng.integers(1, 9, runs)
+    base = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint32)          # runs + 1 cumulative counts
+    total = int(base[-1])
+    city = np.sort(rng.integers(1, 40, runs)).astype(np.uint16)
+    fine_cuts = np.sort(rng.choice(np.arange(1, total), size=runs * 2, replace=False))
+    fine = np.concatenate([[0], fine_cuts, [total]]).astype(np.uint32)
+    status = rng.integers(0, 4, len(fine) - 1).astype(np.uint8)
+    ts = (synth.BASE_TS + rng.integers(0, 3 * 86400, runs)).astype(np.uint32)
+    fare = (rng.integers(0, 6400, runs) / 64.0).astype(np.float32)
+    cols, keep = [], []
+    for dt, v, ok, counts in ((A.Uint32, ts, rng.random(runs) > 0.02, None), (A.Uint16, city, None, base),
+                              (A.Uint8, status, rng.random(len(status)) > 0.05, fine), (A.Float32, fare, rng.random(runs) > 0.02, None)):
+        buf, vp = columns.make_column(be.space, dt, v, valid=ok, counts=counts)
+        cols.append(vp)
+        keep.append(buf)
+    bc = be.put(base)
+    return Batch(cols, runs, base_counts=bc, start_count=0, keep=keep)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["cfg2", "cfg3_count", "int_sum", "min_city"])
+def test_fused_plan_on_archive_style_batches(name):
+    """Mode-3 columns and base counts go through ExecuteBatchPlan too (generic kernel: positional run
+    search per access) and agree with the reference sequence, including the x run-length of SUM / COUNT."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    q = queries()[name]
+    exp_ex, got_ex = LegacyBatchExecutor(orc.lib, orc.space, q), FusedBatchExecutor(eng.lib, eng.space, q)
+    for seed in (1, 2):
+        exp_ex.process_batch(_archive_batch(orc, seed))
+        got_ex.process_batch(_archive_batch(eng, seed))
+    exp, got = exp_ex.result(), got_ex.result()
+    got_ex.close()
+    assert exp.groups > 0
+    assert_same_result(got, exp, ctx=f"archive/{name}")
+
+
+@pytest.mark.parametrize("name", ["cfg2", "cfg3_count"])
+def test_archive_style_batches_oracle_vs_reference(name):
+    ref, orc = H.get_backend("ref"), H.get_backend("oracle")
+    q = queries()[name]
+    a, b = LegacyBatchExecutor(ref.lib, ref.space, q), LegacyBatchExecutor(orc.lib, orc.space, q)
+    a.process_batch(_archive_batch(ref, 1))
+    b.process_batch(_archive_batch(orc, 1))
+    assert a.result().groups > 0
+    assert_same_result(b.result(), a.result(), ctx=f"archive/{name}")
