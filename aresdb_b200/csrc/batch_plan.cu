@@ -826,6 +826,9 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
     int dt = bp.Columns[c].DataType;
     P.cols[c].width = dt == Bool ? 0 : (dt == Int8 || dt == Uint8) ? 1 : (dt == Int16 || dt == Uint16) ? 2
                     : (dt == Int64 || dt == Uint64) ? 8 : dt == UUID ? 16 : 4;
+    P.cols[c].used = 0;      // set below by the instructions that read the column: only those are staged
+    P.cols[c].staged = 0;
+    P.cols[c].hasNulls = 0;
   }
   const DimLayout &RL = st->rowLayout;
   std::vector<uint8_t> stack;
@@ -847,6 +850,7 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
     if (pi.NumOperands == 2 && pi.B.Kind != PLAN_OPERAND_STACK) bcls = operandClassOf(pi.B, bp, stack);
     auto fill = [&](const PlanOperand &o, uint8_t &kind, uint8_t &col, uint8_t &valid, uint32_t &k) {
       kind = o.Kind; col = o.Column; valid = o.ConstValid;
+      if (o.Kind == PLAN_OPERAND_COLUMN) P.cols[o.Column].used = 1;
       if (o.Kind == PLAN_OPERAND_CONST) {
         if (o.ConstType == ConstFloat) memcpy(&k, &o.Const.FloatVal, 4); else k = (uint32_t)o.Const.IntVal;
       }
@@ -941,7 +945,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   uint32_t rowBits = 0;
   for (int c = 0; c < P.ncols; c++) {
     DevColumn &col = P.cols[c];
-    if (col.in.mode == 0) continue;
+    if (col.in.mode == 0 || !col.used) continue;
     if (col.in.mode == 3) { canStage = false; break; }  // RLE: positional search, direct path
     if (col.width > 4) continue;                          // wide dims are read directly
     const uintptr_t v = reinterpret_cast<uintptr_t>(col.in.base + col.in.valuesOff);
@@ -965,7 +969,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
     size_t stage = 0;
     for (int c = 0; c < P.ncols; c++) {
       const DevColumn &col = P.cols[c];
-      if (col.in.mode == 0 || col.width > 4) continue;
+      if (col.in.mode == 0 || !col.used || col.width > 4) continue;
       stage += ((col.width ? (size_t)tr * col.width : tr / 8 + 16) + 15) / 16 * 16;
       if (col.in.mode == 2) stage += (tr / 8 + 16 + 15) / 16 * 16;
     }
@@ -990,7 +994,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   if (tileRows) {
     for (int c = 0; c < P.ncols; c++) {
       DevColumn &col = P.cols[c];
-      if (col.in.mode == 0 || col.width > 4) continue;
+      if (col.in.mode == 0 || !col.used || col.width > 4) continue;
       col.staged = 1;
       anyStaged = true;
       col.smemValues = (uint32_t)stageBytes;

@@ -173,14 +173,16 @@ __device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, u
 // h2.  A lookup therefore costs one probe for ~85 % of the rows and exactly two for nearly all others —
 // what matters is that the SECOND step is a fixed short sequence, because with 18 live lanes some lane of
 // the warp needs it almost every time.  Slots are addressed by byte offset throughout.
-__device__ __forceinline__ uint32_t smemHome1(const SmemTable &T, unsigned long long key) {
-  const uint32_t x = ((uint32_t)key ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
+__device__ __forceinline__ uint32_t smemHashWord(unsigned long long key) {
+  return ((uint32_t)key ^ (uint32_t)(key >> 32) * 0x85EBCA6Bu) * 0x9E3779B1u;
+}
+// h1: top bits of the hash word.  h2: h1 XOR a non-zero displacement taken from the word's low bits
+// (three instructions, never equal to h1).
+__device__ __forceinline__ uint32_t smemHome1(const SmemTable &T, uint32_t x) {
   return (x >> (29 - __popc(T.mask))) & (T.mask << 3);
 }
-__device__ __forceinline__ uint32_t smemHome2(const SmemTable &T, unsigned long long key, uint32_t off1) {
-  const uint32_t x = ((uint32_t)(key >> 32) ^ (uint32_t)key * 0xC2B2AE35u) * 0x27D4EB2Fu;
-  const uint32_t off2 = (x >> (29 - __popc(T.mask))) & (T.mask << 3);
-  return off2 != off1 ? off2 : (off1 + 8) & (T.mask << 3);
+__device__ __forceinline__ uint32_t smemHome2(const SmemTable &T, uint32_t x, uint32_t off1) {
+  return off1 ^ (((x << 3) & (T.mask << 3)) | 8u);
 }
 
 // Out-of-line insertion of a key the inlined lookup did not find: replays the placement rule with CAS.
@@ -211,11 +213,12 @@ static __device__ __noinline__ uint32_t smemInsert(unsigned long long *keys, uin
 __device__ __forceinline__ bool smemUpdate(const SmemTable &T, const DevTable &G, AggOp op, unsigned long long key,
                                            const uint64_t *roww, uint64_t val, bool allowClaim) {
   const uint8_t *kb = reinterpret_cast<const uint8_t *>(T.keys);
-  const uint32_t off1 = smemHome1(T, key);
+  const uint32_t x = smemHashWord(key);
+  const uint32_t off1 = smemHome1(T, x);
   uint32_t off = off1;
   unsigned long long k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);
   if (k != key) {
-    const uint32_t off2 = smemHome2(T, key, off1);
+    const uint32_t off2 = smemHome2(T, x, off1);
     if (k != kEmptyKey) {
       off = off2;
       k = *reinterpret_cast<const volatile unsigned long long *>(kb + off);

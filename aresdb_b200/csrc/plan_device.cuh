@@ -24,7 +24,7 @@ struct DevColumn {
   uint8_t width;           // bytes per value, 0 for bit-packed bool
   uint8_t staged;          // values staged
   uint8_t hasNulls;        // mode 2 bitmap staged
-  uint8_t pad;
+  uint8_t used;            // some instruction reads the column (unreferenced columns of the batch cost nothing)
 };
 
 struct DevInst {

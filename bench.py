@@ -166,7 +166,7 @@ def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: in
         import build_oracle
         build_oracle.build()
     cores = os.cpu_count() or 1
-    workers = workers or max(1, min(cores, 128))
+    workers = workers or max(1, min(cores, 64))   # one per physical core: 128 SMT workers measured 30-45 % slower on the GPU box
     ctx = mp.get_context("spawn")
     with ctx.Pool(workers) as pool:
         t0 = time.perf_counter()
