@@ -242,7 +242,7 @@ _TOKEN = re.compile(r"\s*(?:(\d+\.\d*|\.\d+|\d+)|'((?:[^']|'')*)'|([A-Za-z_][A-Z
 _BINARY = {"or": (1, A.Or), "and": (2, A.And), "=": (4, A.Equal), "!=": (4, A.NotEqual), "<>": (4, A.NotEqual),
            "<": (4, A.LessThan), "<=": (4, A.LessThanOrEqual), ">": (4, A.GreaterThan), ">=": (4, A.GreaterThanOrEqual),
            "+": (5, A.Plus), "-": (5, A.Minus), "*": (6, A.Multiply), "/": (6, A.Divide), "%": (6, A.Mod)}
-AGGREGATES = ("count", "sum", "min", "max", "hll", "countdistincthll")
+AGGREGATES = ("count", "sum", "min", "max", "avg", "hll", "countdistincthll")
 
 
 @dataclass

@@ -332,6 +332,12 @@ __device__ __forceinline__ void processQuad(const DevPlan &P, const DevTable &G,
         for (int r = 0; r < R; r++) {
           if ((rv >> r) & 1) {
             uint64_t o = cvt(res[r], (ValClass)I.rclass, (ValClass)I.oclass);
+            if (P.aggOp == OP_AVG) {  // (float average, count) pair, as assignAvg packs it (query/iterator.hpp:636-645)
+              uint32_t cnt = 1;
+              if (P.baseCounts != nullptr && (uint32_t)r < nrows) cnt = P.baseCounts[row0 + r + 1] - P.baseCounts[row0 + r];
+              meas[r] = ((uint64_t)cnt << 32) | (uint32_t)cvt(o, (ValClass)I.oclass, VC_F32);
+              continue;
+            }
             if (!P.skipCount && P.baseCounts != nullptr && (uint32_t)r < nrows) {
               uint32_t cnt = P.baseCounts[row0 + r + 1] - P.baseCounts[row0 + r];
               switch ((ValClass)I.oclass) {
@@ -714,8 +720,7 @@ static void describeState(AggState *st, const AggSpec &spec) {
   st->keyMode = st->rowLayout.rowBytes <= 8 ? KEY_PACKED : KEY_HASHED;
   st->measClass = measureClassOf(spec.MeasureDataType);
   int bytes = (st->measClass == VC_I64 || st->measClass == VC_F64) ? 8 : 4;
-  if (spec.AggFunc == AGGR_AVG_FLOAT)
-    throw EngineError("the AVG aggregate is not available on the fused path; use the per-node entry points");
+  if (spec.AggFunc == AGGR_AVG_FLOAT && bytes != 8) throw EngineError("an AVG measure is 8 bytes (average, count)");
   st->hll = spec.AggFunc == AGGR_HLL;
   st->hllDense = st->hll && spec.ExpectedGroups <= kHllDenseMaxGroups;
   if (st->hll) {

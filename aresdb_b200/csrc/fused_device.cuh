@@ -154,6 +154,7 @@ __device__ __forceinline__ void smemAtomic(AggOp op, unsigned long long *addr, u
     case OP_MIN_I32: atomicMin(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
     case OP_MAX_U32: atomicMax(reinterpret_cast<unsigned int *>(addr), (unsigned int)v); break;
     case OP_MAX_I32: atomicMax(reinterpret_cast<int *>(addr), (int)(uint32_t)v); break;
+    case OP_AVG: aggAtomic(op, addr, v); break;  // 64-bit CAS loop around the rolling-average combine
     default: {  // float min / max
       unsigned int *a = reinterpret_cast<unsigned int *>(addr);
       unsigned int old = *a, assumed;

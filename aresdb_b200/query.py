@@ -18,7 +18,7 @@ from . import expr as E
 
 @dataclass
 class Measure:
-    kind: str                 # "count" | "sum" | "min" | "max" | "hll" | "countdistincthll"
+    kind: str                 # "count" | "sum" | "min" | "max" | "avg" | "hll" | "countdistincthll"
     expr: E.Expr | None = None
 
 
@@ -50,6 +50,12 @@ class AggQuery:
                 raise ValueError("expect 1 argument to be a valid hll column")
             self.measure = col if measure.kind == "hll" else E.resolve(E.Unary(A.GetHLLValue, col))
             self.agg_func, self.measure_bytes = A.AGGR_HLL, 4
+        elif measure.kind == "avg":
+            # 4 bytes for the average and 4 for the count; always the float aggregate (aql_compiler.go:1212-1216)
+            self.measure = E.resolve(measure.expr)
+            if self.measure.type not in (E.Type.Unsigned, E.Type.Signed, E.Type.Float):
+                raise ValueError("unsupported input type for avg")
+            self.agg_func, self.measure_bytes = A.AGGR_AVG_FLOAT, 8
         else:
             self.measure = E.resolve(measure.expr)
             t = self.measure.type
@@ -142,6 +148,10 @@ class QueryResult:
         if query.agg_func == A.AGGR_SUM_UNSIGNED and query.measure_bytes == 8:
             np_meas = np.uint64
         self.measures = measures_raw[:groups * query.measure_bytes].view(np_meas).copy()
+        self.counts = None
+        if query.agg_func == A.AGGR_AVG_FLOAT:   # packed (float average, uint32 count); the average is what is reported
+            pairs = measures_raw[:groups * 8].view(np.uint32).reshape(groups, 2)
+            self.measures, self.counts = pairs[:, 0].copy().view(np.float32), pairs[:, 1].copy()
         self.dim_values: list[np.ndarray] = [None] * len(query.dimensions)
         self.dim_valid: list[np.ndarray] = [None] * len(query.dimensions)
         n = len(query.layout_widths)

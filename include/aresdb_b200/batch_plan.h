@@ -90,7 +90,8 @@ enum AresReduceMode {
 typedef struct {
   uint8_t NumDimsPerDimWidth[NUM_DIM_WIDTH]; /* as DimensionVector */
   uint8_t Reserved[3];
-  int32_t AggFunc;         /* enum AggregateFunction: SUM/MIN/MAX families, or AGGR_HLL (measure = Uint32
+  int32_t AggFunc;         /* enum AggregateFunction: SUM/MIN/MAX families, AGGR_AVG_FLOAT (8-byte (float average, count)
+                            * pairs combined with the reference's rolling average), or AGGR_HLL (measure = Uint32
                             * rho << 16 | reg values; group identity and results as HyperLogLog's,
                             * query/hll.cu:21-290; read the result with AggStateFinalizeHLL) */
   int32_t MeasureDataType; /* enum DataType of one measure element: Int32/Uint32/Float32/Int64/Float64 */

@@ -61,3 +61,11 @@ def test_hll_queries_specialise_in_both_modes():
         size, src = _dry_run(lib, q)
         assert size > 0, name
         assert "#define JIT_HLL 2" in src and "#define JIT_DENSE_SLOTS 8192" in src
+
+
+def test_avg_queries_specialise():
+    lib = A.load_engine()
+    for name, q in T.avg_queries().items():
+        size, src = _dry_run(lib, q)
+        assert size > 0, name
+        assert "(1ull << 32)" in src      # (float average, count = 1) packing of the measure

@@ -199,3 +199,58 @@ def test_archive_style_batches_oracle_vs_reference(name):
     b.process_batch(_archive_batch(orc, 1))
     assert a.result().groups > 0
     assert_same_result(b.result(), a.result(), ctx=f"archive/{name}")
+
+
+# ---- AVG: (float average, count) pairs combined with the reference's rolling average -------------------
+def avg_queries():
+    return {
+        "avg_fare_by_city": AggQuery([E.eq(STATUS, E.Lit(1))], [CITY], Measure("avg", FARE)),
+        "avg_city_by_hour": AggQuery([], [E.floor(TS, E.Lit(3600)), STATUS], Measure("avg", CITY)),   # integer input
+    }
+
+
+def assert_same_avg(got, exp, ctx="", exact=False):
+    """Counts are exact.  The rolling average (avg_l / n * n_l + avg_r / n * n_r in float32,
+    query/functor.hpp:1414-1436) depends on the order rows meet, which differs between a sequential
+    reduce, a shuffle tree and atomics: averages are compared to 2e-5 relative unless the order is the same."""
+    assert got.rows == exp.rows, f"{ctx}: dimension rows / order differ"
+    assert got.counts.tolist() == exp.counts.tolist(), f"{ctx}: counts differ"
+    if exact:
+        assert got.measures.tobytes() == exp.measures.tobytes(), f"{ctx}: averages differ"
+    else:
+        np.testing.assert_allclose(got.measures, exp.measures, rtol=2e-5, atol=1e-6, err_msg=ctx)
+
+
+@pytest.mark.parametrize("name", list(avg_queries()))
+def test_avg_sequence_oracle_vs_reference(name, host_batches):
+    ref, orc = H.get_backend("ref"), H.get_backend("oracle")
+    q = avg_queries()[name]
+    exp, got = run_legacy(ref, q, host_batches), run_legacy(orc, q, host_batches)
+    assert exp.groups > 0 and exp.counts.sum() > 0
+    assert_same_avg(got, exp, name, exact=True)
+    # and the averages are what they should be
+    hb = host_batches
+    if name == "avg_fare_by_city":
+        city = np.concatenate([b.values[1] for b in hb]); ok = np.concatenate([b.valid[1] for b in hb]).astype(bool)
+        st = np.concatenate([b.values[2] for b in hb]); st_ok = np.concatenate([b.valid[2] for b in hb]).astype(bool)
+        fare = np.concatenate([b.values[3] for b in hb]).astype(np.float64); f_ok = np.concatenate([b.valid[3] for b in hb]).astype(bool)
+        keep = st_ok & (st == 1)
+        cities = dict(zip([d for d in exp.decoded_dims()[0]], zip(exp.measures.tolist(), exp.counts.tolist())))
+        for c in (1, 7, 33):
+            sel = keep & ok & (city == c)
+            avg, cnt = cities[c]
+            # NULL fares enter as (0, count 0): they do not move the average
+            assert cnt == int((sel & f_ok).sum())
+            assert abs(avg - fare[sel & f_ok].mean()) < 1e-3
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(avg_queries()))
+def test_avg_on_b200(name, host_batches):
+    """Per-node entry points and the fused plan (AVG accumulates through a 64-bit CAS around the same
+    rolling-average combine)."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    q = avg_queries()[name]
+    exp = run_legacy(orc, q, host_batches)
+    assert_same_avg(run_legacy(eng, q, host_batches), exp, f"{name}/legacy")
+    assert_same_avg(run_fused(eng, q, host_batches), exp, f"{name}/fused")
