@@ -125,3 +125,20 @@ def all_gather_results_host(dist, result: QueryResult) -> list[dict]:
     gathered = [None] * world
     dist.all_gather_object(gathered, result.as_dict())
     return gathered
+
+
+def merge_hll_results_host(parts: list[dict]) -> dict:
+    """hll queries: per-rank {packed dim row: uint8[16384] registers} maps folded with the per-register
+    maximum (broker/result_merge.go: HLL merge = Merge of the register sets)."""
+    out: dict = {}
+    for part in parts:
+        for k, regs in part.items():
+            out[k] = np.maximum(out[k], regs) if k in out else regs
+    return out
+
+
+def all_gather_hll_host(dist, result) -> list[dict]:
+    """all_gather_object of the dense register maps of an HLLResult."""
+    gathered = [None] * dist.get_world_size()
+    dist.all_gather_object(gathered, result.dense_registers())
+    return gathered

@@ -32,6 +32,13 @@ def _worker(rank, world, port, out_dir):
         merged = sharding.merge_results_host(q, sharding.all_gather_results_host(dist, local))
         full = T.run_legacy(orc, q, hbs).as_dict()
         ok = ok and merged.keys() == full.keys() and all(np.array_equal(merged[k], full[k]) for k in full)
+    # hll queries: per-register max of the ranks' register sets == the single-process run over all batches
+    import test_hll_pipeline as HP
+    for name, q in HP.hll_queries().items():
+        mine = [hbs[i] for i in sharding.assign_batches(len(hbs), world, rank)]
+        merged = sharding.merge_hll_results_host(sharding.all_gather_hll_host(dist, HP.run_hll_query(orc, q, mine)))
+        full = HP.run_hll_query(orc, q, hbs).dense_registers()
+        ok = ok and merged.keys() == full.keys() and all(np.array_equal(merged[k], full[k]) for k in full)
     (Path(out_dir) / f"rank{rank}.txt").write_text("ok" if ok else "mismatch")
     dist.destroy_process_group()
 
