@@ -69,3 +69,21 @@ def test_avg_queries_specialise():
         size, src = _dry_run(lib, q)
         assert size > 0, name
         assert "(1ull << 32)" in src      # (float average, count = 1) packing of the measure
+
+
+def test_on_disk_cubin_cache(tmp_path, monkeypatch):
+    """ARESDB_B200_JIT_CACHE_DIR: the second compile of the same shape is served from disk; an entry whose
+    stored source differs (hash collision / stale build) is ignored."""
+    import time
+    monkeypatch.setenv("ARESDB_B200_JIT_CACHE_DIR", str(tmp_path))
+    lib = A.load_engine()
+    q = T.queries()["cfg3_sum"]
+    t0 = time.perf_counter(); size1, _ = _dry_run(lib, q); t1 = time.perf_counter()
+    size2, _ = _dry_run(lib, q); t2 = time.perf_counter()
+    files = sorted(p.name for p in tmp_path.iterdir())
+    assert len(files) == 2 and files[0].endswith(".cu") and files[1].endswith(".cubin")
+    assert size1 == size2 > 0 and (t2 - t1) < 0.5 * (t1 - t0)
+    src = tmp_path / files[0]
+    src.write_bytes(src.read_bytes() + b"// tampered")
+    size3, _ = _dry_run(lib, q)
+    assert size3 == size1     # recompiled, not served from the mismatching entry
