@@ -87,3 +87,35 @@ def test_on_disk_cubin_cache(tmp_path, monkeypatch):
     src.write_bytes(src.read_bytes() + b"// tampered")
     size3, _ = _dry_run(lib, q)
     assert size3 == size1     # recompiled, not served from the mismatching entry
+
+
+def test_mixed_column_modes_and_wide_dims_specialise():
+    """Mode-0 / mode-1 columns, bool columns with a bit offset and 8- / 16-byte dimension columns."""
+    lib = A.load_engine()
+    fn = lib.alg.AresJitDryRun
+    fn.argtypes = [A.AggSpec, C.POINTER(A.BatchPlan), C.POINTER(C.c_char_p)]
+    fn.restype = A.CGoCallResHandle
+    rows = 100000
+    for name, q in T.mixed_queries().items():
+        p = A.BatchPlan()
+        insts = q.plan_instructions()
+        p.NumInsts = len(insts)
+        for i, pi in enumerate(insts):
+            p.Insts[i] = pi
+        base = 0x7F0000000000
+        specs = [(A.Uint32, 1, 0), None, (A.Bool, 2, 3), (A.Float32, 2, 0), (A.Int64, 2, 0), (A.UUID, 2, 0)]
+        p.NumColumns = len(specs)
+        for i, sp in enumerate(specs):
+            if sp is None:
+                p.Columns[i] = columns.constant_column(A.Uint16, 7, True)
+            else:
+                dt, mode, sb = sp
+                p.Columns[i] = columns.slice_of(base + i * (1 << 32), dt, rows, 0, 64 * 200, mode, sb)
+        p.NumRows = rows
+        src = C.c_char_p()
+        h = fn(q.agg_spec(), C.byref(p), C.byref(src))
+        assert not h.pStrErr, C.string_at(h.pStrErr).decode()
+        if name == "uuid_dim":   # reads only a 16-byte and a constant column: nothing to stage, the generic kernel runs it
+            assert int(h.res or 0) == 0
+        else:
+            assert int(h.res or 0) > 0, f"{name} was not eligible for specialisation"
