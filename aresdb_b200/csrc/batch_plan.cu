@@ -1110,7 +1110,7 @@ static void denseCarried(AggState *st, cudaStream_t s, DenseCarried &out, bool c
   checkLastError("compactGroups");
   Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
   iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);
-  radixSortPairs<uint32_t>(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 0, 64, s);
+  sortKeyIndexPairs(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 64, s);
   Scratch counts(sizeof(uint32_t) * (size_t)n, s), offsets(sizeof(uint32_t) * ((size_t)n + 1), s);
   hllDenseCountKernel<<<n, 256, 0, s>>>(st->table.regs, slotOf.as<uint32_t>(), order.as<uint32_t>(), counts.as<uint32_t>());
   checkLastError("hllDenseCount");
@@ -1183,8 +1183,7 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
     ARES_CUDA(cudaStreamSynchronize(s));
     return n;
   }
-  radixSortPairs<uint32_t>(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 0,
-                           st->hashBits, s);
+  sortKeyIndexPairs(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, st->hashBits, s);
   Scratch rep(sizeof(uint32_t) * (size_t)n, s);
   Scratch mergedVals((size_t)width * n, s);
   const int g = reduceByHash(hash.as<uint64_t>(), order.as<uint32_t>(), vals.as<uint8_t>(), width, st->op, n,

@@ -178,6 +178,60 @@ void radixSortPairs(uint64_t *keys, V *vals, uint64_t *keysTmp, V *valsTmp, int 
   }
 }
 
+// One CTA: bucket by the top 8 key bits (unordered scatter into the tmp arrays), then every element finds its
+// rank inside its bucket by comparing (key, index) with the bucket's other members.  With hash keys a bucket
+// holds n / 256 elements, so the rank loop is short; a degenerate bucket only costs time, never correctness.
+__global__ void __launch_bounds__(1024)
+smallSortKernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ index, uint64_t *__restrict__ tmpK,
+                uint32_t *__restrict__ tmpI, int n, int shift) {
+  __shared__ uint32_t cnt[kRadix], off[kRadix + 1], cur[kRadix];
+  __shared__ uint32_t sWarp[1024 / 32 + 1];
+  if (threadIdx.x < kRadix) { cnt[threadIdx.x] = 0; cur[threadIdx.x] = 0; }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) atomicAdd(&cnt[(uint32_t)(keys[i] >> shift) & (kRadix - 1)], 1u);
+  __syncthreads();
+  {
+    uint32_t total;
+    const uint32_t c = threadIdx.x < kRadix ? cnt[threadIdx.x] : 0;
+    const uint32_t excl = blockExclusiveScan<1024>(c, sWarp, &total);
+    if (threadIdx.x < kRadix) off[threadIdx.x] = excl;
+    if (threadIdx.x == 0) off[kRadix] = total;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const uint64_t k = keys[i];
+    const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
+    const uint32_t p = off[d] + atomicAdd(&cur[d], 1u);
+    tmpK[p] = k;
+    tmpI[p] = index[i];
+  }
+  __syncthreads();   // the CTA's own global writes are visible to it after the barrier
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const uint64_t k = tmpK[i];
+    const uint32_t v = tmpI[i];
+    const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
+    const uint32_t lo = off[d], hi = off[d + 1];
+    uint32_t rank = 0;
+    for (uint32_t j = lo; j < hi; j++) {
+      const uint64_t kj = tmpK[j];
+      rank += (kj < k) || (kj == k && tmpI[j] < v);
+    }
+    keys[lo + rank] = k;
+    index[lo + rank] = v;
+  }
+}
+
+void sortKeyIndexPairs(uint64_t *keys, uint32_t *index, uint64_t *keysTmp, uint32_t *indexTmp, int n, int keyBits,
+                       cudaStream_t s) {
+  if (n <= 1) return;
+  if (n > kSmallSortMax || keyBits < kRadixBits) {
+    radixSortPairs<uint32_t>(keys, index, keysTmp, indexTmp, n, 0, keyBits, s);
+    return;
+  }
+  smallSortKernel<<<1, 1024, 0, s>>>(keys, index, keysTmp, indexTmp, n, keyBits - kRadixBits);
+  checkLastError("sortKeyIndexPairs");
+}
+
 template void radixSortPairs<uint32_t>(uint64_t *, uint32_t *, uint64_t *, uint32_t *, int, int, int, cudaStream_t);
 template void radixSortPairs<uint64_t>(uint64_t *, uint64_t *, uint64_t *, uint64_t *, int, int, int, cudaStream_t);
 

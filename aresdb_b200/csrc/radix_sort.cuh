@@ -27,6 +27,14 @@ template <typename V>
 void radixSortPairs(uint64_t *keys, V *vals, uint64_t *keysTmp, V *valsTmp, int n, int beginBit, int endBit,
                     cudaStream_t s);
 
+// Sort of (key, index) pairs whose indices are pairwise distinct (finalize sorts group hashes with an iota
+// payload): ties are broken by the index, so the result equals the stable sort of the iota-ordered input.
+// n <= kSmallSortMax runs as ONE launch of one CTA (top-digit bucketing in shared memory, then an in-bucket
+// rank sort) instead of 3 launches per 8-bit digit; larger inputs take radixSortPairs.
+constexpr int kSmallSortMax = 32768;
+void sortKeyIndexPairs(uint64_t *keys, uint32_t *index, uint64_t *keysTmp, uint32_t *indexTmp, int n, int keyBits,
+                       cudaStream_t s);
+
 // Bytes of scratch radixSortPairs needs besides the ping-pong buffers.
 size_t radixSortScratchBytes(int n);
 
