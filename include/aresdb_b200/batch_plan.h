@@ -70,7 +70,7 @@ typedef struct {
 /* One batch of one table shard: column slices already resident on the device. */
 typedef struct {
   VectorPartySlice Columns[ARES_MAX_PLAN_COLUMNS];
-  int32_t NumColumns;
+  int32_t NumColumns; /* at most 16 per call: list the columns the query reads (what transferBatch copies), not the table */
   PlanInst Insts[ARES_MAX_PLAN_INSTS];
   int32_t NumInsts;
   /* Index space of the batch = rows of the first column (as in the reference).  BaseCounts
@@ -108,7 +108,9 @@ extern "C" {
 CGoCallResHandle AggStateCreate(AggSpec spec, void *cudaStream, int device);
 
 /* Fused preExec+filter+project+reduce of one batch into `state`.  Asynchronous on
- * cudaStream: nothing is returned to the host, nothing is synchronised (res = 0). */
+ * cudaStream: nothing is returned to the host, nothing is synchronised (res = 0).  A state is used from
+ * one stream at a time (the batches of a query follow each other, as in the reference); different states
+ * run concurrently on different streams / devices. */
 CGoCallResHandle ExecuteBatchPlan(void *state, const BatchPlan *plan, void *cudaStream, int device);
 
 /* Folds already-reduced rows (a DimensionVector block + measure vector, e.g. the carried
