@@ -16,6 +16,7 @@
 // each group's packed dimension row with the reference's murmur3, sorts the g groups by hash,
 // merges equal hashes and writes the reference's output layout — the observable result of the
 // reference's Sort+Reduce (ARES_REDUCE_SORT) or HashReduce (ARES_REDUCE_HASH) over all batches.
+#include <memory>
 #include <vector>
 
 #include "agg.cuh"
@@ -340,12 +341,7 @@ __device__ __forceinline__ void processQuad(const DevPlan &P, const DevTable &G,
             }
             if (!P.skipCount && P.baseCounts != nullptr && (uint32_t)r < nrows) {
               uint32_t cnt = P.baseCounts[row0 + r + 1] - P.baseCounts[row0 + r];
-              switch ((ValClass)I.oclass) {
-                case VC_I32: case VC_U32: o = (uint32_t)o * cnt; break;
-                case VC_F32: o = fromF32(asF32(o) * (float)cnt); break;
-                case VC_I64: o = (uint64_t)((int64_t)o * (int64_t)(uint64_t)cnt); break;
-                default: o = fromF64(asF64(o) * (double)cnt); break;
-              }
+              o = mulCount(o, (ValClass)I.oclass, cnt);
             }
             meas[r] = o;
           }
@@ -942,6 +938,41 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
   P.accNeutral = st->accNeutral;
 }
 
+// ---------------------------------------------------------------------------------------
+// archive batches: run-length encoded (mode-3) columns are expanded once per batch into plain
+// mode-2 scratch columns (one value + one validity bit per index position), so that the staged,
+// specialised kernel can run on them instead of a positional run search per access per row.
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+expandRleKernel(InputDesc d, const uint32_t *__restrict__ baseCounts, uint32_t startCount, uint32_t n, int width, bool direct,
+                uint8_t *__restrict__ outValues, uint32_t *__restrict__ outNulls) {
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warpsPerGrid = gridDim.x * (blockDim.x >> 5);
+  const uint32_t *counts = reinterpret_cast<const uint32_t *>(d.base);
+  const uint8_t *vals = d.base + d.valuesOff, *nulls = d.base + d.nullsOff;
+  for (uint32_t w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w * 32 < n; w += warpsPerGrid) {
+    const uint32_t i = w * 32 + lane;
+    bool valid = false, bit = false;
+    if (i < n) {
+      // index position i stands for row baseCounts[i] (or startCount + i); `direct`: this column's own
+      // count vector IS the batch's base counts, so its run number is i
+      const uint32_t p = direct ? i : rlePosition(counts, d.length, baseCounts ? baseCounts[i] : startCount + i);
+      valid = bitAt(nulls, p + d.startBit);
+      switch (width) {
+        case 0: bit = bitAt(vals, p + d.startBit); break;
+        case 1: outValues[i] = vals[p]; break;
+        case 2: reinterpret_cast<uint16_t *>(outValues)[i] = reinterpret_cast<const uint16_t *>(vals)[p]; break;
+        default: reinterpret_cast<uint32_t *>(outValues)[i] = reinterpret_cast<const uint32_t *>(vals)[p]; break;
+      }
+    }
+    const uint32_t vword = __ballot_sync(0xFFFFFFFFu, valid), bword = __ballot_sync(0xFFFFFFFFu, bit);
+    if (lane == 0) {
+      outNulls[w] = vword;
+      if (width == 0) reinterpret_cast<uint32_t *>(outValues)[w] = bword;
+    }
+  }
+}
+
 // Decides staged vs direct, the tile size, the stage layout, the TMA ring depth and the shared table
 // size.  The shared table gets what the workload needs first (a table that overflows sends rows to
 // contended L2 atomics, profiles/r01_agg_microbench.txt), the ring takes the rest.
@@ -978,6 +1009,8 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
       stage += ((col.width ? (size_t)tr * col.width : tr / 8 + 16) + 15) / 16 * 16;
       if (col.in.mode == 2) stage += (tr / 8 + 16 + 15) / 16 * 16;
     }
+    // base counts of an RLE batch ride along when a SUM / AVG measure needs the run lengths
+    if (P.baseCounts != nullptr && !P.skipCount && (reinterpret_cast<uintptr_t>(P.baseCounts) & 15) == 0) stage += ((size_t)tr + 4) * 4;
     return stage;
   };
   uint32_t tileRows = 0, stages = 0;
@@ -1015,6 +1048,13 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
       }
     }
   }
+  P.smemBc = 0;
+  P.tileBcBytes = 0;
+  if (anyStaged && P.baseCounts != nullptr && !P.skipCount && (reinterpret_cast<uintptr_t>(P.baseCounts) & 15) == 0) {
+    P.smemBc = (uint32_t)stageBytes;
+    P.tileBcBytes = (tileRows + 4) * 4;   // one count more than rows (run length = difference), padded to 16 bytes
+    stageBytes += P.tileBcBytes;
+  }
   P.staged = anyStaged;
   P.tileRows = anyStaged ? tileRows : 4 * kFusedThreads;
   P.numStages = anyStaged ? stages : 0;
@@ -1034,6 +1074,32 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   compilePlan(st, bp, P);
   P.tailBegin = 0;
   P.ctaAcc = st->ctaAcc;
+  // archive batches: expand the RLE columns the plan reads (ARESDB_B200_EXPAND_RLE=0 keeps the positional path)
+  std::vector<std::unique_ptr<Scratch>> expanded;
+  static const bool expandRle = [] { const char *e = getenv("ARESDB_B200_EXPAND_RLE"); return !(e && e[0] == '0'); }();
+  if (expandRle && bp.NumRows >= 1024) {
+    const uint32_t n = bp.NumRows;
+    for (int c = 0; c < P.ncols; c++) {
+      DevColumn &col = P.cols[c];
+      if (!col.used || col.in.mode != 3 || col.width > 4) continue;
+      const size_t nullBytes = ((size_t)(n + 31) / 32 * 4 + 16 + 63) / 64 * 64;
+      const size_t valueBytes = (col.width ? (size_t)n * col.width : (size_t)(n + 31) / 32 * 4) + 64;
+      expanded.emplace_back(new Scratch(nullBytes + valueBytes, s));
+      uint8_t *buf = expanded.back()->as<uint8_t>();
+      const bool direct = bp.BaseCounts != nullptr && reinterpret_cast<const uint32_t *>(col.in.base) == bp.BaseCounts;
+      int blocks = divUp((int64_t)(n + 31) / 32, 8);
+      if (blocks > smCount() * 16) blocks = smCount() * 16;
+      expandRleKernel<<<blocks, 256, 0, s>>>(col.in, bp.BaseCounts, bp.StartCount, n, col.width, direct, buf + nullBytes,
+                                             reinterpret_cast<uint32_t *>(buf));
+      checkLastError("expandRle");
+      col.in.base = buf;
+      col.in.nullsOff = 0;
+      col.in.valuesOff = (uint32_t)nullBytes;
+      col.in.length = n;
+      col.in.mode = 2;
+      col.in.startBit = 0;
+    }
+  }
   const size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
   static bool attrSet[64] = {false};
   if (!attrSet[st->device & 63]) {

@@ -332,6 +332,17 @@ ARES_HD Cell evalBinary(int fn, Cell a, Cell b, ValClass tc, ValClass *rc) {
 // Identity element of an aggregate in the sink's value class
 // (reference query/utils.hpp:169-184: note MAX_FLOAT uses FLT_MIN, the smallest positive
 // normal, not -FLT_MAX; reproduced as is).
+// SUM measures of an RLE batch count `count` times: value * count in the sink's arithmetic
+// (reference query/iterator.hpp:626-645, 704-709).
+ARES_HD uint64_t mulCount(uint64_t v, ValClass oc, uint32_t count) {
+  switch (oc) {
+    case VC_I32: case VC_U32: return (uint32_t)((uint32_t)v * count);
+    case VC_F32: return fromF32(asF32(v) * (float)count);
+    case VC_I64: return (uint64_t)((int64_t)v * (int64_t)(uint64_t)count);
+    default: return fromF64(asF64(v) * (double)count);
+  }
+}
+
 ARES_HD uint64_t aggIdentity(int aggFunc, ValClass oc) {
   double d = 0; int64_t s = 0; bool isS = false, isD = false; uint64_t u = 0;
   switch (aggFunc) {

@@ -147,7 +147,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         // bytes of this part that exist for `rows` rows: values rows*width; bit-packed parts cover
         // bits [startBit, startBit + rows)
         const uint32_t per = kPartTileStride[p];                       // bytes per full tile
-        const uint32_t valid = kPartIsBits[p] ? (rows + kPartStartBit[p] + 7) / 8 : (uint32_t)((size_t)per * rows / JIT_TILE_ROWS);
+        // (kPartIsBits 2: the base counts, one 4-byte element more than rows)
+        const uint32_t valid = kPartIsBits[p] == 2 ? (rows + 1) * 4
+                             : kPartIsBits[p] ? (rows + kPartStartBit[p] + 7) / 8 : (uint32_t)((size_t)per * rows / JIT_TILE_ROWS);
         const uint8_t *src = P.partSrc[p] + (size_t)(done / JIT_TILE_ROWS) * per;
         uint8_t *dst = stages + kPartSmemOff[p];
         for (uint32_t i = threadIdx.x; i < kPartBytes[p]; i += JIT_THREADS) dst[i] = i < valid ? src[i] : (uint8_t)0;

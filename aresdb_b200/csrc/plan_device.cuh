@@ -53,6 +53,8 @@ struct DevPlan {
   uint32_t tailBegin;      // first row of the direct (non-staged) pass
   uint32_t numStages;      // depth of the TMA ring (2..kMaxStages)
   uint32_t denseSlots;     // dense HLL mode: slots of the group directory (0 otherwise)
+  uint32_t smemBc;         // staged base counts (RLE batches, SUM / AVG): byte offset inside a stage, tileBcBytes bytes
+  uint32_t tileBcBytes;    // (tileRows + 4) * 4, or 0 when the base counts are not staged
   int32_t ncols, ninsts, lastFilter;
   uint64_t measureIdentity;  // NULL measure -> this (sink class bits)
   uint64_t accNeutral;       // neutral element of the combine op

@@ -10,7 +10,7 @@ from aresdb_b200 import columns, synth
 import test_pipeline_parity as T
 
 
-def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0):
+def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0, base_counts=None):
     fn = lib.alg.AresJitDryRun
     fn.argtypes = [A.AggSpec, C.POINTER(A.BatchPlan), C.POINTER(C.c_char_p)]
     fn.restype = A.CGoCallResHandle
@@ -23,6 +23,8 @@ def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0):
     for i, dt in enumerate(synth.COLUMN_TYPES):  # fake, 64-byte aligned device addresses: nothing is dereferenced
         p.Columns[i] = columns.slice_of(0x7F0000000000 + i * (1 << 30), dt, rows, 0, 64 * 200, 2, start_bit)
     p.NumRows = rows
+    if base_counts is not None:
+        p.BaseCounts = base_counts
     src = C.c_char_p()
     h = fn(q.agg_spec(expected_groups), C.byref(p), C.byref(src))
     if h.pStrErr:
@@ -68,7 +70,7 @@ def test_avg_queries_specialise():
     for name, q in T.avg_queries().items():
         size, src = _dry_run(lib, q)
         assert size > 0, name
-        assert "(1ull << 32)" in src      # (float average, count = 1) packing of the measure
+        assert "<< 32) | (uint32_t)cvt" in src      # (float average, count) packing of the measure
 
 
 def test_on_disk_cubin_cache(tmp_path, monkeypatch):
@@ -119,3 +121,18 @@ def test_mixed_column_modes_and_wide_dims_specialise():
             assert int(h.res or 0) == 0
         else:
             assert int(h.res or 0) > 0, f"{name} was not eligible for specialisation"
+
+
+def test_rle_batches_stage_their_base_counts():
+    """An archive batch (base counts given): SUM / COUNT / AVG kernels stage the cumulative counts and multiply
+    by the run length; MIN / MAX ignore them; unaligned base counts fall back to the generic kernel."""
+    lib = A.load_engine()
+    aligned, unaligned = 0x7E0000000000, 0x7E0000000004
+    size, src = _dry_run(lib, T.queries()["cfg3_count"], base_counts=aligned)
+    assert size > 0 and "runLen[r]" in src and "mulCount(" in src
+    size, src = _dry_run(lib, T.avg_queries()["avg_fare_by_city"], base_counts=aligned)
+    assert size > 0 and "(uint64_t)runLen[r] << 32" in src
+    size, src = _dry_run(lib, T.queries()["min_city"], base_counts=aligned)
+    assert size > 0 and "runLen" not in src
+    size, _ = _dry_run(lib, T.queries()["cfg3_count"], base_counts=unaligned)
+    assert size == 0

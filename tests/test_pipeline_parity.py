@@ -176,11 +176,20 @@ def _archive_batch(be, seed, runs=6000):
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", ["cfg2", "cfg3_count", "int_sum", "min_city"])
 def test_fused_plan_on_archive_style_batches(name):
-    """Mode-3 columns and base counts go through ExecuteBatchPlan too (generic kernel: positional run
-    search per access) and agree with the reference sequence, including the x run-length of SUM / COUNT."""
+    """Mode-3 columns and base counts go through ExecuteBatchPlan too — the RLE columns are expanded once per
+    batch, the base counts are staged with the columns — and agree with the reference sequence, including
+    the x run-length of SUM / COUNT."""
+    import ctypes as C
     eng, orc = H.get_backend("b200"), H.get_backend("oracle")
     q = queries()[name]
+
+    def jit_launches():
+        out = (C.c_ulonglong * 2)()
+        eng.lib.alg.AresJitStats(out)
+        return int(out[1])
+
     exp_ex, got_ex = LegacyBatchExecutor(orc.lib, orc.space, q), FusedBatchExecutor(eng.lib, eng.space, q)
+    before = jit_launches()
     for seed in (1, 2):
         exp_ex.process_batch(_archive_batch(orc, seed))
         got_ex.process_batch(_archive_batch(eng, seed))
@@ -188,6 +197,8 @@ def test_fused_plan_on_archive_style_batches(name):
     got_ex.close()
     assert exp.groups > 0
     assert_same_result(got, exp, ctx=f"archive/{name}")
+    # the RLE columns were expanded and the batches ran on the specialised (staged) kernel
+    assert jit_launches() - before == 2
 
 
 @pytest.mark.parametrize("name", ["cfg2", "cfg3_count"])
