@@ -173,10 +173,16 @@ class PlanInst(C.Structure):
                 ("A", PlanOperand), ("B", PlanOperand)]
 
 
+class ColumnRange(C.Structure):
+    """Zone-map hint of one column of one batch (batch_plan.h): valid values lie in [Min, Max]."""
+    _fields_ = [("Known", C.c_uint8), ("Reserved", C.c_uint8 * 3), ("Min", C.c_uint32), ("Max", C.c_uint32)]
+
+
 class BatchPlan(C.Structure):
     _fields_ = [("Columns", VectorPartySlice * ARES_MAX_PLAN_COLUMNS), ("NumColumns", C.c_int32),
                 ("Insts", PlanInst * ARES_MAX_PLAN_INSTS), ("NumInsts", C.c_int32),
-                ("BaseCounts", C.c_void_p), ("StartCount", C.c_uint32), ("NumRows", C.c_uint32)]
+                ("BaseCounts", C.c_void_p), ("StartCount", C.c_uint32), ("NumRows", C.c_uint32),
+                ("Ranges", ColumnRange * ARES_MAX_PLAN_COLUMNS)]
 
 
 class AggSpec(C.Structure):

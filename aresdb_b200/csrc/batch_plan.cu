@@ -828,6 +828,10 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
     P.cols[c].width = dt == Bool ? 0 : (dt == Int8 || dt == Uint8) ? 1 : (dt == Int16 || dt == Uint16) ? 2
                     : (dt == Int64 || dt == Uint64) ? 8 : dt == UUID ? 16 : 4;
     P.cols[c].used = 0;      // set below by the instructions that read the column: only those are staged
+    const ColumnRange &cr = bp.Ranges[c];
+    P.cols[c].rangeKnown = cr.Known && cr.Min <= cr.Max && cr.Max < 0x80000000u && P.cols[c].width <= 4 ? 1 : 0;
+    P.cols[c].rangeLo = cr.Min;
+    P.cols[c].rangeHi = cr.Max;
     P.cols[c].staged = 0;
     P.cols[c].hasNulls = 0;
   }

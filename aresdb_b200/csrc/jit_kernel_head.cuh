@@ -11,6 +11,7 @@ constexpr int kJitMaxParts = 32;
 constexpr int kJitMaxConsts = 64;
 constexpr int kJitMaxWide = 8;
 constexpr int kJitMaxMagic = 16;
+constexpr int kJitMaxDenseDims = 8;
 
 struct JitParams {
   const uint8_t *partSrc[kJitMaxParts];   // global base address of every staged part
@@ -24,6 +25,10 @@ struct JitParams {
   unsigned long long *ctaAcc;             // [grid][JIT_SMEM_SLOTS] accumulator slices in global memory
   uint32_t numFullTiles;
   uint32_t numRows;                       // rows of the batch (tail = numRows - numFullTiles * JIT_TILE_ROWS)
+  // direct-indexed aggregation (JIT_DENSE): dimension k of a row has index (value or quotient) - dLo[k], valid when
+  // below dCnt[k]; index dCnt[k] is the dimension's NULL; slot = sum_k index_k * dStride[k]; value = (dLo + index) * dStep
+  uint32_t dLo[kJitMaxDenseDims], dCnt[kJitMaxDenseDims], dStride[kJitMaxDenseDims], dStep[kJitMaxDenseDims];
+  uint32_t dTotal, dReps;                 // slots of one copy; lane-private copies (power of two)
 };
 
 // rows 4q .. 4q+3 of a staged value column of W bytes per value

@@ -13,14 +13,108 @@ __device__ __forceinline__ void jitIssueTile(const JitParams &P, uint32_t tile, 
     tmaLoad1D(stage + kPartSmemOff[p], P.partSrc[p] + (size_t)tile * kPartTileStride[p], kPartBytes[p], bar);
 }
 
-// Group identity of row r of a quad: the packed row itself, or the reference's hash of it.
+// Group identity of a packed dimension row: the row itself, or the reference's hash of it.
+__device__ __forceinline__ unsigned long long jitKeyOfRow(const uint64_t (&key)[JIT_KW]) {
+  if (JIT_KW == 1) return key[0];
+  uint64_t w[4] = {key[0], key[JIT_KW > 1 ? 1 : 0], key[JIT_KW > 2 ? 2 : 0], key[JIT_KW > 3 ? 3 : 0]};
+  return JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+}
 __device__ __forceinline__ unsigned long long jitKeyOf(const uint64_t (&key)[4][JIT_KW], const uint64_t (&meas)[4], int r) {
-  if (JIT_KW == 1) return key[r][0];
-  uint64_t w[4] = {key[r][0], key[r][JIT_KW > 1 ? 1 : 0], key[r][JIT_KW > 2 ? 2 : 0], key[r][JIT_KW > 3 ? 3 : 0]};
-  unsigned long long k = JIT_HASH_BITS == 64 ? murmur3_128_lo(w, JIT_ROW_BYTES, 0) : (unsigned long long)murmur3_32(w, JIT_ROW_BYTES, 0);
+  unsigned long long k = jitKeyOfRow(key[r]);
   if (JIT_HLL == 1) k = (k & 0xFFFFFFFFFFFF0000ull) | (meas[r] & 0x3FFFu);  // the reference's HLL key
   return k;
 }
+
+#if JIT_DENSE
+// ---- direct-indexed aggregation (zone map known for every dimension, see jit.cu) --------------------
+// A row whose dimension values fall outside the announced ranges (or a NULL whose stored value is not the
+// canonical zero): the global hash table, keyed like every other path.
+static __device__ __noinline__ void denseSlowRow(const JitParams &P, const uint32_t (&dvr)[JIT_ND], uint32_t vb, uint64_t meas) {
+  uint64_t key[JIT_KW];
+  densePack(dvr, vb, key);
+  globalUpdate(P.G, (AggOp)JIT_AGG_OP, jitKeyOfRow(key), JIT_KW == 1 ? nullptr : key, meas);
+}
+
+// Where the accumulators of the direct-indexed slots live (JIT_DENSE_ACC, chosen by the host):
+//   0  the CTA's private slice of global memory, updated with fire-and-forget RED (one L2 atomic per row);
+//   1  shared memory (native ATOMS for 4-byte aggregates, a CAS loop for 8-byte ones);
+//   2  both: row positions 0-1 of a quad go to shared memory, 2-3 to the L2 slice, so that neither the SM's
+//      shared-memory atomic path nor the L2 atomic units carry the whole stream; the flush adds the two halves.
+constexpr uint32_t kDenseCap = JIT_SMEM_SLOTS / 8 * 7;   // touched bytes + 8-byte accumulators fit the key region
+// layout of the key region (dynamic shared memory + 128) in this mode: touched[kDenseCap] | acc[kDenseCap] (8 bytes each)
+__device__ __forceinline__ unsigned long long *denseSharedAcc() {
+  extern __shared__ __align__(128) uint8_t denseSmem[];
+  return reinterpret_cast<unsigned long long *>(denseSmem + 128 + kDenseCap);
+}
+
+// predicated single-instruction updates (no branch, no reconvergence point around them)
+__device__ __forceinline__ void stsFlag(uint32_t addr, bool p) {
+  asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p st.shared.u8 [%1], %2; }" ::"r"((uint32_t)p), "r"(addr), "r"(1u) : "memory");
+}
+template <int OP>
+__device__ __forceinline__ void redGlobalPred(unsigned long long *a, uint64_t v, bool p) {
+  const uint32_t pp = p;
+  if (OP == OP_SUM_F64) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.add.f64 [%1], %2; }" ::"r"(pp), "l"(a), "d"(__longlong_as_double((long long)v)) : "memory");
+  else if (OP == OP_SUM_I64) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.add.u64 [%1], %2; }" ::"r"(pp), "l"(a), "l"(v) : "memory");
+  else if (OP == OP_SUM_I32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.add.u32 [%1], %2; }" ::"r"(pp), "l"(a), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_SUM_F32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.add.f32 [%1], %2; }" ::"r"(pp), "l"(a), "f"(__uint_as_float((uint32_t)v)) : "memory");
+  else if (OP == OP_MIN_U32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.min.u32 [%1], %2; }" ::"r"(pp), "l"(a), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_MAX_U32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.max.u32 [%1], %2; }" ::"r"(pp), "l"(a), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_MIN_I32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.min.s32 [%1], %2; }" ::"r"(pp), "l"(a), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_MAX_I32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.max.s32 [%1], %2; }" ::"r"(pp), "l"(a), "r"((uint32_t)v) : "memory");
+  else if (p) aggAtomic((AggOp)OP, a, v);   // float min / max, AVG: CAS loops
+}
+template <int OP>
+__device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long *generic, uint64_t v, bool p) {
+  const uint32_t pp = p;
+  if (OP == OP_SUM_I32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.add.u32 [%1], %2; }" ::"r"(pp), "r"(addr), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_SUM_F32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.add.f32 [%1], %2; }" ::"r"(pp), "r"(addr), "f"(__uint_as_float((uint32_t)v)) : "memory");
+  else if (OP == OP_MIN_U32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.min.u32 [%1], %2; }" ::"r"(pp), "r"(addr), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_MAX_U32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.max.u32 [%1], %2; }" ::"r"(pp), "r"(addr), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_MIN_I32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.min.s32 [%1], %2; }" ::"r"(pp), "r"(addr), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_MAX_I32) asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.shared.max.s32 [%1], %2; }" ::"r"(pp), "r"(addr), "r"((uint32_t)v) : "memory");
+  else if (OP == OP_SUM_F64) {
+    if (p) {   // 64-bit shared-memory adds are compare-and-swap loops on this hardware either way; keep ours minimal
+      unsigned long long old, assumed;
+      asm volatile("ld.shared.u64 %0, [%1];" : "=l"(old) : "r"(addr) : "memory");
+      do {
+        assumed = old;
+        const unsigned long long want = (unsigned long long)__double_as_longlong(__longlong_as_double((long long)assumed) + __longlong_as_double((long long)v));
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(old) : "r"(addr), "l"(assumed), "l"(want) : "memory");
+      } while (old != assumed);
+    }
+  } else if (OP == OP_SUM_I64) {
+    if (p) asm volatile("red.shared.add.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+  } else if (p) smemAtomic((AggOp)OP, generic, v);
+}
+
+__device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P, uint32_t alive,
+                                                  const uint32_t (&dslot)[4], const uint32_t (&dv)[4][JIT_ND],
+                                                  const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
+  const uint32_t rep = (threadIdx.x & (P.dReps - 1u)) * P.dTotal;
+  uint32_t s[4];
+  bool fast[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    fast[r] = ((alive >> r) & 1) && dslot[r] != 0xFFFFFFFFu;
+    s[r] = dslot[r] + rep;
+  }
+#pragma unroll
+  for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
+  const uint32_t sAccAddr = touchedAddr + kDenseCap;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const bool toShared = JIT_DENSE_ACC == 1 || (JIT_DENSE_ACC == 2 && r < 2);
+    if (toShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
+    else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
+  }
+  if (__builtin_expect(((alive & 1) && !fast[0]) || ((alive & 2) && !fast[1]) || ((alive & 4) && !fast[2]) || ((alive & 8) && !fast[3]), 0)) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (((alive >> r) & 1) && !fast[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
+  }
+}
+#endif
 
 // Folds the surviving rows of one quad.  Normal mode: the CTA's shared table first, the global table
 // for rows it cannot take (counted in *misses).  Bypass mode (the batch has far more groups than the
@@ -84,10 +178,23 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 
   SmemTable T;
   T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = JIT_SMEM_SLOTS - 1;
+#if JIT_DENSE
+  // no keys: the slot index IS the group; one byte per slot records that a row reached it
+  uint8_t *touched = reinterpret_cast<uint8_t *>(tKeys);
+  uint32_t touchedAddr = smemAddr(touched);
+  asm volatile("" : "+r"(touchedAddr));   // keep it in a register: the compiler otherwise rebuilds the window address per store
+  const uint32_t denseSlots = P.dTotal * P.dReps;   // <= kDenseCap (host)
+  for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
+    touched[i] = 0;
+    if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
+    if (JIT_DENSE_ACC != 0) denseSharedAcc()[i] = P.accNeutral;
+  }
+#else
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     tKeys[i] = kEmptyKey;
     if (JIT_HLL != 2) tAcc[i] = P.accNeutral;
   }
+#endif
   if (threadIdx.x == 0) {
     *claims = 0;
     *misses = 0;
@@ -125,10 +232,17 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
       const bool bypass = JIT_BYPASS && !allowClaim && *reinterpret_cast<volatile uint32_t *>(misses) > 4u * JIT_SMEM_SLOTS;
       {
         const uint32_t q = threadIdx.x;
-        uint64_t key[4][JIT_KW];
         uint64_t meas[4];
+#if JIT_DENSE
+        uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
+        const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, dslot, dv, dvalid, meas);
+        jitAggregateDense(touchedAddr, tAcc, P, alive, dslot, dv, dvalid, meas);
+        (void)allowClaim; (void)bypass;
+#else
+        uint64_t key[4][JIT_KW];
         const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
         jitAggregate(T, P, alive, key, meas, allowClaim, bypass, misses);
+#endif
       }
       __syncwarp();
       if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
@@ -156,18 +270,46 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
       }
       __syncthreads();
       for (uint32_t q = threadIdx.x; q * 4 < rows; q += JIT_THREADS) {
-        uint64_t key[4][JIT_KW];
         uint64_t meas[4];
-        uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
         const uint32_t nvalid = rows - q * 4 < 4 ? rows - q * 4 : 4;
+#if JIT_DENSE
+        uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
+        uint32_t alive = rowEval(stages, q, done + q * 4, P, dslot, dv, dvalid, meas);
+        alive &= (1u << nvalid) - 1u;
+        jitAggregateDense(touchedAddr, tAcc, P, alive, dslot, dv, dvalid, meas);
+#else
+        uint64_t key[4][JIT_KW];
+        uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
         alive &= (1u << nvalid) - 1u;
         jitAggregate(T, P, alive, key, meas, true, false, misses);
+#endif
       }
       done += rows;
     }
   }
   __syncthreads();
   if (JIT_HLL == 2) return;  // nothing CTA-private to fold: registers are updated in place
+#if JIT_DENSE
+  // fold the touched slots into the global table: the slot index decodes to the dimension values
+  for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
+    if (!touched[i]) continue;
+    uint32_t rem = i % P.dTotal, dvr[JIT_ND], vb = 0;
+#pragma unroll
+    for (int k = JIT_ND - 1; k >= 0; k--) {
+      const uint32_t ix = rem / P.dStride[k];
+      rem -= ix * P.dStride[k];
+      const bool valid = ix != P.dCnt[k];
+      dvr[k] = valid ? (P.dLo[k] + ix) * P.dStep[k] : 0u;
+      vb |= (valid ? 1u : 0u) << k;
+    }
+    uint64_t key[JIT_KW];
+    densePack(dvr, vb, key);
+    const unsigned long long k = jitKeyOfRow(key);
+    if (JIT_DENSE_ACC != 1) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, __ldcg(&tAcc[i]));
+    if (JIT_DENSE_ACC != 0) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, denseSharedAcc()[i]);
+  }
+  return;
+#endif
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
     if (k != kEmptyKey) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, nullptr, __ldcg(&tAcc[i]));

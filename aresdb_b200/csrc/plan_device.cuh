@@ -25,6 +25,9 @@ struct DevColumn {
   uint8_t staged;          // values staged
   uint8_t hasNulls;        // mode 2 bitmap staged
   uint8_t used;            // some instruction reads the column (unreferenced columns of the batch cost nothing)
+  uint32_t rangeLo, rangeHi;  // zone map of the batch (BatchPlan.Ranges): valid values lie in [rangeLo, rangeHi]
+  uint8_t rangeKnown;
+  uint8_t pad[3];
 };
 
 struct DevInst {

@@ -31,6 +31,9 @@ class Batch:
     base_counts: Buf | None = None   # cumulative counts of the first (RLE) column, or None
     start_count: int = 0
     keep: list = field(default_factory=list)  # owning buffers
+    # zone map: {column index: (min, max)} of the VALID values of this batch (BatchPlan.Ranges; a hint the
+    # fused kernel verifies per row — what LiveVectorParty.GetMinMaxValue / the archive day give the reference)
+    ranges: dict | None = None
 
 
 def dim_offsets(num_dims_per_width, capacity: int):
@@ -267,6 +270,10 @@ class FusedBatchExecutor:
         p.BaseCounts = batch.base_counts.ptr if batch.base_counts else None
         p.StartCount = batch.start_count
         p.NumRows = batch.num_rows
+        for i in range(len(batch.columns)):
+            r = batch.ranges.get(i) if batch.ranges else None
+            p.Ranges[i].Known = 0 if r is None else 1
+            p.Ranges[i].Min, p.Ranges[i].Max = (0, 0) if r is None else (int(r[0]), int(r[1]))
         self.calls += 1
         self.lib.ExecuteBatchPlan(self.state, C.byref(p), self.space.stream if stream is None else stream,
                                   self.space.device)

@@ -54,6 +54,27 @@ def generate_batch(day: int, rows: int, num_cities: int = 100, null_rate: float 
     return HostBatch(values, valid, rows, day)
 
 
+def zone_map(hb: HostBatch) -> dict:
+    """{column index: (min, max)} over the VALID values of the integer columns of a batch — what the
+    memstore keeps per batch (LiveVectorParty.GetMinMaxValue for the time column; archive day, enum
+    dictionary size) and hands to the engine as BatchPlan.Ranges."""
+    out = {}
+    for i, (v, ok) in enumerate(zip(hb.values, hb.valid)):
+        if v.dtype.kind not in "ui":
+            continue
+        sel = v[ok != 0]
+        if sel.size and int(sel.min()) >= 0 and int(sel.max()) < 2 ** 31:
+            out[i] = (int(sel.min()), int(sel.max()))
+    return out
+
+
+def zone_map_of_day(day: int, num_cities: int = 100) -> dict:
+    """Zone map of a generated day-batch by construction (generate_batch / generate_batch_cuda): what the
+    archive store knows without looking at the data — batch ID = day, city ids 1..num_cities, 4 status values."""
+    return {COL_REQUEST_AT: (BASE_TS + day * 86400, BASE_TS + day * 86400 + 86399), COL_CITY_ID: (1, num_cities),
+            COL_STATUS: (0, 3)}
+
+
 # ---- large-scale generation on the GPU (bench.py): same schema, torch RNG -------------------------
 def generate_batch_cuda(day: int, rows: int, device, num_cities: int = 100, null_rate: float = 0.01,
                         seed: int = 20260922, exact_fares: bool = True):

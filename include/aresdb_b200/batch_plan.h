@@ -67,6 +67,22 @@ typedef struct {
   PlanOperand B;
 } PlanInst;
 
+/* Optional zone-map entry of one column of one batch: every VALID (non-NULL) value of the column in this
+ * batch lies in [Min, Max] as a non-negative integer below 2^31 (Bool / Uint8 / Uint16 / Uint32 columns and
+ * non-negative signed ones).  The reference keeps exactly this for the time column of live batches
+ * (LiveVectorParty.GetMinMaxValue, memstore/common/vector_party.go:184-186, used for batch skipping in
+ * query/aql_processor.go:1509) and knows it by construction for archive batches (batch ID = day) and for
+ * enum columns (dictionary size).  It is a HINT: when every dimension of the query has a small known range
+ * the fused kernel addresses its CTA-private accumulators directly by (dimension value - Min) instead of
+ * probing a hash table; every row is checked against the range and rows outside it take the hash path, so a
+ * stale or wrong entry costs speed, never correctness.  Known = 0: no information. */
+typedef struct {
+  uint8_t Known;
+  uint8_t Reserved[3];
+  uint32_t Min;
+  uint32_t Max;
+} ColumnRange;
+
 /* One batch of one table shard: column slices already resident on the device. */
 typedef struct {
   VectorPartySlice Columns[ARES_MAX_PLAN_COLUMNS];
@@ -80,6 +96,7 @@ typedef struct {
   uint32_t *BaseCounts;
   uint32_t StartCount;
   uint32_t NumRows;
+  ColumnRange Ranges[ARES_MAX_PLAN_COLUMNS]; /* zone map per entry of Columns (all zero: none) */
 } BatchPlan;
 
 enum AresReduceMode {

@@ -10,7 +10,7 @@ from aresdb_b200 import columns, synth
 import test_pipeline_parity as T
 
 
-def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0, base_counts=None):
+def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0, base_counts=None, ranges=None):
     fn = lib.alg.AresJitDryRun
     fn.argtypes = [A.AggSpec, C.POINTER(A.BatchPlan), C.POINTER(C.c_char_p)]
     fn.restype = A.CGoCallResHandle
@@ -25,6 +25,8 @@ def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0, base_counts=No
     p.NumRows = rows
     if base_counts is not None:
         p.BaseCounts = base_counts
+    for col, (lo, hi) in (ranges or {}).items():
+        p.Ranges[col].Known, p.Ranges[col].Min, p.Ranges[col].Max = 1, lo, hi
     src = C.c_char_p()
     h = fn(q.agg_spec(expected_groups), C.byref(p), C.byref(src))
     if h.pStrErr:
@@ -136,3 +138,32 @@ def test_rle_batches_stage_their_base_counts():
     assert size > 0 and "runLen" not in src
     size, _ = _dry_run(lib, T.queries()["cfg3_count"], base_counts=unaligned)
     assert size == 0
+
+
+DAY_RANGES = {synth.COL_REQUEST_AT: (synth.BASE_TS, synth.BASE_TS + 86399), synth.COL_CITY_ID: (0, 100),
+              synth.COL_STATUS: (0, 3)}
+
+
+def test_zone_map_selects_direct_indexed_aggregation():
+    """With a zone map (BatchPlan.Ranges) that bounds every dimension the kernel is generated in its
+    direct-indexed form: slots addressed by (value - min), no key table.  The ranges themselves are runtime
+    parameters (another day, another city range: same kernel text); unknown or too wide ranges, HLL and
+    high-cardinality plans keep the hash-table form."""
+    lib = A.load_engine()
+    q = T.queries()["cfg3_sum"]
+    size, src = _dry_run(lib, q, ranges=DAY_RANGES)
+    assert size > 0 and "#define JIT_DENSE 1" in src and "#define JIT_ND 2" in src and "densePack" in src
+    other_day = dict(DAY_RANGES)
+    other_day[synth.COL_REQUEST_AT] = (synth.BASE_TS + 5 * 86400, synth.BASE_TS + 6 * 86400 - 1)
+    other_day[synth.COL_CITY_ID] = (1, 57)
+    assert _dry_run(lib, q, ranges=other_day)[1] == src
+    # no zone map / only one of the two dimensions bounded / range too wide for the CTA's slots
+    assert "#define JIT_DENSE 0" in _dry_run(lib, q)[1]
+    assert "#define JIT_DENSE 0" in _dry_run(lib, q, ranges={synth.COL_CITY_ID: (0, 100)})[1]
+    wide = dict(DAY_RANGES)
+    wide[synth.COL_CITY_ID] = (0, 65535)
+    assert "#define JIT_DENSE 0" in _dry_run(lib, q, ranges=wide)[1]
+    # every aggregate of the suite compiles in the dense form
+    for name, qq in list(T.queries().items()) + list(T.avg_queries().items()):
+        size, s2 = _dry_run(lib, qq, ranges=DAY_RANGES)
+        assert size > 0, name

@@ -18,13 +18,13 @@ from aresdb_b200.query import AggQuery, Measure
 TS, CITY, STATUS, FARE = (E.Col(i, t, n) for i, (t, n) in enumerate(zip(synth.COLUMN_TYPES, synth.COLUMN_NAMES)))
 
 
-def upload(be, hb: synth.HostBatch, start_bit=0) -> Batch:
+def upload(be, hb: synth.HostBatch, start_bit=0, ranges=None) -> Batch:
     cols, keep = [], []
     for dt, v, ok in zip(synth.COLUMN_TYPES, hb.values, hb.valid):
         buf, vp = columns.make_column(be.space, dt, v, valid=ok, start_bit=start_bit)
         cols.append(vp)
         keep.append(buf)
-    return Batch(cols, hb.num_rows, keep=keep)
+    return Batch(cols, hb.num_rows, keep=keep, ranges=ranges)
 
 
 def queries():
@@ -57,11 +57,12 @@ def run_legacy(be, q, host_batches, start_bit=0):
     return ex.result()
 
 
-def run_fused(be, q, host_batches, start_bit=0, expected_groups=0):
+def run_fused(be, q, host_batches, start_bit=0, expected_groups=0, zone_maps=None):
+    """zone_maps: None, or one {column: (min, max)} per batch (BatchPlan.Ranges)."""
     ex = FusedBatchExecutor(be.lib, be.space, q, expected_groups)
     keep = []
-    for hb in host_batches:
-        b = upload(be, hb, start_bit)
+    for i, hb in enumerate(host_batches):
+        b = upload(be, hb, start_bit, zone_maps[i] if zone_maps else None)
         keep.append(b)
         ex.process_batch(b)
     r = ex.result()
@@ -117,6 +118,73 @@ def test_fused_plan_on_b200(name, start_bit, host_batches):
     exp = run_legacy(orc, q, host_batches, start_bit)
     got = run_fused(eng, q, host_batches, start_bit)
     assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"{name}/bit{start_bit}")
+
+
+def dense_launches(be) -> int:
+    import ctypes as C
+    fn = be.lib.alg.AresJitDenseLaunches
+    fn.restype = C.c_ulonglong
+    return int(fn())
+
+
+def zone_maps_for(host_batches, mode):
+    """exact: min / max of the valid values of every batch.  narrow: deliberately too tight (the upper half of
+    every range is cut off, so about half the rows fall outside and must take the hash path).  stale: the
+    zone map of ANOTHER batch (wrong day: every time value is outside).  All three must give the same bits."""
+    exact = [synth.zone_map(hb) for hb in host_batches]
+    if mode == "exact":
+        return exact
+    if mode == "narrow":
+        return [{c: (lo, lo + (hi - lo) // 2) for c, (lo, hi) in zm.items()} for zm in exact]
+    return exact[1:] + exact[:1]
+
+
+DENSE_QUERIES = ["cfg2", "cfg3_sum", "cfg3_count", "int_sum", "min_city"]   # every dimension bounded by the zone map
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["exact", "narrow", "stale"])
+@pytest.mark.parametrize("name", list(queries()))
+def test_fused_plan_with_zone_maps_on_b200(name, mode, host_batches):
+    """BatchPlan.Ranges switches the kernel to direct-indexed aggregation; the result is the reference's bit for
+    bit whether the zone map is right, too narrow or plain wrong (rows outside it take the hash path)."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    q = queries()[name]
+    exp = run_legacy(orc, q, host_batches)
+    before = dense_launches(eng)
+    got = run_fused(eng, q, host_batches, zone_maps=zone_maps_for(host_batches, mode))
+    assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"{name}/{mode}")
+    if name in DENSE_QUERIES:
+        assert dense_launches(eng) - before == len(host_batches), "the direct-indexed kernel did not run"
+    else:   # minute buckets x city, raw timestamps or a float quotient as a dimension: the hash table stays
+        assert dense_launches(eng) == before
+
+
+@pytest.mark.gpu
+def test_zone_map_null_dimensions_and_replicas():
+    """NULL dimension values have their own slot (computed dimensions) or need the canonical zero under the
+    NULL (verbatim columns: a non-zero stored value under a NULL goes to the hash path, as the reference keys
+    the row by its stored bytes); a handful of slots is replicated per lane.  No filter here, so nothing proves
+    the dimension columns valid and the NULL slots are live."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    hbs = [synth.generate_batch(d, 25000, num_cities=7, null_rate=0.2) for d in range(2)]
+    rng = np.random.default_rng(5)
+    for hb in hbs:   # garbage under some of the NULL city ids
+        c = hb.values[synth.COL_CITY_ID]
+        dirty = (hb.valid[synth.COL_CITY_ID] == 0) & (rng.random(c.size) < 0.5)
+        c[dirty] = 77
+    for q in (AggQuery([], [CITY, E.floor(TS, E.Lit(7200))], Measure("sum", FARE)),
+              AggQuery([], [STATUS], Measure("count")),
+              AggQuery([E.gt(FARE, E.Lit(50.0))], [CITY, STATUS], Measure("max", FARE)),
+              avg_queries()["avg_fare_by_city"]):
+        before = dense_launches(eng)
+        got = run_fused(eng, q, hbs, zone_maps=[synth.zone_map(hb) for hb in hbs])
+        exp = run_legacy(orc, q, hbs)
+        if q.measure_kind == "avg":
+            assert_same_avg(got, exp, ctx="avg/zone map")
+        else:
+            assert_same_result(got, exp, ctx="null dims")
+        assert dense_launches(eng) - before == len(hbs)
 
 
 @pytest.mark.gpu
