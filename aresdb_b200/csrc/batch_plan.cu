@@ -980,7 +980,7 @@ expandRleKernel(InputDesc d, const uint32_t *__restrict__ baseCounts, uint32_t s
 // Decides staged vs direct, the tile size, the stage layout, the TMA ring depth and the shared table
 // size.  The shared table gets what the workload needs first (a table that overflows sends rows to
 // contended L2 atomics, profiles/r01_agg_microbench.txt), the ring takes the rest.
-static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
+static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense = true) {
   bool canStage = P.numRows >= 1024;
   uint32_t rowBits = 0;
   for (int c = 0; c < P.ncols; c++) {
@@ -1001,6 +1001,9 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   // The caller expects far more groups than the shared table holds (or HLL, whose entries are
   // (group, register) pairs): compile the kernel with the direct-to-global mode it can switch to.
   P.bypassOk = (P.hll || expectedGroups > 4 * slots) ? 1 : 0;
+  // zone map known for every dimension: no key table, slots addressed by dimension value (jit.cu)
+  if (allowDense) jitAnalyzeDense(P, P.bypassOk != 0);
+  else P.denseNd = 0;
   if (const char *e = getenv("ARESDB_B200_SMEM_SLOTS")) {  // tuning / experiments
     uint32_t v = (uint32_t)atoi(e);
     if (v >= 256 && v <= 8192 && (v & (v - 1)) == 0) slots = v;
@@ -1021,15 +1024,36 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   if (canStage && rowBits > 0) {
     uint32_t forceTile = 0;
     if (const char *e = getenv("ARESDB_B200_TILE_ROWS")) forceTile = (uint32_t)atoi(e);  // tuning / experiments
-    for (uint32_t sl : {slots, slots / 2, slots / 4}) {
-      for (uint32_t tr : {3968u, 1920u, 896u}) {  // 128 rows x (31 | 15 | 7) consumer warps
+    if (P.denseNd != 0) {
+      // Dense slots cost 9 bytes each (flag + 8-byte accumulator).  Give the ring as many stages as possible
+      // and the slots the rest: the capacity (part of the kernel text) then depends on the stage layout only,
+      // not on the batch's ranges.
+      for (uint32_t tr : {3968u, 1920u, 896u}) {
         if (forceTile && tr != forceTile) continue;
-        size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8;
-        uint32_t n = (uint32_t)(avail / stageBytesFor(tr));
-        if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; break; }
+        for (uint32_t n = kMaxStages; n >= 2 && !tileRows; n--) {
+          const size_t need = 128 + n * stageBytesFor(tr);
+          if (need >= (size_t)kSmemBudget) continue;
+          uint32_t cap = (uint32_t)(((size_t)kSmemBudget - need) / 9 / 16 * 16);
+          if (cap > kDenseMaxSlots) cap = kDenseMaxSlots;
+          if (cap >= P.denseTotal) { tileRows = tr; stages = n; slots = cap; }
+        }
+        if (tileRows) break;
       }
-      if (tileRows) { slots = sl; break; }
+      if (!tileRows) P.denseNd = 0;   // no layout holds the slots: hash table
     }
+    if (!tileRows) {
+      for (uint32_t sl : {slots, slots / 2, slots / 4}) {
+        for (uint32_t tr : {3968u, 1920u, 896u}) {  // 128 rows x (31 | 15 | 7) consumer warps
+          if (forceTile && tr != forceTile) continue;
+          size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8;
+          uint32_t n = (uint32_t)(avail / stageBytesFor(tr));
+          if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; break; }
+        }
+        if (tileRows) { slots = sl; break; }
+      }
+    }
+  } else {
+    P.denseNd = 0;
   }
   size_t stageBytes = 0;
   bool anyStaged = false;
@@ -1065,10 +1089,11 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups) {
   // keep >= 128 rows for the direct tail so that the last staged tile's 16-byte bitmap over-read
   // stays inside the column
   P.numFullTiles = anyStaged && P.numRows > 128 ? (P.numRows - 128) / tileRows : 0;
-  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; P.numStages = 0; }
+  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; P.numStages = 0; P.denseNd = 0; if (slots > 8192) slots = 8192; }
   P.stageBytes = (uint32_t)stageBytes;
   P.smemSlots = slots;
-  return 128 + (size_t)slots * 8 + stageBytes * P.numStages;
+  P.tableBytes = P.denseNd != 0 ? (slots * 9 + 127) / 128 * 128 : slots * 8;
+  return 128 + (size_t)P.tableBytes + stageBytes * P.numStages;
 }
 
 static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
@@ -1104,19 +1129,27 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
       col.in.startBit = 0;
     }
   }
-  const size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
+  size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
   static bool attrSet[64] = {false};
   if (!attrSet[st->device & 63]) {
     ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
     attrSet[st->device & 63] = true;
   }
-  int grid = smCount() < kMaxGridCtas ? smCount() : kMaxGridCtas;
-  const uint32_t work = P.staged ? P.numFullTiles : (P.numRows + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
-  if ((uint32_t)grid > work) grid = work ? (int)work : 1;
+  auto gridFor = [&]() {
+    int g = smCount() < kMaxGridCtas ? smCount() : kMaxGridCtas;
+    const uint32_t work = P.staged ? P.numFullTiles : (P.numRows + 4 * kFusedThreads - 1) / (4 * kFusedThreads);
+    if ((uint32_t)g > work) g = work ? (int)work : 1;
+    return g;
+  };
+  int grid = gridFor();
   // the specialised kernel covers the staged tiles AND the tail; the interpreter below is the
   // generic fallback (unaligned / RLE columns, NVRTC unavailable or disabled)
   if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) return;
+  if (P.denseNd != 0) {  // the interpreter needs the key-table layout
+    smemBytes = layoutStages(P, st->spec.ExpectedGroups, /*allowDense=*/false);
+    grid = gridFor();
+  }
   if (st->keyMode == KEY_HASHED) fusedBatchKernel<true><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
   else fusedBatchKernel<false><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
   checkLastError("ExecuteBatchPlan");

@@ -39,9 +39,10 @@ static __device__ __noinline__ void denseSlowRow(const JitParams &P, const uint3
 //   0  the CTA's private slice of global memory, updated with fire-and-forget RED (one L2 atomic per row);
 //   1  shared memory (native ATOMS for 4-byte aggregates, a CAS loop for 8-byte ones);
 //   2  both: row positions 0-1 of a quad go to shared memory, 2-3 to the L2 slice, so that neither the SM's
-//      shared-memory atomic path nor the L2 atomic units carry the whole stream; the flush adds the two halves.
-constexpr uint32_t kDenseCap = JIT_SMEM_SLOTS / 8 * 7;   // touched bytes + 8-byte accumulators fit the key region
-// layout of the key region (dynamic shared memory + 128) in this mode: touched[kDenseCap] | acc[kDenseCap] (8 bytes each)
+//      shared-memory atomic path nor its global-atomic path carries the whole stream; the flush adds the two halves;
+//   3  as 2 with three row positions in shared memory and one in the L2 slice.
+constexpr uint32_t kDenseCap = JIT_SMEM_SLOTS;   // a multiple of 16; JIT_TABLE_BYTES >= 9 * kDenseCap
+// layout of the table region (dynamic shared memory + 128) in this mode: touched[kDenseCap] | acc[kDenseCap] (8 bytes each)
 __device__ __forceinline__ unsigned long long *denseSharedAcc() {
   extern __shared__ __align__(128) uint8_t denseSmem[];
   return reinterpret_cast<unsigned long long *>(denseSmem + 128 + kDenseCap);
@@ -104,7 +105,7 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    const bool toShared = JIT_DENSE_ACC == 1 || (JIT_DENSE_ACC == 2 && r < 2);
+    const bool toShared = JIT_DENSE_ACC == 1 || (JIT_DENSE_ACC == 2 && r < 2) || (JIT_DENSE_ACC == 3 && r < 3);
     if (toShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
     else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
   }
@@ -174,7 +175,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   // keys of the CTA's table in shared memory (latency-critical, read-mostly); accumulators in an
   // L2-resident private slice of global memory, updated with fire-and-forget RED
   unsigned long long *tAcc = P.ctaAcc + (size_t)blockIdx.x * JIT_SMEM_SLOTS;
-  uint8_t *stages = reinterpret_cast<uint8_t *>(tKeys + JIT_SMEM_SLOTS);
+  uint8_t *stages = smem + 128 + JIT_TABLE_BYTES;
 
   SmemTable T;
   T.keys = tKeys; T.acc = tAcc; T.claims = claims; T.mask = JIT_SMEM_SLOTS - 1;

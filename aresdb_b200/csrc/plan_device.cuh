@@ -64,11 +64,22 @@ struct DevPlan {
   uint8_t keyMode, rowBytes, valueBytes, hashBits;
   uint8_t aggOp, measWidth, measClass, skipCount;
   uint8_t hasMeasure, staged, hll, bypassOk;
+  // direct-indexed aggregation (jitAnalyzeDense; denseNd == 0: hash table).  Dimension k is produced by instruction
+  // denseInst[k]; its slot index is (quotient or value) - denseLo[k], below denseCnt[k]; index denseCnt[k] = NULL.
+  uint8_t denseNd;
+  uint8_t denseInst[8], denseViaQuot[8], denseNullCanon[8];
+  uint32_t denseLo[8], denseCnt[8], denseStep[8];
+  uint32_t denseTotal;     // slots of one copy = prod (denseCnt[k] + 1)
+  uint32_t tableBytes;     // shared memory between the header and the first stage (keys, or flags + accumulators)
 };
+
+constexpr uint32_t kDenseMaxSlots = 8192;   // = slots of a CTA's accumulator slice in AggState::ctaAcc
 
 // jit.cu: runs the staged tiles of `P` with a kernel specialised for the plan's shape.  Returns false
 // when NVRTC is unavailable or disabled (ARESDB_B200_JIT=0) so that the caller falls back to the
 // interpreter kernel; throws EngineError when code generation / compilation fails.
+bool jitAvailable();
+void jitAnalyzeDense(DevPlan &P, bool bypass);
 size_t jitCompileOnly(const DevPlan &P, std::string *sourceOut);
 bool jitLaunchStaged(const DevPlan &P, const DevTable &G, size_t smemBytes, int grid, cudaStream_t s);
 
