@@ -89,17 +89,13 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
   } else if (p) smemAtomic((AggOp)OP, generic, v);
 }
 
-__device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P, uint32_t alive,
-                                                  const uint32_t (&dslot)[4], const uint32_t (&dv)[4][JIT_ND],
-                                                  const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
+__device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P,
+                                                  const bool (&fast)[4], const bool (&slow)[4], const uint32_t (&dslot)[4],
+                                                  const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
   const uint32_t rep = (threadIdx.x & (P.dReps - 1u)) * P.dTotal;
   uint32_t s[4];
-  bool fast[4];
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    fast[r] = ((alive >> r) & 1) && dslot[r] != 0xFFFFFFFFu;
-    s[r] = dslot[r] + rep;
-  }
+  for (int r = 0; r < 4; r++) s[r] = dslot[r] + rep;
 #pragma unroll
   for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
@@ -109,10 +105,10 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     if (toShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
     else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
   }
-  if (__builtin_expect(((alive & 1) && !fast[0]) || ((alive & 2) && !fast[1]) || ((alive & 4) && !fast[2]) || ((alive & 8) && !fast[3]), 0)) {
+  if (slow[0] || slow[1] || slow[2] || slow[3]) {
 #pragma unroll
     for (int r = 0; r < 4; r++)
-      if (((alive >> r) & 1) && !fast[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
+      if (slow[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
   }
 }
 #endif
@@ -236,8 +232,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         uint64_t meas[4];
 #if JIT_DENSE
         uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
-        const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, dslot, dv, dvalid, meas);
-        jitAggregateDense(touchedAddr, tAcc, P, alive, dslot, dv, dvalid, meas);
+        bool fast[4], slow[4];
+        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, slow, dslot, dv, dvalid, meas))
+          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas);
         (void)allowClaim; (void)bypass;
 #else
         uint64_t key[4][JIT_KW];
@@ -275,9 +272,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         const uint32_t nvalid = rows - q * 4 < 4 ? rows - q * 4 : 4;
 #if JIT_DENSE
         uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
-        uint32_t alive = rowEval(stages, q, done + q * 4, P, dslot, dv, dvalid, meas);
-        alive &= (1u << nvalid) - 1u;
-        jitAggregateDense(touchedAddr, tAcc, P, alive, dslot, dv, dvalid, meas);
+        bool fast[4], slow[4];
+        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, slow, dslot, dv, dvalid, meas))
+          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas);
 #else
         uint64_t key[4][JIT_KW];
         uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
