@@ -96,8 +96,10 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   uint32_t s[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) s[r] = dslot[r] + rep;
+  if (JIT_DENSE_FLAGS) {
 #pragma unroll
-  for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
+    for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
+  }
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
 #pragma unroll
   for (int r = 0; r < 4; r++) {
@@ -290,7 +292,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #if JIT_DENSE
   // fold the touched slots into the global table: the slot index decodes to the dimension values
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
-    if (!touched[i]) continue;
+    if (JIT_DENSE_FLAGS ? !touched[i] : (uint32_t)denseSharedAcc()[i] == 0u) continue;
     uint32_t rem = i % P.dTotal, dvr[JIT_ND], vb = 0;
 #pragma unroll
     for (int k = JIT_ND - 1; k >= 0; k--) {

@@ -178,30 +178,38 @@ void radixSortPairs(uint64_t *keys, V *vals, uint64_t *keysTmp, V *valsTmp, int 
   }
 }
 
-// One CTA: bucket by the top 8 key bits (unordered scatter into the tmp arrays), then every element finds its
-// rank inside its bucket by comparing (key, index) with the bucket's other members.  With hash keys a bucket
-// holds n / 256 elements, so the rank loop is short; a degenerate bucket only costs time, never correctness.
+// One CTA: bucket by the top kSmallBits key bits (unordered scatter into the tmp arrays), then every element
+// finds its rank inside its bucket by comparing (key, index) with the bucket's other members.  With hash keys and
+// 4096 buckets a bucket of the largest input (32768 keys) holds 8 elements on average, so the rank loop is a handful
+// of L1-resident loads; a degenerate bucket only costs time, never correctness.
+constexpr int kSmallBits = 12;
+constexpr int kSmallBuckets = 1 << kSmallBits;
 __global__ void __launch_bounds__(1024)
 smallSortKernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ index, uint64_t *__restrict__ tmpK,
                 uint32_t *__restrict__ tmpI, int n, int shift) {
-  __shared__ uint32_t cnt[kRadix], off[kRadix + 1], cur[kRadix];
+  __shared__ uint32_t cnt[kSmallBuckets], off[kSmallBuckets + 1];
   __shared__ uint32_t sWarp[1024 / 32 + 1];
-  if (threadIdx.x < kRadix) { cnt[threadIdx.x] = 0; cur[threadIdx.x] = 0; }
+  constexpr int kPer = kSmallBuckets / 1024;   // buckets per thread in the scan
+  for (int b = threadIdx.x; b < kSmallBuckets; b += 1024) cnt[b] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += 1024) atomicAdd(&cnt[(uint32_t)(keys[i] >> shift) & (kRadix - 1)], 1u);
+  for (int i = threadIdx.x; i < n; i += 1024) atomicAdd(&cnt[(uint32_t)(keys[i] >> shift) & (kSmallBuckets - 1)], 1u);
   __syncthreads();
   {
-    uint32_t total;
-    const uint32_t c = threadIdx.x < kRadix ? cnt[threadIdx.x] : 0;
-    const uint32_t excl = blockExclusiveScan<1024>(c, sWarp, &total);
-    if (threadIdx.x < kRadix) off[threadIdx.x] = excl;
-    if (threadIdx.x == 0) off[kRadix] = total;
+    uint32_t c[kPer], sum = 0, total;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) { c[j] = cnt[threadIdx.x * kPer + j]; sum += c[j]; }
+    uint32_t excl = blockExclusiveScan<1024>(sum, sWarp, &total);
+#pragma unroll
+    for (int j = 0; j < kPer; j++) { off[threadIdx.x * kPer + j] = excl; excl += c[j]; }
+    if (threadIdx.x == 0) off[kSmallBuckets] = total;
   }
+  __syncthreads();
+  for (int b = threadIdx.x; b < kSmallBuckets; b += 1024) cnt[b] = 0;   // reused as the scatter cursors
   __syncthreads();
   for (int i = threadIdx.x; i < n; i += 1024) {
     const uint64_t k = keys[i];
-    const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
-    const uint32_t p = off[d] + atomicAdd(&cur[d], 1u);
+    const uint32_t d = (uint32_t)(k >> shift) & (kSmallBuckets - 1);
+    const uint32_t p = off[d] + atomicAdd(&cnt[d], 1u);
     tmpK[p] = k;
     tmpI[p] = index[i];
   }
@@ -209,7 +217,7 @@ smallSortKernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ index, uint6
   for (int i = threadIdx.x; i < n; i += 1024) {
     const uint64_t k = tmpK[i];
     const uint32_t v = tmpI[i];
-    const uint32_t d = (uint32_t)(k >> shift) & (kRadix - 1);
+    const uint32_t d = (uint32_t)(k >> shift) & (kSmallBuckets - 1);
     const uint32_t lo = off[d], hi = off[d + 1];
     uint32_t rank = 0;
     for (uint32_t j = lo; j < hi; j++) {
@@ -224,11 +232,11 @@ smallSortKernel(uint64_t *__restrict__ keys, uint32_t *__restrict__ index, uint6
 void sortKeyIndexPairs(uint64_t *keys, uint32_t *index, uint64_t *keysTmp, uint32_t *indexTmp, int n, int keyBits,
                        cudaStream_t s) {
   if (n <= 1) return;
-  if (n > kSmallSortMax || keyBits < kRadixBits) {
+  if (n > kSmallSortMax || keyBits < kSmallBits) {
     radixSortPairs<uint32_t>(keys, index, keysTmp, indexTmp, n, 0, keyBits, s);
     return;
   }
-  smallSortKernel<<<1, 1024, 0, s>>>(keys, index, keysTmp, indexTmp, n, keyBits - kRadixBits);
+  smallSortKernel<<<1, 1024, 0, s>>>(keys, index, keysTmp, indexTmp, n, keyBits - kSmallBits);
   checkLastError("sortKeyIndexPairs");
 }
 
