@@ -636,6 +636,41 @@ fillTableKernel(unsigned long long *keys, unsigned long long *acc, size_t cap, u
   }
 }
 
+// Global dense slots (DevPlan::denseGlobal): after the batch, every reached slot of the state's accumulator array is
+// folded into the group table under the packed dimension row its index decodes to, and reset to the neutral element.
+struct DenseFold {
+  uint32_t lo[8], cnt[8], step[8], stride[8];
+  uint8_t rowOff[8], width[8], nullOff[8];
+  uint32_t nd, total;
+  uint8_t keyMode, hashBits, rowBytes, op;
+  unsigned long long neutral;
+};
+
+__global__ void __launch_bounds__(256)
+denseFoldKernel(unsigned long long *__restrict__ acc, DenseFold F, DevTable G) {
+  const uint32_t strideAll = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.total; i += strideAll) {
+    const unsigned long long v = acc[i];
+    if (v == F.neutral) continue;
+    acc[i] = F.neutral;
+    uint64_t row[4] = {0, 0, 0, 0};
+    uint8_t *rb = reinterpret_cast<uint8_t *>(row);
+    uint32_t rem = i;
+    for (int k = (int)F.nd - 1; k >= 0; k--) {
+      const uint32_t ix = rem / F.stride[k];
+      rem -= ix * F.stride[k];
+      const bool valid = ix != F.cnt[k];
+      const uint32_t val = valid ? (F.lo[k] + ix) * F.step[k] : 0u;
+      for (int b = 0; b < F.width[k]; b++) rb[F.rowOff[k] + b] = (uint8_t)(val >> (8 * b));
+      rb[F.nullOff[k]] = valid ? 1 : 0;
+    }
+    unsigned long long key;
+    if (F.keyMode == KEY_PACKED) key = row[0];
+    else key = F.hashBits == 64 ? murmur3_128_lo(row, F.rowBytes, 0) : (unsigned long long)murmur3_32(row, F.rowBytes, 0);
+    globalUpdate(G, (AggOp)F.op, key, F.keyMode == KEY_PACKED ? nullptr : row, v);
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -655,6 +690,7 @@ struct AggState {
   DevTable table;
   void *mem;               // single allocation behind the table
   unsigned long long *ctaAcc;  // [kMaxGridCtas][8192] private accumulator slices of the fused kernel's CTAs
+  unsigned long long *denseAcc = nullptr;  // [kGlobalDenseMaxSlots] shared accumulators of the global dense form (lazy)
 };
 
 constexpr uint32_t kHllDenseMaxGroups = 4096;   // dense HLL: directory of 8192 slots, 64 KB of registers per slot
@@ -932,6 +968,17 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
   P.valueBytes = (uint8_t)RL.valueBytes;
   P.hashBits = (uint8_t)st->hashBits;
   P.aggOp = st->op;
+  {  // can a reached accumulator return to the neutral element?  (global dense slots carry no "reached" flags)
+    bool safe = st->op != OP_SUM_I32 && st->op != OP_SUM_I64;   // float sums (-0.0), min / max (extreme), AVG (count 0)
+    if (!safe)   // integer sums: only of a positive literal (count(*)): never 0 again below 2^32 rows
+      for (int i = 0; i < P.ninsts; i++) {
+        const DevInst &I = P.insts[i];
+        if (I.sink == PLAN_SINK_MEASURE && !I.wide && I.nops == 1 && I.fn == Noop && I.akind == OPK_CONST && I.avalid &&
+            (I.aclass == VC_I32 || I.aclass == VC_U32) && (int32_t)I.aconst > 0)
+          safe = true;
+      }
+    P.neutralSafe = safe && !st->hll;
+  }
   P.measWidth = (uint8_t)st->measWidth;
   P.measClass = st->measClass;
   P.hll = st->hll ? (st->hllDense ? 2 : 1) : 0;
@@ -1002,6 +1049,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   // (group, register) pairs): compile the kernel with the direct-to-global mode it can switch to.
   P.bypassOk = (P.hll || expectedGroups > 4 * slots) ? 1 : 0;
   // zone map known for every dimension: no key table, slots addressed by dimension value (jit.cu)
+  P.denseGlobal = 0;
   if (allowDense) jitAnalyzeDense(P, P.bypassOk != 0);
   else P.denseNd = 0;
   if (const char *e = getenv("ARESDB_B200_SMEM_SLOTS")) {  // tuning / experiments
@@ -1038,6 +1086,14 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
           if (cap >= P.denseTotal) { tileRows = tr; stages = n; slots = cap; }
         }
         if (tileRows) break;
+      }
+      if (!tileRows && P.neutralSafe && P.denseTotal <= kGlobalDenseMaxSlots) {
+        // more slots than a CTA holds: one accumulator array in global memory for the whole grid; shared memory is all ring
+        for (uint32_t tr : {3968u, 1920u, 896u}) {
+          if (forceTile && tr != forceTile) continue;
+          const uint32_t n = (uint32_t)(((size_t)kSmemBudget - 128 - 256) / stageBytesFor(tr));
+          if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; slots = 16; P.denseGlobal = 1; break; }
+        }
       }
       if (!tileRows) P.denseNd = 0;   // no layout holds the slots: hash table
     }
@@ -1089,7 +1145,8 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   // keep >= 128 rows for the direct tail so that the last staged tile's 16-byte bitmap over-read
   // stays inside the column
   P.numFullTiles = anyStaged && P.numRows > 128 ? (P.numRows - 128) / tileRows : 0;
-  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; P.numStages = 0; P.denseNd = 0; if (slots > 8192) slots = 8192; }
+  if (P.numFullTiles == 0) { P.staged = 0; stageBytes = 0; P.numStages = 0; P.denseNd = 0; P.denseGlobal = 0; if (slots > 8192 || slots < 256) slots = 8192; }
+  if (P.denseNd == 0) P.denseGlobal = 0;
   P.stageBytes = (uint32_t)stageBytes;
   P.smemSlots = slots;
   P.tableBytes = P.denseNd != 0 ? (slots * 9 + 127) / 128 * 128 : slots * 8;
@@ -1143,9 +1200,40 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
     return g;
   };
   int grid = gridFor();
+  if (P.denseGlobal) {
+    if (!st->denseAcc) {   // first use: 16 MB of accumulators at the neutral element (denseFoldKernel leaves them so)
+      void *mem = nullptr;
+      CGoCallResHandle h = deviceMalloc(&mem, (size_t)kGlobalDenseMaxSlots * sizeof(unsigned long long));
+      if (h.pStrErr) { std::string m(h.pStrErr); free((void *)h.pStrErr); throw EngineError(m); }
+      st->denseAcc = static_cast<unsigned long long *>(mem);
+      fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->denseAcc, st->denseAcc, kGlobalDenseMaxSlots, st->accNeutral);
+      checkLastError("denseAcc fill");
+    }
+    P.denseAcc = st->denseAcc;
+  }
   // the specialised kernel covers the staged tiles AND the tail; the interpreter below is the
   // generic fallback (unaligned / RLE columns, NVRTC unavailable or disabled)
-  if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) return;
+  if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) {
+    if (P.denseGlobal) {
+      DenseFold F;
+      memset(&F, 0, sizeof(F));
+      uint32_t stride = 1;
+      for (int k = 0; k < P.denseNd; k++) {
+        const DevInst &I = P.insts[P.denseInst[k]];
+        F.lo[k] = P.denseLo[k]; F.cnt[k] = P.denseCnt[k]; F.step[k] = P.denseStep[k]; F.stride[k] = stride;
+        F.rowOff[k] = I.rowOff; F.width[k] = I.width; F.nullOff[k] = I.nullOff;
+        stride *= P.denseCnt[k] + 1;
+      }
+      F.nd = P.denseNd; F.total = P.denseTotal;
+      F.keyMode = P.keyMode; F.hashBits = P.hashBits; F.rowBytes = P.rowBytes; F.op = P.aggOp;
+      F.neutral = P.accNeutral;
+      int blocks = divUp((int64_t)P.denseTotal, 256);
+      if (blocks > smCount() * 8) blocks = smCount() * 8;
+      denseFoldKernel<<<blocks, 256, 0, s>>>(st->denseAcc, F, st->table);
+      checkLastError("denseFold");
+    }
+    return;
+  }
   if (P.denseNd != 0) {  // the interpreter needs the key-table layout
     smemBytes = layoutStages(P, st->spec.ExpectedGroups, /*allowDense=*/false);
     grid = gridFor();
@@ -1471,6 +1559,7 @@ CGoCallResHandle AggStateDestroy(void *state, int device) {
   return guarded("AggStateDestroy", device, [&]() -> int64_t {
     AggState *st = asState(state);
     if (st->mem) deviceFree(st->mem);
+    if (st->denseAcc) deviceFree(st->denseAcc);
     delete st;
     return 0;
   });

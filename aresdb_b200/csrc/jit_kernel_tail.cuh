@@ -89,10 +89,64 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
   } else if (p) smemAtomic((AggOp)OP, generic, v);
 }
 
+// N double adds into shared memory at once: the loads and compare-and-swaps of the N rows are issued back to back so
+// that their latencies overlap (one CAS loop per row in sequence leaves the warp waiting on the shared-memory
+// scoreboard for most of its time: profiles/r01_summary.md).
+template <int N>
+__device__ __forceinline__ void addSharedF64Multi(const uint32_t (&addr)[N], const uint64_t (&v)[N], const bool (&p)[N]) {
+  unsigned long long old[N];
+  bool need[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    need[i] = p[i];
+    old[i] = 0;
+    if (need[i]) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(old[i]) : "r"(addr[i]) : "memory");
+  }
+  bool any;
+  do {
+    unsigned long long got[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      got[i] = old[i];
+      if (need[i]) {
+        const unsigned long long want =
+            (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[i]) + __longlong_as_double((long long)v[i]));
+        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(got[i]) : "r"(addr[i]), "l"(old[i]), "l"(want) : "memory");
+      }
+    }
+    any = false;
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      need[i] = need[i] && got[i] != old[i];
+      old[i] = got[i];
+      any = any || need[i];
+    }
+  } while (any);
+}
+
 __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P,
                                                   const bool (&fast)[4], const bool (&slow)[4], const uint32_t (&dslot)[4],
                                                   const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
-  const uint32_t rep = (threadIdx.x & (P.dReps - 1u)) * P.dTotal;
+  if (JIT_DENSE == 2) {
+    // One accumulator array for the whole grid (more slots than a CTA holds).  No flags: a slot was reached iff it
+    // differs from the aggregate's neutral element, so a row whose value would leave it there (-0.0 for float sums,
+    // the extreme for min / max) goes down the hash path instead; the host only selects this form for aggregates
+    // that cannot return to the neutral element otherwise.
+    bool later[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const bool f = fast[r] && meas[r] != P.accNeutral;
+      later[r] = slow[r] || (fast[r] && !f);
+      redGlobalPred<JIT_AGG_OP>(P.gAcc + dslot[r], meas[r], f);
+    }
+    if (later[0] || later[1] || later[2] || later[3]) {
+#pragma unroll
+      for (int r = 0; r < 4; r++)
+        if (later[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
+    }
+    return;
+  }
+  const uint32_t rep = (threadIdx.x & (P.dReps - 1u)) * P.dRepStride;
   uint32_t s[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) s[r] = dslot[r] + rep;
@@ -101,11 +155,23 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
   }
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
+  constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
+  if (JIT_AGG_OP == OP_SUM_F64 && kToShared > 0) {
+    uint32_t a[kToShared > 0 ? kToShared : 1];
+    uint64_t v[kToShared > 0 ? kToShared : 1];
+    bool p[kToShared > 0 ? kToShared : 1];
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    const bool toShared = JIT_DENSE_ACC == 1 || (JIT_DENSE_ACC == 2 && r < 2) || (JIT_DENSE_ACC == 3 && r < 3);
-    if (toShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
-    else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
+    for (int r = 0; r < kToShared; r++) { a[r] = sAccAddr + 8u * s[r]; v[r] = meas[r]; p[r] = fast[r]; }
+    // the L2 half first: fire-and-forget, in flight while the shared-memory half spins
+#pragma unroll
+    for (int r = kToShared; r < 4; r++) redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
+    addSharedF64Multi<(kToShared > 0 ? kToShared : 1)>(a, v, p);
+  } else {
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
+      else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
+    }
   }
   if (slow[0] || slow[1] || slow[2] || slow[3]) {
 #pragma unroll
@@ -182,7 +248,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   uint8_t *touched = reinterpret_cast<uint8_t *>(tKeys);
   uint32_t touchedAddr = smemAddr(touched);
   asm volatile("" : "+r"(touchedAddr));   // keep it in a register: the compiler otherwise rebuilds the window address per store
-  const uint32_t denseSlots = P.dTotal * P.dReps;   // <= kDenseCap (host)
+  const uint32_t denseSlots = JIT_DENSE == 2 ? 0u : P.dRepStride * P.dReps;   // <= kDenseCap (host); 2: nothing CTA-private
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
     touched[i] = 0;
     if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
@@ -289,11 +355,13 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   }
   __syncthreads();
   if (JIT_HLL == 2) return;  // nothing CTA-private to fold: registers are updated in place
-#if JIT_DENSE
+#if JIT_DENSE == 2
+  return;   // denseFoldKernel (batch_plan.cu) folds the shared array after the batch
+#elif JIT_DENSE
   // fold the touched slots into the global table: the slot index decodes to the dimension values
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
     if (JIT_DENSE_FLAGS ? !touched[i] : (uint32_t)denseSharedAcc()[i] == 0u) continue;
-    uint32_t rem = i % P.dTotal, dvr[JIT_ND], vb = 0;
+    uint32_t rem = i % P.dRepStride, dvr[JIT_ND], vb = 0;   // (padding slots between copies are never reached)
 #pragma unroll
     for (int k = JIT_ND - 1; k >= 0; k--) {
       const uint32_t ix = rem / P.dStride[k];

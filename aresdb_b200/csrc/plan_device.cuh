@@ -71,9 +71,16 @@ struct DevPlan {
   uint32_t denseLo[8], denseCnt[8], denseStep[8];
   uint32_t denseTotal;     // slots of one copy = prod (denseCnt[k] + 1)
   uint32_t tableBytes;     // shared memory between the header and the first stage (keys, or flags + accumulators)
+  // more slots than a CTA holds: ONE array of accumulators in global memory (L2-resident) shared by all CTAs, folded
+  // into the group table by denseFoldKernel after the batch; a slot was reached iff it differs from accNeutral
+  unsigned long long *denseAcc;
+  uint8_t denseGlobal;
+  uint8_t neutralSafe;     // no sequence of row values can bring a reached accumulator back to accNeutral (set by compilePlan)
+  uint8_t pad2[6];
 };
 
 constexpr uint32_t kDenseMaxSlots = 8192;   // = slots of a CTA's accumulator slice in AggState::ctaAcc
+constexpr uint32_t kGlobalDenseMaxSlots = 1u << 21;   // 16 MB of accumulators per state, allocated on first use
 
 // jit.cu: runs the staged tiles of `P` with a kernel specialised for the plan's shape.  Returns false
 // when NVRTC is unavailable or disabled (ARESDB_B200_JIT=0) so that the caller falls back to the

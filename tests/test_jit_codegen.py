@@ -5,6 +5,9 @@ import ctypes as C
 
 import pytest
 
+from aresdb_b200 import expr as E
+from aresdb_b200.query import AggQuery, Measure
+
 from aresdb_b200 import cabi as A
 from aresdb_b200 import columns, synth
 import test_pipeline_parity as T
@@ -160,9 +163,16 @@ def test_zone_map_selects_direct_indexed_aggregation():
     # no zone map / only one of the two dimensions bounded / range too wide for the CTA's slots
     assert "#define JIT_DENSE 0" in _dry_run(lib, q)[1]
     assert "#define JIT_DENSE 0" in _dry_run(lib, q, ranges={synth.COL_CITY_ID: (0, 100)})[1]
+    # more slots than a CTA holds (25 hours x 65537 cities): ONE accumulator array in global memory for the whole grid
     wide = dict(DAY_RANGES)
     wide[synth.COL_CITY_ID] = (0, 65535)
-    assert "#define JIT_DENSE 0" in _dry_run(lib, q, ranges=wide)[1]
+    assert "#define JIT_DENSE 2" in _dry_run(lib, q, ranges=wide)[1]
+    # ... which has no "reached" flags, so a sum of an integer column (may return to 0) keeps the hash table there,
+    wide_int = AggQuery(q.filters, [E.floor(T.TS, E.Lit(3600)), T.CITY], Measure("sum", T.CITY))
+    assert "#define JIT_DENSE 0" in _dry_run(lib, wide_int, ranges=wide)[1]
+    assert "#define JIT_DENSE 2" in _dry_run(lib, AggQuery(q.filters, [E.floor(T.TS, E.Lit(3600)), T.CITY], Measure("count")), ranges=wide)[1]
+    # and beyond 2^21 slots nothing is dense
+    assert "#define JIT_DENSE 0" in _dry_run(lib, AggQuery([], [T.TS, T.CITY], Measure("count")), ranges=DAY_RANGES)[1]
     # every aggregate of the suite compiles in the dense form
     for name, qq in list(T.queries().items()) + list(T.avg_queries().items()):
         size, s2 = _dry_run(lib, qq, ranges=DAY_RANGES)

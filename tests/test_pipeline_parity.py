@@ -139,7 +139,8 @@ def zone_maps_for(host_batches, mode):
     return exact[1:] + exact[:1]
 
 
-DENSE_QUERIES = ["cfg2", "cfg3_sum", "cfg3_count", "int_sum", "min_city"]   # every dimension bounded by the zone map
+# every dimension bounded by the zone map: slots in the CTAs, or (cfg4_hash: minute x city, 75,000 slots) one global array
+DENSE_QUERIES = ["cfg2", "cfg3_sum", "cfg3_count", "cfg4_hash", "int_sum", "min_city"]
 
 
 @pytest.mark.gpu
@@ -156,7 +157,7 @@ def test_fused_plan_with_zone_maps_on_b200(name, mode, host_batches):
     assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"{name}/{mode}")
     if name in DENSE_QUERIES:
         assert dense_launches(eng) - before == len(host_batches), "the direct-indexed kernel did not run"
-    else:   # minute buckets x city, raw timestamps or a float quotient as a dimension: the hash table stays
+    else:   # raw timestamps or a float quotient as a dimension: the hash table stays
         assert dense_launches(eng) == before
 
 
@@ -185,6 +186,34 @@ def test_zone_map_null_dimensions_and_replicas():
         else:
             assert_same_result(got, exp, ctx="null dims")
         assert dense_launches(eng) - before == len(hbs)
+
+
+@pytest.mark.gpu
+def test_zone_map_global_slots():
+    """More slots than a CTA holds: one accumulator array for the whole grid, folded into the group table after each
+    batch.  It has no flags — a slot counts as reached when it differs from the neutral element — so rows whose value
+    would leave it there (-0.0 for float sums, the extreme for min / max) must still produce their group, and integer
+    column sums (which can return to 0) must not take this form."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    hbs = [synth.generate_batch(d, 30000, num_cities=40, null_rate=0.05) for d in range(2)]
+    rng = np.random.default_rng(11)
+    for hb in hbs:   # negative zeros and zeros among the fares; some city ids at the u16 extreme
+        f = hb.values[synth.COL_FARE]
+        f[rng.random(f.size) < 0.3] = np.float32(-0.0)
+        f[rng.random(f.size) < 0.1] = np.float32(0.0)
+    zms = [synth.zone_map(hb) for hb in hbs]
+    dims = [CITY, E.floor(TS, E.Lit(60))]
+    cases = [(AggQuery([], dims, Measure("sum", FARE), reduce_mode=A.ARES_REDUCE_HASH), True),
+             (AggQuery([], dims, Measure("count")), True),
+             (AggQuery([E.eq(STATUS, E.Lit(1))], dims, Measure("min", FARE)), True),
+             (AggQuery([], dims, Measure("max", CITY)), True),
+             (AggQuery([], dims, Measure("sum", CITY)), False)]
+    for q, dense in cases:
+        before = dense_launches(eng)
+        got = run_fused(eng, q, hbs, zone_maps=zms)
+        exp = run_legacy(orc, q, hbs)
+        assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"global slots {q.measure_kind}")
+        assert (dense_launches(eng) - before == len(hbs)) == dense
 
 
 @pytest.mark.gpu
