@@ -636,6 +636,14 @@ fillTableKernel(unsigned long long *keys, unsigned long long *acc, size_t cap, u
   }
 }
 
+// out[i] = in[i] + (+0.0): float sums of the hash-reduce mode (see finalize())
+__global__ void __launch_bounds__(256) copyPlusZeroKernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out, int n, int width) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  if (width == 8) reinterpret_cast<double *>(out)[i] = reinterpret_cast<const double *>(in)[i] + 0.0;
+  else reinterpret_cast<float *>(out)[i] = reinterpret_cast<const float *>(in)[i] + 0.0f;
+}
+
 // Global dense slots (DevPlan::denseGlobal): after the batch, every reached slot of the state's accumulator array is
 // folded into the group table under the packed dimension row its index decodes to, and reset to the neutral element.
 struct DenseFold {
@@ -1387,7 +1395,15 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
   emitGroupsKernel<<<blocks, 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), rep.as<uint32_t>(), (uint32_t)g,
                                           out.DimValues, L, out.IndexVector);
   checkLastError("emitGroups");
-  ARES_CUDA(cudaMemcpyAsync(outValues, mergedVals.ptr, (size_t)width * g, cudaMemcpyDeviceToDevice, s));
+  if (st->spec.ReduceMode == ARES_REDUCE_HASH && (st->op == OP_SUM_F64 || st->op == OP_SUM_F32)) {
+    // The reference's hash map folds every value into a slot that starts at the identity +0.0
+    // (query/hash_reduction.cu:246-249 + the map's unused element), so a group whose values are all -0.0 ends
+    // at +0.0 there, while its sort-reduce (and this table, whose neutral element is -0.0) keeps -0.0.
+    copyPlusZeroKernel<<<divUp(g, 256), 256, 0, s>>>(mergedVals.as<uint8_t>(), outValues, g, width);
+    checkLastError("copyPlusZero");
+  } else {
+    ARES_CUDA(cudaMemcpyAsync(outValues, mergedVals.ptr, (size_t)width * g, cudaMemcpyDeviceToDevice, s));
+  }
   ARES_CUDA(cudaStreamSynchronize(s));
   return g;
 }

@@ -89,41 +89,6 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
   } else if (p) smemAtomic((AggOp)OP, generic, v);
 }
 
-// N double adds into shared memory at once: the loads and compare-and-swaps of the N rows are issued back to back so
-// that their latencies overlap (one CAS loop per row in sequence leaves the warp waiting on the shared-memory
-// scoreboard for most of its time: profiles/r01_summary.md).
-template <int N>
-__device__ __forceinline__ void addSharedF64Multi(const uint32_t (&addr)[N], const uint64_t (&v)[N], const bool (&p)[N]) {
-  unsigned long long old[N];
-  bool need[N];
-#pragma unroll
-  for (int i = 0; i < N; i++) {
-    need[i] = p[i];
-    old[i] = 0;
-    if (need[i]) asm volatile("ld.shared.u64 %0, [%1];" : "=l"(old[i]) : "r"(addr[i]) : "memory");
-  }
-  bool any;
-  do {
-    unsigned long long got[N];
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      got[i] = old[i];
-      if (need[i]) {
-        const unsigned long long want =
-            (unsigned long long)__double_as_longlong(__longlong_as_double((long long)old[i]) + __longlong_as_double((long long)v[i]));
-        asm volatile("atom.shared.cas.b64 %0, [%1], %2, %3;" : "=l"(got[i]) : "r"(addr[i]), "l"(old[i]), "l"(want) : "memory");
-      }
-    }
-    any = false;
-#pragma unroll
-    for (int i = 0; i < N; i++) {
-      need[i] = need[i] && got[i] != old[i];
-      old[i] = got[i];
-      any = any || need[i];
-    }
-  } while (any);
-}
-
 __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P,
                                                   const bool (&fast)[4], const bool (&slow)[4], const uint32_t (&dslot)[4],
                                                   const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
@@ -155,23 +120,13 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
   }
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
+  // (issuing the compare-and-swap loops of the shared-memory rows interleaved instead of one after the other was
+  // measured and changed nothing: 0.376 vs 0.372 ms on cfg3)
   constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
-  if (JIT_AGG_OP == OP_SUM_F64 && kToShared > 0) {
-    uint32_t a[kToShared > 0 ? kToShared : 1];
-    uint64_t v[kToShared > 0 ? kToShared : 1];
-    bool p[kToShared > 0 ? kToShared : 1];
 #pragma unroll
-    for (int r = 0; r < kToShared; r++) { a[r] = sAccAddr + 8u * s[r]; v[r] = meas[r]; p[r] = fast[r]; }
-    // the L2 half first: fire-and-forget, in flight while the shared-memory half spins
-#pragma unroll
-    for (int r = kToShared; r < 4; r++) redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
-    addSharedF64Multi<(kToShared > 0 ? kToShared : 1)>(a, v, p);
-  } else {
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
-      else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
-    }
+  for (int r = 0; r < 4; r++) {
+    if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
+    else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
   }
   if (slow[0] || slow[1] || slow[2] || slow[3]) {
 #pragma unroll

@@ -188,6 +188,21 @@ def test_zone_map_null_dimensions_and_replicas():
         assert dense_launches(eng) - before == len(hbs)
 
 
+def test_negative_zero_sums_oracle_vs_reference():
+    """CPU: a group whose fares are all -0.0 sums to -0.0 through Sort + Reduce and to +0.0 through HashReduce (its map
+    folds into a slot that starts at +0.0) — pinned on the reference's HOST build, the GPU test below relies on it."""
+    ref, orc = H.get_backend("ref"), H.get_backend("oracle")
+    hbs = [synth.generate_batch(0, 4000, num_cities=40, null_rate=0.05)]
+    hbs[0].values[synth.COL_FARE][::3] = np.float32(-0.0)
+    dims = [CITY, E.floor(TS, E.Lit(60))]
+    for mode in (A.ARES_REDUCE_SORT, A.ARES_REDUCE_HASH):
+        q = AggQuery([], dims, Measure("sum", FARE), reduce_mode=mode)
+        exp, got = run_legacy(ref, q, hbs), run_legacy(orc, q, hbs)
+        assert_same_result(got, exp, ordered=mode == A.ARES_REDUCE_SORT, ctx=f"-0.0 sums, mode {mode}")
+        signs = np.signbit(exp.measures[exp.measures == 0])
+        assert signs.size > 0 and (signs.any() if mode == A.ARES_REDUCE_SORT else not signs.any())
+
+
 @pytest.mark.gpu
 def test_zone_map_global_slots():
     """More slots than a CTA holds: one accumulator array for the whole grid, folded into the group table after each
@@ -195,25 +210,25 @@ def test_zone_map_global_slots():
     would leave it there (-0.0 for float sums, the extreme for min / max) must still produce their group, and integer
     column sums (which can return to 0) must not take this form."""
     eng, orc = H.get_backend("b200"), H.get_backend("oracle")
-    hbs = [synth.generate_batch(d, 30000, num_cities=40, null_rate=0.05) for d in range(2)]
+    clean = [synth.generate_batch(d, 30000, num_cities=40, null_rate=0.05) for d in range(2)]
+    negz = [synth.generate_batch(d, 30000, num_cities=40, null_rate=0.05) for d in range(2)]
     rng = np.random.default_rng(11)
-    for hb in hbs:   # negative zeros and zeros among the fares; some city ids at the u16 extreme
+    for hb in negz:   # a third of the fares is -0.0: most of the (single-row) groups then sum to exactly -0.0
         f = hb.values[synth.COL_FARE]
         f[rng.random(f.size) < 0.3] = np.float32(-0.0)
-        f[rng.random(f.size) < 0.1] = np.float32(0.0)
-    zms = [synth.zone_map(hb) for hb in hbs]
     dims = [CITY, E.floor(TS, E.Lit(60))]
-    cases = [(AggQuery([], dims, Measure("sum", FARE), reduce_mode=A.ARES_REDUCE_HASH), True),
-             (AggQuery([], dims, Measure("count")), True),
-             (AggQuery([E.eq(STATUS, E.Lit(1))], dims, Measure("min", FARE)), True),
-             (AggQuery([], dims, Measure("max", CITY)), True),
-             (AggQuery([], dims, Measure("sum", CITY)), False)]
-    for q, dense in cases:
+    cases = [("sum, hash mode, -0.0", negz, AggQuery([], dims, Measure("sum", FARE), reduce_mode=A.ARES_REDUCE_HASH), True),
+             ("sum, sort mode, -0.0", negz, AggQuery([], dims, Measure("sum", FARE)), True),
+             ("count", clean, AggQuery([], dims, Measure("count")), True),
+             ("min float", clean, AggQuery([E.eq(STATUS, E.Lit(1))], dims, Measure("min", FARE)), True),
+             ("max u32 (0 = neutral)", clean, AggQuery([], dims, Measure("max", CITY)), True),
+             ("integer column sum", clean, AggQuery([], dims, Measure("sum", CITY)), False)]
+    for name, hbs, q, dense in cases:
         before = dense_launches(eng)
-        got = run_fused(eng, q, hbs, zone_maps=zms)
+        got = run_fused(eng, q, hbs, zone_maps=[synth.zone_map(hb) for hb in hbs])
         exp = run_legacy(orc, q, hbs)
-        assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"global slots {q.measure_kind}")
-        assert (dense_launches(eng) - before == len(hbs)) == dense
+        assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"global slots: {name}")
+        assert (dense_launches(eng) - before == len(hbs)) == dense, name
 
 
 @pytest.mark.gpu
