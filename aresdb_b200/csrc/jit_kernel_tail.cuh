@@ -100,7 +100,7 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     bool later[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const bool f = fast[r] && meas[r] != P.accNeutral;
+      const bool f = fast[r] && (!JIT_DENSE_CHECK || meas[r] != P.accNeutral);
       later[r] = slow[r] || (fast[r] && !f);
       redGlobalPred<JIT_AGG_OP>(P.gAcc + dslot[r], meas[r], f);
     }
@@ -113,11 +113,17 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   }
   const uint32_t rep = (threadIdx.x & (P.dReps - 1u)) * P.dRepStride;
   uint32_t s[4];
+  bool go[4], later[4];
 #pragma unroll
-  for (int r = 0; r < 4; r++) s[r] = dslot[r] + rep;
+  for (int r = 0; r < 4; r++) {
+    s[r] = dslot[r] + rep;
+    // no flags: a row that would leave its slot at the neutral element goes down the hash path instead
+    go[r] = fast[r] && (JIT_DENSE_FLAGS || !JIT_DENSE_CHECK || meas[r] != P.accNeutral);
+    later[r] = slow[r] || (fast[r] && !go[r]);
+  }
   if (JIT_DENSE_FLAGS) {
 #pragma unroll
-    for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], fast[r]);
+    for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], go[r]);
   }
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
   // (issuing the compare-and-swap loops of the shared-memory rows interleaved instead of one after the other was
@@ -125,13 +131,13 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
 #pragma unroll
   for (int r = 0; r < 4; r++) {
-    if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], fast[r]);
-    else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], fast[r]);
+    if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], go[r]);
+    else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], go[r]);
   }
-  if (slow[0] || slow[1] || slow[2] || slow[3]) {
+  if (later[0] || later[1] || later[2] || later[3]) {
 #pragma unroll
     for (int r = 0; r < 4; r++)
-      if (slow[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
+      if (later[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
   }
 }
 #endif
@@ -205,7 +211,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   asm volatile("" : "+r"(touchedAddr));   // keep it in a register: the compiler otherwise rebuilds the window address per store
   const uint32_t denseSlots = JIT_DENSE == 2 ? 0u : P.dRepStride * P.dReps;   // <= kDenseCap (host); 2: nothing CTA-private
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
-    touched[i] = 0;
+    if (JIT_DENSE_FLAGS) touched[i] = 0;
     if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
     if (JIT_DENSE_ACC != 0) denseSharedAcc()[i] = P.accNeutral;
   }
@@ -315,7 +321,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #elif JIT_DENSE
   // fold the touched slots into the global table: the slot index decodes to the dimension values
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
-    if (JIT_DENSE_FLAGS ? !touched[i] : (uint32_t)denseSharedAcc()[i] == 0u) continue;
+    const unsigned long long accS = JIT_DENSE_ACC != 0 ? denseSharedAcc()[i] : P.accNeutral;
+    const unsigned long long accG = JIT_DENSE_ACC != 1 ? __ldcg(&tAcc[i]) : P.accNeutral;
+    if (JIT_DENSE_FLAGS ? !touched[i] : (accS == P.accNeutral && accG == P.accNeutral)) continue;
     uint32_t rem = i % P.dRepStride, dvr[JIT_ND], vb = 0;   // (padding slots between copies are never reached)
 #pragma unroll
     for (int k = JIT_ND - 1; k >= 0; k--) {
@@ -328,8 +336,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     uint64_t key[JIT_KW];
     densePack(dvr, vb, key);
     const unsigned long long k = jitKeyOfRow(key);
-    if (JIT_DENSE_ACC != 1) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, __ldcg(&tAcc[i]));
-    if (JIT_DENSE_ACC != 0) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, denseSharedAcc()[i]);
+    if (JIT_DENSE_ACC != 1) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, accG);
+    if (JIT_DENSE_ACC != 0) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, accS);
   }
   return;
 #endif

@@ -170,10 +170,12 @@ def test_zone_map_null_dimensions_and_replicas():
     eng, orc = H.get_backend("b200"), H.get_backend("oracle")
     hbs = [synth.generate_batch(d, 25000, num_cities=7, null_rate=0.2) for d in range(2)]
     rng = np.random.default_rng(5)
-    for hb in hbs:   # garbage under some of the NULL city ids
-        c = hb.values[synth.COL_CITY_ID]
+    for hb in hbs:   # garbage under some of the NULL city ids; -0.0 fares (the neutral element of a float sum:
+        c = hb.values[synth.COL_CITY_ID]   # such rows must not be lost by the flag-less slots)
         dirty = (hb.valid[synth.COL_CITY_ID] == 0) & (rng.random(c.size) < 0.5)
         c[dirty] = 77
+        f = hb.values[synth.COL_FARE]
+        f[rng.random(f.size) < 0.2] = np.float32(-0.0)
     for q in (AggQuery([], [CITY, E.floor(TS, E.Lit(7200))], Measure("sum", FARE)),
               AggQuery([], [STATUS], Measure("count")),
               AggQuery([E.gt(FARE, E.Lit(50.0))], [CITY, STATUS], Measure("max", FARE)),
