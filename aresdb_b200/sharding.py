@@ -46,6 +46,14 @@ class ShardedFusedQuery:
         # the merged state sees every rank's groups: same table hint (and, for hll, the same table mode)
         merged_groups = expected_groups if merged_groups is None else merged_groups
         self.merged = FusedBatchExecutor(lib, space, q, merged_groups) if self.world > 1 else None
+        # Fixed-capacity exchange (queries that do not announce more groups than this): every rank sends
+        # [row count | dimension block | measures] for EXCHANGE_ROWS rows in ONE all-gather, so no count has to be agreed on
+        # first (one collective and one host sync less per query); a rank with more rows flags it in its header and
+        # every rank repeats the step with the exact-size protocol.
+        import os
+        self._fixed_cap = self.EXCHANGE_ROWS if (self.world > 1 and expected_groups <= self.EXCHANGE_ROWS and not q.is_hll
+                                                 and os.environ.get("ARESDB_B200_EXCHANGE", "fixed") != "exact") else 0
+        self._send = self._recv = None
 
     def reset(self):
         self.local.reset()
@@ -53,7 +61,48 @@ class ShardedFusedQuery:
     def process_batch(self, batch, stream=None):
         self.local.process_batch(batch, stream)
 
+    EXCHANGE_ROWS = 65536
+    _HDR = 64
+
+    def _exchange_fixed(self):
+        """Returns the number of rows gathered, or None when some rank holds more than EXCHANGE_ROWS rows."""
+        import torch
+        q, sp, dist, lib = self.q, self.space, self.dist, self.lib
+        cap = self._fixed_cap
+        _, _, _, dim_bytes = dim_offsets(q.num_dims_per_width, cap)
+        dim_bytes = (dim_bytes + 15) // 16 * 16
+        part = (self._HDR + dim_bytes + q.measure_bytes * cap + 63) // 64 * 64
+        if self._send is None:
+            self._send = torch.zeros(part, dtype=torch.uint8, device=sp.dev)
+            self._recv = torch.empty(self.world * part, dtype=torch.uint8, device=sp.dev)
+        send, recv = self._send, self._recv
+        base = send.data_ptr() + self._HDR
+        try:
+            dv = A.make_dimension_vector(base, None, None, q.num_dims_per_width, cap)
+            n = lib.AggStateExport(self.local.state, dv, base + dim_bytes, sp.stream, sp.device)
+        except A.AresError:
+            n = cap + 1   # more rows than the fixed part holds
+        send[:8].view(torch.int64).fill_(n)
+        dist.all_gather_into_tensor(recv, send)
+        counts = recv.view(self.world, part)[:, :8].contiguous().view(torch.int64).flatten().tolist()
+        if max(counts) > cap:
+            return None
+        self.merged.reset()
+        rbase = recv.data_ptr()
+        for r in range(self.world):
+            if counts[r]:
+                dv = A.make_dimension_vector(rbase + r * part + self._HDR, None, None, q.num_dims_per_width, cap)
+                self.merged.merge(dv, rbase + r * part + self._HDR + dim_bytes, counts[r])
+        return int(sum(counts))
+
     def _exchange(self):
+        if self._fixed_cap:
+            rows = self._exchange_fixed()
+            if rows is not None:
+                return rows
+        return self._exchange_exact()
+
+    def _exchange_exact(self):
         """The one exchange step: every rank exports its table (AggStateExport: unordered rows, no
         sort), ONE all-gather moves [dim block | measure vector] of every rank, and every rank folds
         all of them into `self.merged`.  Returns the number of rows gathered (an upper bound of the
