@@ -206,6 +206,29 @@ def test_negative_zero_sums_oracle_vs_reference():
 
 
 @pytest.mark.gpu
+def test_zone_map_wide_rows_and_small_batches():
+    """Dimension rows wider than 8 bytes are keyed by the reference hash of the packed row: the slots' flush
+    (CTA form) and denseFoldKernel (global form) must rebuild exactly those bytes.  Batches too small to be staged
+    ignore the zone map."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    hbs = [synth.generate_batch(d, 20011, num_cities=12, null_rate=0.03) for d in range(2)]
+    zms = [synth.zone_map(hb) for hb in hbs]
+    dims4 = [E.floor(TS, E.Lit(21600)), CITY, STATUS, E.floor(TS, E.Lit(86400))]      # 15-byte rows; 5 x 13 x 5 x 2 slots (CTA)
+    dims4g = [E.floor(TS, E.Lit(600)), CITY, STATUS, E.floor(TS, E.Lit(86400))]       # 146 x 13 x 5 x 2 slots (global array)
+    for dims, mode in ((dims4, A.ARES_REDUCE_SORT), (dims4, A.ARES_REDUCE_HASH), (dims4g, A.ARES_REDUCE_SORT), (dims4g, A.ARES_REDUCE_HASH)):
+        q = AggQuery([E.ne(CITY, E.Lit(3))], dims, Measure("sum", FARE), reduce_mode=mode)
+        assert q.row_bytes > 8
+        before = dense_launches(eng)
+        got, exp = run_fused(eng, q, hbs, zone_maps=zms), run_legacy(orc, q, hbs)
+        assert_same_result(got, exp, ordered=mode == A.ARES_REDUCE_SORT, ctx=f"wide rows, mode {mode}")
+        assert dense_launches(eng) - before == len(hbs)
+    q = queries()["cfg3_count"]
+    for rows in (1, 127, 1023, 1025, 4097):
+        hb = [synth.generate_batch(0, rows, num_cities=5)]
+        assert_same_result(run_fused(eng, q, hb, zone_maps=[synth.zone_map(hb[0])]), run_legacy(orc, q, hb), ctx=f"rows={rows}")
+
+
+@pytest.mark.gpu
 def test_zone_map_global_slots():
     """More slots than a CTA holds: one accumulator array for the whole grid, folded into the group table after each
     batch.  It has no flags — a slot counts as reached when it differs from the neutral element — so rows whose value

@@ -5,6 +5,7 @@
 set -u
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3 | tee gpurun_out/pytest_gpu.log
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -2 | tee gpurun_out/smoke.log
 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench_default.err | tee gpurun_out/bench_default.json | cut -c1-200
 python bench.py --impl reference --steps 2 --warmup 1 2>gpurun_out/bench_reference.err | tee gpurun_out/bench_reference.json | cut -c1-200
 for w in cfg2 cfg3_count cfg4 cfg4_hll; do
@@ -17,4 +18,6 @@ ncu --set full --clock-control none --import-source on -k regex:aresFusedJit -s 
     python bench.py --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:aresFusedJit -s 10 -c 1 -f -o gpurun_out/prof_fused_jit_count \
     python bench.py --workload cfg3_count --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full_count.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:aresFusedJit -s 10 -c 1 -f -o gpurun_out/prof_fused_jit_cfg4 \
+    python bench.py --workload cfg4 --steps 1 --warmup 3 --no-e2e --no-cpu > gpurun_out/ncu_full_cfg4.log 2>&1
 tail -2 gpurun_out/ncu_full.log
