@@ -50,13 +50,16 @@ def dim_offsets(num_dims_per_width, capacity: int):
 
 
 class _ResultBuffers:
-    def __init__(self, space, query: AggQuery, capacity: int):
+    def __init__(self, space, query: AggQuery, capacity: int, zero: bool = True):
+        """zero=True is what the reference's DeviceAllocate gives the per-node sequence (it reads carried rows back);
+        AggStateFinalize writes every byte of the rows it returns, so the fused path skips the four fill launches."""
         self.capacity = capacity
         _, _, _, total = dim_offsets(query.num_dims_per_width, capacity)
-        self.dims = space.zeros(total)
-        self.hash = space.zeros(8 * capacity)
-        self.index = space.zeros(4 * capacity)
-        self.measures = space.zeros(query.measure_bytes * capacity)
+        alloc = space.zeros if zero else space.empty
+        self.dims = alloc(total)
+        self.hash = alloc(8 * capacity)
+        self.index = alloc(4 * capacity)
+        self.measures = alloc(query.measure_bytes * capacity)
 
     def dimension_vector(self, query: AggQuery) -> A.DimensionVector:
         return A.make_dimension_vector(self.dims.ptr, self.hash.ptr, self.index.ptr, query.num_dims_per_width,
@@ -287,7 +290,7 @@ class FusedBatchExecutor:
     def finalize_into(self, capacity: int | None = None):
         """Returns (groups, _ResultBuffers) with the result left in device memory."""
         cap = max(capacity if capacity is not None else self.group_count(), 1)
-        out = _ResultBuffers(self.space, self.q, cap)
+        out = _ResultBuffers(self.space, self.q, cap, zero=not getattr(self.space, "is_cuda", False))
         g = self.lib.AggStateFinalize(self.state, out.dimension_vector(self.q), out.measures.ptr, self.space.stream,
                                       self.space.device)
         return g, out
