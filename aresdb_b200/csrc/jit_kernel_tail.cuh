@@ -91,8 +91,7 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
 
 __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P,
                                                   const bool (&fast)[4], const bool (&slow)[4], const uint32_t (&dslot)[4],
-                                                  const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4],
-                                                  const uint32_t (&mraw)[4]) {
+                                                  const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
   if (JIT_DENSE == 2) {
     // One accumulator array for the whole grid (more slots than a CTA holds).  No flags: a slot was reached iff it
     // differs from the aggregate's neutral element, so a row whose value would leave it there (-0.0 for float sums,
@@ -127,28 +126,6 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], go[r]);
   }
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
-  if (JIT_DENSE_ACC == 4) {
-    // exact integer accumulation of a float sum (see jit.cu): slot = (low word, high word) of a 64-bit integer
-    uint32_t ix[4];
-    bool onGrid[4];
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      const float x = __uint_as_float(mraw[r]);
-      const float y = x * P.fxScale;
-      ix[r] = __float2uint_rz(y);
-      onGrid[r] = go[r] && x > 0.0f && y < 4294967296.0f && __uint2float_rn(ix[r]) == y;
-    }
-#pragma unroll
-    for (int r = 0; r < 4; r++) redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], go[r] && !onGrid[r]);   // off the grid: double add
-#pragma unroll
-    for (int r = 0; r < 4; r++) {
-      if (onGrid[r]) {
-        uint32_t old;
-        asm volatile("atom.shared.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(sAccAddr + 8u * s[r]), "r"(ix[r]) : "memory");
-        if (old + ix[r] < old) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(sAccAddr + 8u * s[r] + 4u), "r"(1u) : "memory");
-      }
-    }
-  } else {
   // (issuing the compare-and-swap loops of the shared-memory rows interleaved instead of one after the other was
   // measured and changed nothing: 0.376 vs 0.372 ms on cfg3)
   constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
@@ -156,7 +133,6 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   for (int r = 0; r < 4; r++) {
     if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], go[r]);
     else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], go[r]);
-  }
   }
   if (later[0] || later[1] || later[2] || later[3]) {
 #pragma unroll
@@ -237,7 +213,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
     if (JIT_DENSE_FLAGS) touched[i] = 0;
     if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
-    if (JIT_DENSE_ACC != 0) denseSharedAcc()[i] = JIT_DENSE_ACC == 4 ? 0ull : P.accNeutral;
+    if (JIT_DENSE_ACC != 0) denseSharedAcc()[i] = P.accNeutral;
   }
 #else
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
@@ -286,9 +262,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #if JIT_DENSE
         uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
         bool fast[4], slow[4];
-        uint32_t mraw[4];
-        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, slow, dslot, dv, dvalid, meas, mraw))
-          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas, mraw);
+        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, slow, dslot, dv, dvalid, meas))
+          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas);
         (void)allowClaim; (void)bypass;
 #else
         uint64_t key[4][JIT_KW];
@@ -327,9 +302,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #if JIT_DENSE
         uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
         bool fast[4], slow[4];
-        uint32_t mraw[4];
-        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, slow, dslot, dv, dvalid, meas, mraw))
-          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas, mraw);
+        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, slow, dslot, dv, dvalid, meas))
+          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas);
 #else
         uint64_t key[4][JIT_KW];
         uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
@@ -347,10 +321,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #elif JIT_DENSE
   // fold the touched slots into the global table: the slot index decodes to the dimension values
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
-    unsigned long long accS = JIT_DENSE_ACC != 0 ? denseSharedAcc()[i] : P.accNeutral;
-    // integer form: only positive values were added, so 0 = no such row (adding the neutral element below is a no-op);
-    // 2^-S is a power of two and the integer is exact below 2^53
-    if (JIT_DENSE_ACC == 4) accS = accS == 0 ? P.accNeutral : (unsigned long long)__double_as_longlong(__ull2double_rn(accS) * P.fxInv);
+    const unsigned long long accS = JIT_DENSE_ACC != 0 ? denseSharedAcc()[i] : P.accNeutral;
     const unsigned long long accG = JIT_DENSE_ACC != 1 ? __ldcg(&tAcc[i]) : P.accNeutral;
     if (JIT_DENSE_FLAGS ? !touched[i] : (accS == P.accNeutral && accG == P.accNeutral)) continue;
     uint32_t rem = i % P.dRepStride, dvr[JIT_ND], vb = 0;   // (padding slots between copies are never reached)
