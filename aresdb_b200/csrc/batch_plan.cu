@@ -1089,7 +1089,8 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
         for (uint32_t n = kMaxStages; n >= 2 && !tileRows; n--) {
           const size_t need = 128 + n * stageBytesFor(tr);
           if (need >= (size_t)kSmemBudget) continue;
-          uint32_t cap = (uint32_t)(((size_t)kSmemBudget - need) / 9 / 16 * 16);
+          const size_t slotBytes = P.denseFx ? 12 : 9;   // three 32-bit piece counters, or flag + 8-byte accumulator
+          uint32_t cap = (uint32_t)(((size_t)kSmemBudget - need) / slotBytes / 16 * 16);
           if (cap > kDenseMaxSlots) cap = kDenseMaxSlots;
           if (cap >= P.denseTotal) { tileRows = tr; stages = n; slots = cap; }
         }
@@ -1157,7 +1158,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   if (P.denseNd == 0) P.denseGlobal = 0;
   P.stageBytes = (uint32_t)stageBytes;
   P.smemSlots = slots;
-  P.tableBytes = P.denseNd != 0 ? (slots * 9 + 127) / 128 * 128 : slots * 8;
+  P.tableBytes = P.denseNd != 0 ? (slots * (P.denseFx ? 12 : 9) + 127) / 128 * 128 : slots * 8;
   return 128 + (size_t)P.tableBytes + stageBytes * P.numStages;
 }
 

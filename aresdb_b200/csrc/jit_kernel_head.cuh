@@ -30,6 +30,9 @@ struct JitParams {
   uint32_t dLo[kJitMaxDenseDims], dCnt[kJitMaxDenseDims], dStride[kJitMaxDenseDims], dStep[kJitMaxDenseDims];
   uint32_t dTotal, dReps, dRepStride;     // slots of one copy; lane-private copies (power of two), dRepStride slots apart
   unsigned long long *gAcc;               // JIT_DENSE == 2: the state's global accumulator array (dTotal slots in use)
+  double fxInv;                           // JIT_DENSE_ACC == 4: 2^-S
+  float fxScale;                          //                     2^S (a float sum's rows are added as integers x * 2^S)
+  uint32_t fxPad;
 };
 
 // rows 4q .. 4q+3 of a staged value column of W bytes per value

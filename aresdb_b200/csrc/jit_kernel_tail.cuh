@@ -91,7 +91,8 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
 
 __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P,
                                                   const bool (&fast)[4], const bool (&slow)[4], const uint32_t (&dslot)[4],
-                                                  const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4]) {
+                                                  const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4],
+                                                  const uint32_t (&mraw)[4]) {
   if (JIT_DENSE == 2) {
     // One accumulator array for the whole grid (more slots than a CTA holds).  No flags: a slot was reached iff it
     // differs from the aggregate's neutral element, so a row whose value would leave it there (-0.0 for float sums,
@@ -126,6 +127,42 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], go[r]);
   }
   const uint32_t sAccAddr = touchedAddr + kDenseCap;
+  if (JIT_DENSE_ACC == 4) {
+    // Exact integer accumulation of a float sum (jitAnalyzeDense): a slot is three 32-bit counters for the 11 / 11 / 10
+    // bit pieces of x * 2^S, updated with fire-and-forget adds (nothing returns, nothing spins), and carries no flag —
+    // it was reached iff a counter is non-zero or its double half on the L2 slice left the neutral element.  Rows with
+    // x > 0 on the grid take that path.  The rest is rare and sits behind one branch: -0.0 (it would leave the double
+    // half at its neutral element) takes the hash path, everything else (zeros, NULL -> +0.0, negative, off the grid,
+    // beyond the announced maximum, NaN) is added in double.
+    const uint32_t fxAddr = touchedAddr;   // the table region holds only the counters in this mode
+    uint32_t ix[4];
+    bool onGrid[4];
+    bool rare = false;
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const float x = __uint_as_float(mraw[r]);
+      const float y = x * P.fxScale;
+      ix[r] = __float2uint_rz(y);
+      onGrid[r] = fast[r] && x > 0.0f && y < 4294967296.0f && __uint2float_rn(ix[r]) == y;
+      rare = rare || slow[r] || (fast[r] && !onGrid[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      if (onGrid[r]) {   // one branch around the three adds
+        const uint32_t a = fxAddr + 12u * s[r];
+        asm volatile("red.shared.add.u32 [%0], %1;\n\tred.shared.add.u32 [%0+4], %2;\n\tred.shared.add.u32 [%0+8], %3;"
+                     ::"r"(a), "r"(ix[r] & 0x7FFu), "r"((ix[r] >> 11) & 0x7FFu), "r"(ix[r] >> 22) : "memory");
+      }
+    }
+    if (rare) {
+#pragma unroll
+      for (int r = 0; r < 4; r++) {
+        if (slow[r] || (fast[r] && mraw[r] == 0x80000000u)) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
+        else if (fast[r] && !onGrid[r]) aggAtomic((AggOp)JIT_AGG_OP, tAcc + s[r], meas[r]);
+      }
+    }
+    return;
+  } else {
   // (issuing the compare-and-swap loops of the shared-memory rows interleaved instead of one after the other was
   // measured and changed nothing: 0.376 vs 0.372 ms on cfg3)
   constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
@@ -133,6 +170,7 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   for (int r = 0; r < 4; r++) {
     if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], go[r]);
     else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], go[r]);
+  }
   }
   if (later[0] || later[1] || later[2] || later[3]) {
 #pragma unroll
@@ -213,7 +251,12 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
     if (JIT_DENSE_FLAGS) touched[i] = 0;
     if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
-    if (JIT_DENSE_ACC != 0) denseSharedAcc()[i] = P.accNeutral;
+    if (JIT_DENSE_ACC == 4) {
+      uint32_t *c = reinterpret_cast<uint32_t *>(tKeys) + 3u * i;
+      c[0] = 0; c[1] = 0; c[2] = 0;
+    } else if (JIT_DENSE_ACC != 0) {
+      denseSharedAcc()[i] = P.accNeutral;
+    }
   }
 #else
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
@@ -262,8 +305,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #if JIT_DENSE
         uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
         bool fast[4], slow[4];
-        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, slow, dslot, dv, dvalid, meas))
-          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas);
+        uint32_t mraw[4];
+        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, slow, dslot, dv, dvalid, meas, mraw))
+          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas, mraw);
         (void)allowClaim; (void)bypass;
 #else
         uint64_t key[4][JIT_KW];
@@ -302,8 +346,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #if JIT_DENSE
         uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
         bool fast[4], slow[4];
-        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, slow, dslot, dv, dvalid, meas))
-          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas);
+        uint32_t mraw[4];
+        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, slow, dslot, dv, dvalid, meas, mraw))
+          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas, mraw);
 #else
         uint64_t key[4][JIT_KW];
         uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
@@ -321,7 +366,16 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
 #elif JIT_DENSE
   // fold the touched slots into the global table: the slot index decodes to the dimension values
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
-    const unsigned long long accS = JIT_DENSE_ACC != 0 ? denseSharedAcc()[i] : P.accNeutral;
+    unsigned long long accS = P.accNeutral;
+    if (JIT_DENSE_ACC == 4) {
+      // pieces -> integer -> double: only positive values were added, so 0 = no such row (adding the neutral element
+      // below is then a no-op); 2^-S is a power of two and the integer is exact below 2^53
+      const uint32_t *c = reinterpret_cast<const uint32_t *>(tKeys) + 3u * i;
+      const unsigned long long v = (unsigned long long)c[0] + ((unsigned long long)c[1] << 11) + ((unsigned long long)c[2] << 22);
+      if (v != 0) accS = (unsigned long long)__double_as_longlong(__ull2double_rn(v) * P.fxInv);
+    } else if (JIT_DENSE_ACC != 0) {
+      accS = denseSharedAcc()[i];
+    }
     const unsigned long long accG = JIT_DENSE_ACC != 1 ? __ldcg(&tAcc[i]) : P.accNeutral;
     if (JIT_DENSE_FLAGS ? !touched[i] : (accS == P.accNeutral && accG == P.accNeutral)) continue;
     uint32_t rem = i % P.dRepStride, dvr[JIT_ND], vb = 0;   // (padding slots between copies are never reached)

@@ -76,10 +76,14 @@ struct DevPlan {
   unsigned long long *denseAcc;
   uint8_t denseGlobal;
   uint8_t neutralSafe;     // no sequence of row values can bring a reached accumulator back to accNeutral (set by compilePlan)
-  uint8_t pad2[6];
+  uint8_t denseFx;         // float sum accumulated as exact integers (three 32-bit pieces per slot), see jitAnalyzeDense
+  int8_t fxMeasureInst;    // the measure instruction (a verbatim Float32 column with a zone map)
+  int8_t fxShift;          // S: a row adds x * 2^S
+  uint8_t pad2[3];
 };
 
 constexpr uint32_t kDenseMaxSlots = 8192;   // = slots of a CTA's accumulator slice in AggState::ctaAcc
+constexpr uint32_t kFxMaxRowsPerCta = 1u << 21;   // each 32-bit piece accumulator takes 2^21 adds of an 11-bit piece
 constexpr uint32_t kGlobalDenseMaxSlots = 1u << 21;   // 16 MB of accumulators per state, allocated on first use
 
 // jit.cu: runs the staged tiles of `P` with a kernel specialised for the plan's shape.  Returns false

@@ -60,10 +60,13 @@ def zone_map(hb: HostBatch) -> dict:
     dictionary size) and hands to the engine as BatchPlan.Ranges."""
     out = {}
     for i, (v, ok) in enumerate(zip(hb.values, hb.valid)):
-        if v.dtype.kind not in "ui":
-            continue
         sel = v[ok != 0]
-        if sel.size and int(sel.min()) >= 0 and int(sel.max()) < 2 ** 31:
+        if not sel.size:
+            continue
+        if v.dtype == np.float32:   # non-negative finite floats: the IEEE bit patterns (same order as the values)
+            if np.isfinite(sel).all() and not np.signbit(sel).any():
+                out[i] = (int(sel.min().view(np.uint32)), int(sel.max().view(np.uint32)))
+        elif v.dtype.kind in "ui" and int(sel.min()) >= 0 and int(sel.max()) < 2 ** 31:
             out[i] = (int(sel.min()), int(sel.max()))
     return out
 
@@ -72,7 +75,7 @@ def zone_map_of_day(day: int, num_cities: int = 100) -> dict:
     """Zone map of a generated day-batch by construction (generate_batch / generate_batch_cuda): what the
     archive store knows without looking at the data — batch ID = day, city ids 1..num_cities, 4 status values."""
     return {COL_REQUEST_AT: (BASE_TS + day * 86400, BASE_TS + day * 86400 + 86399), COL_CITY_ID: (1, num_cities),
-            COL_STATUS: (0, 3)}
+            COL_STATUS: (0, 3), COL_FARE: (0, int(np.float32(100.0).view(np.uint32)))}   # fares in [0, 100): float bits
 
 
 # ---- large-scale generation on the GPU (bench.py): same schema, torch RNG -------------------------

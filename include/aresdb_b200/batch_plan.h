@@ -69,7 +69,9 @@ typedef struct {
 
 /* Optional zone-map entry of one column of one batch: every VALID (non-NULL) value of the column in this
  * batch lies in [Min, Max] as a non-negative integer below 2^31 (Bool / Uint8 / Uint16 / Uint32 columns and
- * non-negative signed ones).  The reference keeps exactly this for the time column of live batches
+ * non-negative signed ones; for a Float32 column whose valid values are all >= 0: the IEEE bit patterns of the
+ * smallest and largest value, which order like the values — a float SUM then accumulates the rows that lie on
+ * the 2^-S grid the maximum allows as exact integers).  The reference keeps exactly this for the time column of live batches
  * (LiveVectorParty.GetMinMaxValue, memstore/common/vector_party.go:184-186, used for batch skipping in
  * query/aql_processor.go:1509) and knows it by construction for archive batches (batch ID = day) and for
  * enum columns (dictionary size).  It is a HINT: when every dimension of the query has a small known range

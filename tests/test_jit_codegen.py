@@ -145,6 +145,20 @@ def test_rle_batches_stage_their_base_counts():
 
 DAY_RANGES = {synth.COL_REQUEST_AT: (synth.BASE_TS, synth.BASE_TS + 86399), synth.COL_CITY_ID: (0, 100),
               synth.COL_STATUS: (0, 3)}
+FARE_RANGE = {synth.COL_FARE: (0, 0x42C80000)}   # [0.0, 100.0] as float bits
+
+
+def test_float_sum_accumulates_integers_when_the_measure_is_bounded():
+    """SUM(float column) in f64 with a zone map on the measure column: accumulator mode 4 (exact integers on the 2^-S
+    grid, native 32-bit atomics); without it, or for expressions / other aggregates, the split CAS / RED form."""
+    lib = A.load_engine()
+    q = T.queries()["cfg3_sum"]
+    both = {**DAY_RANGES, **FARE_RANGE}
+    assert "#define JIT_DENSE_ACC 4" in _dry_run(lib, q, ranges=both)[1]
+    assert "#define JIT_DENSE_ACC 2" in _dry_run(lib, q, ranges=DAY_RANGES)[1]
+    doubled = AggQuery(q.filters, [E.floor(T.TS, E.Lit(3600)), T.CITY], Measure("sum", E.mul(T.FARE, E.Lit(2.0))))
+    assert "#define JIT_DENSE_ACC 2" in _dry_run(lib, doubled, ranges=both)[1]
+    assert "#define JIT_DENSE_ACC 1" in _dry_run(lib, T.queries()["cfg3_count"], ranges=both)[1]
 
 
 def test_zone_map_selects_direct_indexed_aggregation():

@@ -206,6 +206,38 @@ def test_negative_zero_sums_oracle_vs_reference():
 
 
 @pytest.mark.gpu
+def test_zone_map_integer_accumulation_of_float_sums():
+    """SUM(float32 column) in f64 with a zone map on the measure column adds the rows that lie on the 2^-S grid as exact
+    integers (native 32-bit atomics + carry) and the others (tiny, negative, zero, -0.0, NULL, beyond the announced
+    maximum) in double.  Quantised fares: bit-identical to the reference.  Arbitrary floats: within 4 ULP of the
+    reference's sequential double sum (tolerance of test_fused_plan_float_tolerance), whatever the zone map says."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    rng = np.random.default_rng(3)
+    q = queries()["cfg2"]                      # filter on status only: NULL fares reach the measure (split CAS / RED form)
+    q3 = queries()["cfg3_sum"]                 # fare > 5.0 proves the measure non-NULL: integer form
+    qall = AggQuery([E.ge(FARE, E.Lit(-1.0e9))], [CITY, STATUS], Measure("sum", FARE))   # integer form, every odd value survives
+    exact = [synth.generate_batch(d, 30000, num_cities=30) for d in range(2)]
+    zm = [synth.zone_map(hb) for hb in exact]
+    assert all(synth.COL_FARE in z for z in zm)
+    for qq in (q, q3, qall):
+        assert_same_result(run_fused(eng, qq, exact, zone_maps=zm), run_legacy(orc, qq, exact), ctx="exact fares")
+    rough = [synth.generate_batch(d, 30000, num_cities=30, exact_fares=False) for d in range(2)]
+    for hb in rough:
+        f = hb.values[synth.COL_FARE]
+        n = f.size
+        f[rng.random(n) < 0.05] *= np.float32(1e-6)          # far below the grid
+        f[rng.random(n) < 0.05] *= np.float32(-1.0)          # negative: outside the announced range
+        f[rng.random(n) < 0.02] = np.float32(-0.0)
+        f[rng.random(n) < 0.02] = np.float32(1e7)            # beyond the announced maximum
+    announced = [dict(z, **{}) for z in zm]                   # the zone map of the OTHER data set: max ~100, all >= 0
+    for qq in (q, q3, qall):
+        got, exp = run_fused(eng, qq, rough, zone_maps=announced), run_legacy(orc, qq, rough)
+        assert got.rows == exp.rows
+        ulp = np.spacing(np.abs(exp.measures))
+        assert np.all(np.abs(got.measures - exp.measures) <= 4 * ulp)
+
+
+@pytest.mark.gpu
 def test_zone_map_wide_rows_and_small_batches():
     """Dimension rows wider than 8 bytes are keyed by the reference hash of the packed row: the slots' flush
     (CTA form) and denseFoldKernel (global form) must rebuild exactly those bytes.  Batches too small to be staged
