@@ -80,7 +80,8 @@ WORKLOADS = {
     "cfg3": dict(desc="cfg3: 1e9-row fact table as 8 day-batches; filters status==1, fare>5.0, city_id!=0, "
                       "request_at in [t0+1800, t0+8d-1800); dims floor(request_at,3600) x city_id; SUM(fare) in f64",
                  query=_q_cfg3, bytes_per_row=4 + 2 + 1 + 4 + 4 / 8.0, rows=1_000_000_000, batches=8, expected_groups=0,
-                 dtype="u32/u16/u8 filters, f32->f64 sum", metric="rows/s, 1e9-row time-bucketed SUM group-by (cfg3)"),
+                 dtype="u32/u16/u8 filters; f32 fares summed into f64 (exactly, as integers on the 2^-S grid the zone map allows)",
+                 metric="rows/s, 1e9-row time-bucketed SUM group-by (cfg3)"),
     "cfg3_count": dict(desc="cfg3 count(*) variant: filters status==1, fare>5.0, city_id!=0; dims floor(request_at,3600) x "
                             "city_id; COUNT in u32", query=_q_cfg3_count, bytes_per_row=4 + 2 + 1 + 4 + 4 / 8.0,
                        rows=1_000_000_000, batches=8, expected_groups=0, dtype="u32 count",
