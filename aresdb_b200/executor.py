@@ -21,6 +21,7 @@ from . import cabi as A
 from . import expr as E
 from .memory import Buf
 from .query import AggQuery, HLLResult, QueryResult
+from .skipping import should_skip_batch
 
 
 @dataclass
@@ -264,8 +265,12 @@ class FusedBatchExecutor:
         for i, pi in enumerate(self.insts):
             self._plan.Insts[i] = pi
         self.calls = 0
+        self.skipped = 0   # batches whose zone map contradicts a filter (skipping.py): never launched
 
     def process_batch(self, batch: Batch, stream=None):
+        if should_skip_batch(self.q, batch.ranges):
+            self.skipped += 1
+            return
         p = self._plan
         p.NumColumns = len(batch.columns)
         for i, vp in enumerate(batch.columns):
