@@ -1,0 +1,136 @@
+"""Archive batches on the host: sorted, run-length encoded columns and the prefilter slicing the reference applies
+before a batch is copied to the device.
+
+An archive batch is sorted by its table's archiving sort columns; a sort column is stored as one value per run plus a
+cumulative count vector (mode 3), runs of a later sort column nest inside runs of the earlier ones, the remaining
+columns hold one value per row.  A query whose filters pin the leading sort columns (equality prefilters, then at most
+one range prefilter — query/aql_compiler.go matchPrefilters) does not scan the batch: it binary-searches the matching
+row range sort column by sort column and ships only those rows (qc.prefilterSlice, query/aql_processor.go:925-982;
+cVectorParty.SliceByValue / SliceIndex, memstore/vector_party.go:371-432).  The sliced batch keeps ABSOLUTE row numbers
+in its count vectors; index space = the finest requested column (transferArchiveBatch, query/aql_processor.go:568-626).
+
+This module mirrors that logic on numpy arrays and hands the result to the executors as an ordinary `Batch`
+(RLE columns are expanded once per batch on the device and then take the fused fast path).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import columns
+from .executor import Batch
+
+NO_BOUNDARY, INCLUSIVE, EXCLUSIVE = 0, 1, 2   # boundaryType of a range prefilter (query/aql_context.go)
+
+
+@dataclass
+class ArchiveColumn:
+    data_type: int
+    values: np.ndarray                 # one per run (compressed) or one per row
+    valid: np.ndarray | None = None    # same length as values, or None (all valid)
+    counts: np.ndarray | None = None   # cumulative row counts, len(values) + 1, counts[0] = first row; None: uncompressed
+
+    @property
+    def compressed(self) -> bool:
+        return self.counts is not None
+
+
+def compress(data_type: int, rows: np.ndarray, valid: np.ndarray | None = None) -> ArchiveColumn:
+    """Run-length encodes a per-row vector (what archiving does for a sort column)."""
+    rows = np.asarray(rows)
+    ok = np.ones(len(rows), np.uint8) if valid is None else np.asarray(valid, np.uint8)
+    change = np.ones(len(rows), bool)
+    change[1:] = (rows[1:] != rows[:-1]) | (ok[1:] != ok[:-1])
+    starts = np.flatnonzero(change)
+    counts = np.concatenate([starts, [len(rows)]]).astype(np.uint32)
+    return ArchiveColumn(data_type, rows[starts].copy(), None if valid is None else ok[starts].copy(), counts)
+
+
+def slice_index(col: ArchiveColumn, lo_row: int, hi_row: int) -> tuple[int, int]:
+    """cVectorParty.SliceIndex: the runs that overlap rows [lo_row, hi_row)."""
+    if not col.compressed:
+        return lo_row, hi_row
+    start = int(np.searchsorted(col.counts, lo_row, side="right")) - 1            # UpperBound(lo) - 1
+    end = start + int(np.searchsorted(col.counts[start:], hi_row, side="left"))    # LowerBound(hi) from start
+    if end == len(col.counts):
+        end -= 1
+    return start, end
+
+
+def slice_by_value(col: ArchiveColumn, lo_row: int, hi_row: int, value) -> tuple[int, int, int, int]:
+    """cVectorParty.SliceByValue: (startRow, endRow, startIndex, endIndex) of the rows in [lo_row, hi_row) whose value
+    equals `value` (the column is sorted within that row range); an absent value yields the empty range at its
+    insertion point, which is what the range prefilter relies on."""
+    if col.compressed:
+        si, ei = slice_index(col, lo_row, hi_row)
+        vals = col.values[si:ei]
+        s = si + int(np.searchsorted(vals, value, side="left"))
+        e = si + int(np.searchsorted(vals, value, side="right"))
+        return int(col.counts[s]), int(col.counts[e]), s, e
+    vals = col.values[lo_row:hi_row]
+    s = lo_row + int(np.searchsorted(vals, value, side="left"))
+    e = lo_row + int(np.searchsorted(vals, value, side="right"))
+    return s, e, s, e
+
+
+@dataclass
+class SlicedBatch:
+    start_row: int
+    end_row: int
+    index_ranges: dict          # column -> (startIndex, endIndex)
+    first_column: int           # finest requested column: its runs (or rows) are the batch's index space
+
+
+def prefilter_slice(cols: dict, scan_order: list, num_rows: int, equality_values=(), range_prefilter=None) -> SlicedBatch:
+    """qc.prefilterSlice over the requested columns.  `scan_order`: column ids, sort columns first in sort order, then the
+    rest; equality_values[k] pins scan_order[k]; range_prefilter = (lower, lower_boundary, upper, upper_boundary) applies
+    to the next sort column."""
+    start, end = 0, num_rows
+    ranges = {}
+    for k, c in enumerate(scan_order):
+        col = cols[c]
+        unmatched = False
+        if k < len(equality_values):
+            start, end, si, ei = slice_by_value(col, start, end, equality_values[k])
+        elif k == len(equality_values) and range_prefilter is not None:
+            lower, lower_b, upper, upper_b = range_prefilter
+            si, ei = slice_index(col, start, end)
+            if lower_b != NO_BOUNDARY:
+                ls, le, lsi, lei = slice_by_value(col, start, end, lower)
+                start, si = (ls, lsi) if lower_b == INCLUSIVE else (le, lei)
+            else:
+                unmatched = True
+            if upper_b != NO_BOUNDARY:
+                us, ue, usi, uei = slice_by_value(col, start, end, upper)
+                end, ei = (ue, uei) if upper_b == INCLUSIVE else (us, usi)
+            else:
+                unmatched = True
+        else:
+            unmatched = True
+        if unmatched:
+            si, ei = slice_index(col, start, end)
+        ranges[c] = (si, ei)
+    return SlicedBatch(start, end, ranges, scan_order[-1])
+
+
+def to_batch(space, cols: dict, num_columns: int, sl: SlicedBatch) -> Batch:
+    """Uploads the sliced vectors (count vectors keep absolute row numbers) and describes them as one Batch."""
+    slices, keep = [None] * num_columns, []
+    for c, (si, ei) in sl.index_ranges.items():
+        col = cols[c]
+        valid = None if col.valid is None else col.valid[si:ei]
+        counts = col.counts[si:ei + 1] if col.compressed else None
+        buf, vp = columns.make_column(space, col.data_type, col.values[si:ei], valid=valid, counts=counts)
+        slices[c] = vp
+        keep.append(buf)
+    for c in range(num_columns):
+        if slices[c] is None:                       # a column the query does not read: empty constant slice
+            slices[c] = columns.constant_column(cols[c].data_type if c in cols else 0, 0, False)
+    first = cols[sl.first_column]
+    si, ei = sl.index_ranges[sl.first_column]
+    if first.compressed:
+        bc = space.put(np.ascontiguousarray(first.counts[si:ei + 1], np.uint32))
+        keep.append(bc)
+        return Batch(slices, ei - si, base_counts=bc, start_count=0, keep=keep)
+    return Batch(slices, sl.end_row - sl.start_row, base_counts=None, start_count=sl.start_row, keep=keep)

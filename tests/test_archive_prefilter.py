@@ -1,0 +1,132 @@
+"""Prefilter slicing of sorted archive batches (aresdb_b200/archive.py; reference qc.prefilterSlice,
+query/aql_processor.go:925-982, cVectorParty.SliceByValue / SliceIndex, memstore/vector_party.go:371-432).
+
+Property: running a query WITHOUT its prefilters on the sliced batch gives what the query WITH the prefilters as
+ordinary filters gives on the whole batch — checked through the reference's per-node call sequence on the C
+restatement and on the reference's own HOST build."""
+import numpy as np
+import pytest
+
+import harness as H
+import test_pipeline_parity as T
+from aresdb_b200 import archive as AR
+from aresdb_b200 import cabi as A
+from aresdb_b200 import expr as E, synth
+from aresdb_b200.executor import LegacyBatchExecutor
+from aresdb_b200.query import AggQuery, Measure
+
+TS, CITY, STATUS, FARE = T.TS, T.CITY, T.STATUS, T.FARE
+SCAN = [synth.COL_CITY_ID, synth.COL_STATUS, synth.COL_REQUEST_AT, synth.COL_FARE]   # sort columns first, in sort order
+N = 12000
+
+
+@pytest.fixture(scope="module")
+def archive():
+    rng = np.random.default_rng(1)
+    city = rng.integers(1, 12, N).astype(np.uint16)
+    status = rng.integers(0, 4, N).astype(np.uint8)
+    order = np.lexsort((status, city))                       # sorted by (city, status), as archiving does
+    city, status = city[order], status[order]
+    ts = (synth.BASE_TS + rng.integers(0, 86400, N)).astype(np.uint32)
+    fare = (rng.integers(0, 6400, N) / 64).astype(np.float32)
+    return {synth.COL_CITY_ID: AR.compress(A.Uint16, city), synth.COL_STATUS: AR.compress(A.Uint8, status),
+            synth.COL_REQUEST_AT: AR.ArchiveColumn(A.Uint32, ts, (rng.random(N) > 0.02).astype(np.uint8)),
+            synth.COL_FARE: AR.ArchiveColumn(A.Float32, fare, (rng.random(N) > 0.02).astype(np.uint8))}
+
+
+def run(be, q, cols, sl, scan=SCAN):
+    ex = LegacyBatchExecutor(be.lib, be.space, q)
+    ex.process_batch(AR.to_batch(be.space, {c: cols[c] for c in scan}, 4, sl))
+    return ex.result()
+
+
+def test_slice_by_value_and_index_match_a_linear_scan(archive):
+    city = archive[synth.COL_CITY_ID]
+    rows = np.repeat(city.values, np.diff(city.counts))
+    for v in (0, 1, 5, 11, 12):
+        s, e, si, ei = AR.slice_by_value(city, 0, N, v)
+        hit = np.flatnonzero(rows == v)
+        assert (s, e) == ((int(hit[0]), int(hit[-1]) + 1) if hit.size else (s, s))
+        assert city.counts[si] == s and city.counts[ei] == e
+    status = archive[synth.COL_STATUS]
+    s, e, _, _ = AR.slice_by_value(city, 0, N, 5)
+    si, ei = AR.slice_index(status, s, e)
+    assert status.counts[si] == s and status.counts[ei] == e          # runs of the finer column nest in the coarser run
+    ts = archive[synth.COL_REQUEST_AT]
+    assert AR.slice_index(ts, s, e) == (s, e)
+
+
+@pytest.mark.parametrize("backend_name", ["oracle", "ref"])
+@pytest.mark.parametrize("eq, rng_pre, filters", [
+    ([7], None, lambda: [E.eq(CITY, E.Lit(7))]),
+    ([7], (1, AR.INCLUSIVE, 3, AR.EXCLUSIVE), lambda: [E.eq(CITY, E.Lit(7)), E.ge(STATUS, E.Lit(1)), E.lt(STATUS, E.Lit(3))]),
+    ([3, 2], None, lambda: [E.eq(CITY, E.Lit(3)), E.eq(STATUS, E.Lit(2))]),
+    ([], (4, AR.EXCLUSIVE, 9, AR.INCLUSIVE), lambda: [E.gt(CITY, E.Lit(4)), E.le(CITY, E.Lit(9))]),
+    ([], (6, AR.INCLUSIVE, 0, AR.NO_BOUNDARY), lambda: [E.ge(CITY, E.Lit(6))]),
+    ([], None, lambda: []),
+])
+def test_sliced_batch_equals_filtered_batch(archive, backend_name, eq, rng_pre, filters):
+    be = H.get_backend(backend_name)
+    dims = [E.floor(TS, E.Lit(3600)), STATUS]
+    for measure in (Measure("sum", FARE), Measure("count")):
+        whole = AR.prefilter_slice(archive, SCAN, N)
+        exp = run(be, AggQuery(filters(), dims, measure), archive, whole)
+        sl = AR.prefilter_slice(archive, SCAN, N, equality_values=eq, range_prefilter=rng_pre)
+        assert 0 <= sl.start_row <= sl.end_row <= N
+        got = run(be, AggQuery([], dims, measure), archive, sl)
+        assert exp.groups > 0
+        T.assert_same_result(got, exp, ctx=f"prefilter {eq} {rng_pre} {measure.kind}")
+
+
+def test_absent_values_give_an_empty_slice(archive):
+    sl = AR.prefilter_slice(archive, SCAN, N, equality_values=[99])
+    assert sl.start_row == sl.end_row
+    sl = AR.prefilter_slice(archive, SCAN, N, equality_values=[7], range_prefilter=(9, AR.INCLUSIVE, 20, AR.INCLUSIVE))
+    assert sl.start_row == sl.end_row
+
+
+def test_only_sort_columns_requested_index_space_is_runs(archive):
+    """When the finest requested column is itself run-length encoded its runs are the index space (base counts): a
+    count(*) then multiplies by the run lengths (query/iterator.hpp:626-645)."""
+    orc = H.get_backend("oracle")
+    scan = [synth.COL_CITY_ID, synth.COL_STATUS]
+    q = AggQuery([], [STATUS], Measure("count"))
+    sl = AR.prefilter_slice(archive, scan, N, equality_values=[5])
+    got = run(orc, q, archive, sl, scan)
+    city = np.repeat(archive[synth.COL_CITY_ID].values, np.diff(archive[synth.COL_CITY_ID].counts))
+    status = np.repeat(archive[synth.COL_STATUS].values, np.diff(archive[synth.COL_STATUS].counts))
+    want = {int(s): int(((city == 5) & (status == s)).sum()) for s in np.unique(status[city == 5])}
+    have = {int(d): int(m) for d, m in zip(got.decoded_dims()[0], got.measures)}
+    assert have == want and sl.first_column == synth.COL_STATUS
+
+
+@pytest.mark.gpu
+def test_fused_path_on_sliced_archive_batches():
+    """The sliced batch (absolute row numbers in the count vectors, start row for uncompressed columns) through
+    ExecuteBatchPlan: RLE columns are expanded once, then the staged fast path runs — same bits as the reference
+    sequence on the whole batch with the prefilters as ordinary filters."""
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    from aresdb_b200.executor import FusedBatchExecutor
+    rng = np.random.default_rng(2)
+    n = 150000
+    city = rng.integers(1, 12, n).astype(np.uint16)
+    status = rng.integers(0, 4, n).astype(np.uint8)
+    order = np.lexsort((status, city))
+    city, status = city[order], status[order]
+    ts = (synth.BASE_TS + rng.integers(0, 86400, n)).astype(np.uint32)
+    fare = (rng.integers(0, 6400, n) / 64).astype(np.float32)
+    cols = {synth.COL_CITY_ID: AR.compress(A.Uint16, city), synth.COL_STATUS: AR.compress(A.Uint8, status),
+            synth.COL_REQUEST_AT: AR.ArchiveColumn(A.Uint32, ts, (rng.random(n) > 0.02).astype(np.uint8)),
+            synth.COL_FARE: AR.ArchiveColumn(A.Float32, fare, (rng.random(n) > 0.02).astype(np.uint8))}
+    dims = [E.floor(TS, E.Lit(3600)), STATUS]
+    for eq, rng_pre, filters in (([7], None, [E.eq(CITY, E.Lit(7))]),
+                                 ([4], (1, AR.INCLUSIVE, 3, AR.EXCLUSIVE), [E.eq(CITY, E.Lit(4)), E.ge(STATUS, E.Lit(1)), E.lt(STATUS, E.Lit(3))])):
+        for measure in (Measure("sum", FARE), Measure("count")):
+            exp = run(orc, AggQuery(filters, dims, measure), cols, AR.prefilter_slice(cols, SCAN, n))
+            sl = AR.prefilter_slice(cols, SCAN, n, equality_values=eq, range_prefilter=rng_pre)
+            ex = FusedBatchExecutor(eng.lib, eng.space, AggQuery([], dims, measure))
+            b = AR.to_batch(eng.space, cols, 4, sl)
+            ex.process_batch(b)
+            got = ex.result()
+            ex.close()
+            T.assert_same_result(got, exp, ctx=f"fused sliced {eq} {rng_pre} {measure.kind}")
