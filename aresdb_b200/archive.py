@@ -134,3 +134,65 @@ def to_batch(space, cols: dict, num_columns: int, sl: SlicedBatch) -> Batch:
         keep.append(bc)
         return Batch(slices, ei - si, base_counts=bc, start_count=0, keep=keep)
     return Batch(slices, sl.end_row - sl.start_row, base_counts=None, start_count=sl.start_row, keep=keep)
+
+
+# ---- the compiler half: which of a query's filters are prefilters (reference AQLQueryContext.matchPrefilters /
+# extractFilter, query/aql_compiler.go:618-765) -----------------------------------------------------------------------
+@dataclass
+class Prefilters:
+    equality_values: list            # one per leading sort column pinned by `column = value`
+    range_prefilter: tuple | None    # (lower, lower_boundary, upper, upper_boundary) on the next sort column, or None
+    prefilter_ids: list              # indexes into the query's filter list (sorted): these are implied by the slice
+    columns: list                    # the sort columns they cover, in sort order
+
+
+def match_prefilters(filters: list, sort_columns: list) -> Prefilters:
+    """Walks the table's archiving sort columns in order: a `column = literal` filter pins the column and matching goes on
+    with the next one; otherwise `column > / >= literal` and `column < / <= literal` filters give the (single) range
+    prefilter and matching stops; a sort column without a candidate filter stops it too.  Only filters of the form
+    `column OP number` with the column on the left qualify, as in the reference; when several filters of one kind
+    name the same column the last one wins (the reference's map assignment)."""
+    from . import cabi as A
+    from . import expr as E
+    cand: dict = {}
+    for fid, f in enumerate(filters):
+        if not isinstance(f, E.Binary) or f.op not in (A.Equal, A.LessThan, A.LessThanOrEqual, A.GreaterThan, A.GreaterThanOrEqual):
+            continue
+        if not isinstance(f.lhs, E.Col):
+            continue
+        slot = cand.setdefault(f.lhs.index, [-1, -1, -1])       # lower bound, upper bound, equality
+        slot[0 if f.op in (A.GreaterThan, A.GreaterThanOrEqual) else 1 if f.op in (A.LessThan, A.LessThanOrEqual) else 2] = fid
+
+    def extract(fid):
+        f = filters[fid]
+        if not isinstance(f.rhs, E.Lit):
+            return None
+        boundary = INCLUSIVE if f.op in (A.GreaterThanOrEqual, A.LessThanOrEqual) else EXCLUSIVE
+        return f.rhs.value, boundary
+
+    out = Prefilters([], None, [], [])
+    for c in sort_columns:
+        if c not in cand:
+            break                                               # stop on the first sort column without a filter
+        lo, hi, eq = cand[c]
+        if eq >= 0:
+            v = extract(eq)
+            if v is None:
+                break
+            out.equality_values.append(v[0])
+            out.prefilter_ids.append(eq)
+            out.columns.append(c)
+            continue
+        lower = upper = None
+        if lo >= 0:
+            lower = extract(lo)
+        if hi >= 0:
+            upper = extract(hi)
+        if lower is not None or upper is not None:
+            out.range_prefilter = (lower[0] if lower else 0, lower[1] if lower else NO_BOUNDARY,
+                                   upper[0] if upper else 0, upper[1] if upper else NO_BOUNDARY)
+            out.prefilter_ids += [i for i, x in ((lo, lower), (hi, upper)) if x is not None]
+            out.columns.append(c)
+        break                                                   # stop after the first range filter
+    out.prefilter_ids.sort()
+    return out

@@ -130,3 +130,41 @@ def test_fused_path_on_sliced_archive_batches():
             got = ex.result()
             ex.close()
             T.assert_same_result(got, exp, ctx=f"fused sliced {eq} {rng_pre} {measure.kind}")
+
+
+def test_match_prefilters_follows_the_sort_column_order():
+    """AQLQueryContext.matchPrefilters (query/aql_compiler.go:658-765): equality filters pin leading sort columns, the
+    first column with only range filters ends the match, a sort column without a filter ends it too."""
+    sort_cols = [synth.COL_CITY_ID, synth.COL_STATUS]
+    f = [E.gt(FARE, E.Lit(5.0)), E.eq(CITY, E.Lit(7)), E.lt(STATUS, E.Lit(3)), E.ge(STATUS, E.Lit(1)), E.ge(TS, E.Lit(100))]
+    pf = AR.match_prefilters(f, sort_cols)
+    assert pf.equality_values == [7] and pf.range_prefilter == (1, AR.INCLUSIVE, 3, AR.EXCLUSIVE)
+    assert pf.prefilter_ids == [1, 2, 3] and pf.columns == sort_cols
+    pf = AR.match_prefilters([E.eq(STATUS, E.Lit(2))], sort_cols)                  # leading sort column has no filter
+    assert pf.equality_values == [] and pf.range_prefilter is None and pf.prefilter_ids == []
+    pf = AR.match_prefilters([E.gt(CITY, E.Lit(4)), E.eq(STATUS, E.Lit(2))], sort_cols)   # a range filter ends the match
+    assert pf.equality_values == [] and pf.range_prefilter == (4, AR.EXCLUSIVE, 0, AR.NO_BOUNDARY) and pf.prefilter_ids == [0]
+    pf = AR.match_prefilters([E.eq(CITY, E.Lit(3)), E.eq(STATUS, E.Lit(2))], sort_cols)
+    assert pf.equality_values == [3, 2] and pf.range_prefilter is None
+    pf = AR.match_prefilters([E.eq(E.Lit(3), CITY)], sort_cols)                    # literal on the left: not matched
+    assert pf.prefilter_ids == []
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_random_queries_match_slice_run(archive, seed):
+    """End to end on the C restatement: match_prefilters -> prefilter_slice -> the query minus its prefilters on the
+    slice == the whole query on the whole batch."""
+    orc = H.get_backend("oracle")
+    rng = np.random.default_rng(100 + seed)
+    pool = [E.eq(CITY, E.Lit(int(rng.integers(1, 12)))), E.ge(CITY, E.Lit(int(rng.integers(1, 6)))), E.lt(CITY, E.Lit(int(rng.integers(6, 13)))),
+            E.eq(STATUS, E.Lit(int(rng.integers(0, 4)))), E.gt(STATUS, E.Lit(0)), E.le(STATUS, E.Lit(2)), E.gt(FARE, E.Lit(20.0))]
+    filters = [pool[i] for i in sorted(rng.choice(len(pool), size=int(rng.integers(1, 5)), replace=False))]
+    if any(f.op == A.Equal and f.lhs is CITY for f in filters):
+        filters = [f for f in filters if f.lhs is not CITY or f.op == A.Equal]     # one kind of filter per column
+    dims = [STATUS, E.floor(TS, E.Lit(7200))]
+    exp = run(orc, AggQuery(filters, dims, Measure("count")), archive, AR.prefilter_slice(archive, SCAN, N))
+    pf = AR.match_prefilters(filters, [synth.COL_CITY_ID, synth.COL_STATUS])
+    rest = [f for i, f in enumerate(filters) if i not in pf.prefilter_ids]
+    sl = AR.prefilter_slice(archive, SCAN, N, pf.equality_values, pf.range_prefilter)
+    got = run(orc, AggQuery(rest, dims, Measure("count")), archive, sl)
+    T.assert_same_result(got, exp, ctx=f"seed {seed}: {len(pf.prefilter_ids)} prefilters of {len(filters)} filters")
