@@ -1,6 +1,7 @@
 """AQL front-end subset: a JSON AQL query (the form of the reference's examples/1k_trips/queries/*.aql)
 -> `AggQuery`, i.e. the part of the reference's query compiler that produces what the hot path consumes
-(SURVEY.md §8 f1).  Mirrors, for UTC and a single fact table:
+(SURVEY.md §8 f1).  Mirrors, for a single fact table and a time zone whose offset does not change inside the
+query's time range (UTC, numeric offsets like "-8" / "05:30", or an IANA name without a daylight-saving switch in range):
 
 * time filters            query/common/time_filter.go:100-420 (calendar-aligned relative / absolute
                           expressions -> `col >= from AND col < to`)
@@ -11,7 +12,11 @@
 * row / common filters    SQL-ish boolean expressions over columns and literals, enum literals translated
                           through the column's dictionary (query/aql_compiler.go:540-600)
 
-Not covered (they raise): joins, non-UTC timezones, geo, array functions, non-aggregate queries.
+* time zones              query/common/time_filter.go:69-85 (ParseTimezone), query/time_bucketizer.go:72-146 (the time
+                          column is shifted with CONVERT_TZ = Plus before it is bucketized), utils/time.go:110-116
+
+Not covered (they raise): joins, time-zone columns / daylight-saving switches inside the range, geo, array functions,
+non-aggregate queries.
 """
 from __future__ import annotations
 
@@ -67,8 +72,24 @@ class Table:
 
 
 # ---- time filter -----------------------------------------------------------------------------------
-def _utc(*a) -> _dt.datetime:
-    return _dt.datetime(*a, tzinfo=_dt.timezone.utc)
+def parse_timezone(text: str | None) -> _dt.tzinfo:
+    """ParseTimezone (query/common/time_filter.go:69-85): "hours[:minutes]" is a fixed zone, anything else an IANA name."""
+    if not text or text == "UTC":
+        return _dt.timezone.utc
+    seg = text.split(":")
+    try:
+        hours = int(seg[0])
+        minutes = int(seg[1]) if len(seg) > 1 else 0
+        if hours < 0 or seg[0].startswith("-"):
+            minutes = -minutes
+        return _dt.timezone(_dt.timedelta(seconds=hours * 3600 + minutes * 60))
+    except ValueError:
+        pass
+    try:
+        import zoneinfo
+        return zoneinfo.ZoneInfo(text)
+    except Exception as e:  # unknown name / no tz database
+        raise AQLError(f"timezone Failed to parse: {text}") from e
 
 
 def _add_months(t: _dt.datetime, months: int) -> _dt.datetime:
@@ -77,7 +98,9 @@ def _add_months(t: _dt.datetime, months: int) -> _dt.datetime:
 
 
 def _apply_offset(base: _dt.datetime, amount: int, unit: str):
-    """start / end of the calendar unit `amount` units away from the one containing `base`."""
+    """start / end of the calendar unit `amount` units away from the one containing `base` (in base's time zone)."""
+    def _utc(*a):   # wall-clock constructor of the query's zone (UTC unless the query names another one)
+        return _dt.datetime(*a, tzinfo=base.tzinfo)
     day = _utc(base.year, base.month, base.day)
     month = _utc(base.year, base.month, 1)
     if unit == "y":
@@ -106,7 +129,7 @@ def _apply_offset(base: _dt.datetime, amount: int, unit: str):
     raise AQLError(f"Unknown time filter unit: {unit}")
 
 
-def _absolute(date_expr: str, time_expr: str):
+def _absolute(date_expr: str, time_expr: str, tz: _dt.tzinfo = _dt.timezone.utc):
     seg = date_expr.split("-")
     if len(seg) > 3:
         raise AQLError(f"Unknown time expression: {date_expr} {time_expr}")
@@ -130,7 +153,7 @@ def _absolute(date_expr: str, time_expr: str):
         if len(ts) == 2:
             minute = int(ts[1])
             unit = "15m" if minute % 15 == 0 else "m"
-    start, end = _apply_offset(_utc(year, month, day, hour, minute), 0, unit)
+    start, end = _apply_offset(_dt.datetime(year, month, day, hour, minute, tzinfo=tz), 0, unit)
     return start, end, unit
 
 
@@ -159,16 +182,17 @@ def _time_expression(expression: str, now: _dt.datetime):
             if seconds > 99999999999:      # milliseconds
                 seconds //= 1000
             if seconds > 9999999:
-                t = _dt.datetime.fromtimestamp(seconds, _dt.timezone.utc)
+                t = _dt.datetime.fromtimestamp(seconds, now.tzinfo)
                 return t, t, "m" if seconds % 60 == 0 else "s"
     if len(seg) > 2:
         raise AQLError(f"Unknown time filter expression: {expression}")
-    return _absolute(seg[0], seg[1] if len(seg) == 2 else "")
+    return _absolute(seg[0], seg[1] if len(seg) == 2 else "", now.tzinfo)
 
 
-def parse_time_filter(time_filter: dict, now: int):
-    """-> (from_ts | None, to_ts | None) in epoch seconds; `to` defaults to now when only `from` is given."""
-    now_t = _dt.datetime.fromtimestamp(int(now), _dt.timezone.utc)
+def parse_time_filter(time_filter: dict, now: int, tz: _dt.tzinfo = _dt.timezone.utc):
+    """-> (from_ts | None, to_ts | None) in epoch seconds; `to` defaults to now when only `from` is given.  Calendar
+    units are those of `tz` (ParseTimeFilter's location argument)."""
+    now_t = _dt.datetime.fromtimestamp(int(now), tz)
     frm = to = None
     if time_filter.get("from"):
         frm = int(_time_expression(time_filter["from"], now_t)[0].timestamp())
@@ -371,8 +395,9 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
         raise AQLError(f"unknown table {query.get('table')}")
     if query.get("joins"):
         raise AQLError("joins are outside this engine")
-    if query.get("timezone", "UTC") not in ("UTC", ""):
-        raise AQLError("only UTC is supported")
+    if "(" in str(query.get("timezone", "")):
+        raise AQLError("time-zone columns (joins with the timezone table) are outside this engine")
+    tz = parse_timezone(query.get("timezone"))
     measures = query.get("measures") or []
     if len(measures) != 1:
         raise AQLError("expect one measure per query")   # aql_compiler.go:1140-1146
@@ -396,19 +421,32 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
     time_col = None
     if tf.get("column"):
         time_col = table.ref(tf["column"])
-        frm, to = parse_time_filter(tf, now)
+        frm, to = parse_time_filter(tf, now, tz)
         if frm is not None:
             filters.append(E.Binary(A.GreaterThanOrEqual, time_col, E.Lit(frm, E.Type.Unsigned)))
         if to is not None:
             filters.append(E.Binary(A.LessThan, time_col, E.Lit(to, E.Type.Unsigned)))
 
+    # fixed offset of the query's zone over [from, to): buildTimeDimensionExpr (query/time_bucketizer.go:72-146) shifts
+    # the time column by it (CONVERT_TZ is Plus, query/time_series_aggregate.go:87) before bucketizing
+    tz_offset = 0
+    if tz is not _dt.timezone.utc:
+        probe = [t for t in ((frm, to) if tf.get("column") else ()) if t is not None] or [int(now)]
+        offsets = {int(_dt.datetime.fromtimestamp(t, tz).utcoffset().total_seconds()) for t in probe}
+        if len(offsets) != 1:
+            raise AQLError("a daylight-saving switch inside the time range is outside this front-end")
+        tz_offset = offsets.pop()
     dims = []
     for d in query.get("dimensions") or []:
         e = parse_expression(d.get("sqlExpression") or d.get("expr"), table)
         if d.get("timeBucketizer"):
+            if tz_offset:
+                e = E.Binary(A.Plus, e, E.Lit(tz_offset, E.Type.Signed if tz_offset < 0 else E.Type.Unsigned))
             e = time_dimension_expr(d["timeBucketizer"], e)
         dims.append(e)
-    return AggQuery(filters, dims, measure, reduce_mode)
+    q = AggQuery(filters, dims, measure, reduce_mode)
+    q.tz_offset = tz_offset     # result formatting: DimensionMeta.from_offset (utils.AdjustOffset, utils/time.go:110-116)
+    return q
 
 
 def time_bucket_start(ts: int, bucketizer: str) -> int:

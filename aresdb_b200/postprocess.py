@@ -25,6 +25,7 @@ class DimensionMeta:
     enum_names: list | None = None
     time_bucketizer: str | None = None     # set for time dimensions
     time_unit: str = ""                    # "", "second", "minute", "hour", "day", "millisecond"
+    from_offset: int = 0                   # seconds the query's time zone is ahead of UTC (AggQuery.tz_offset)
 
 
 def format_float32(x) -> str:
@@ -51,6 +52,7 @@ def _utc(ts: int) -> _dt.datetime:
 
 def format_time_dimension(val: int, meta: DimensionMeta) -> str:
     if meta.time_unit:
+        val -= meta.from_offset             # numeric output is an instant again (utils.AdjustOffset, utils/time.go:110-116)
         div = {"day": 86400, "hour": 3600, "minute": 60}.get(meta.time_unit)
         if div:
             val = int(val / div) if val < 0 else val // div   # Go integer division truncates

@@ -174,3 +174,89 @@ def test_expression_parser_and_measures():
         q("count(*)", joins=[{"table": "cities"}])
     two_dims = q("count(*)", dimensions=[{"sqlExpression": "request_at", "timeBucketizer": "day"}, {"sqlExpression": "city_id"}])
     assert two_dims.num_dims_per_width == [0, 0, 1, 1, 0]
+
+
+# ---- time zones with a fixed offset over the query's range -------------------------------------------------------
+def _tz_table():
+    from aresdb_b200 import aql
+    return aql.Table("trips", [aql.Column("request_at", A.Uint32), aql.Column("city_id", A.Uint16),
+                               aql.Column("fare", A.Float32)])
+
+
+def test_parse_timezone_forms():
+    import datetime as dt
+    from aresdb_b200 import aql
+    assert aql.parse_timezone(None) is dt.timezone.utc and aql.parse_timezone("UTC") is dt.timezone.utc
+    assert aql.parse_timezone("-8").utcoffset(None) == dt.timedelta(hours=-8)
+    assert aql.parse_timezone("5:30").utcoffset(None) == dt.timedelta(hours=5, minutes=30)
+    assert aql.parse_timezone("-3:30").utcoffset(None) == -dt.timedelta(hours=3, minutes=30)
+    with pytest.raises(aql.AQLError):
+        aql.parse_timezone("Not/AZone")
+
+
+def test_fixed_offset_zone_shifts_time_filter_and_bucketizer():
+    """timezone "-8": `today` is the local calendar day (08:00 UTC to 08:00 UTC), and the hour bucketizer floors the
+    local clock: FLOOR(request_at + (-28800), 3600) — query/time_bucketizer.go:72-146."""
+    from aresdb_b200 import aql, expr as E
+    now = 1_727_000_000                                       # 2024-09-22 10:13:20 UTC = 02:13 local
+    q = {"table": "trips", "timezone": "-8", "measures": [{"sqlExpression": "count(*)"}],
+         "timeFilter": {"column": "request_at", "from": "today"},
+         "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}]}
+    agg = aql.compile_query(q, _tz_table(), now)
+    day_start_utc = 1_726_963_200 + 8 * 3600                  # local midnight of 2024-09-22 in UTC-8
+    lits = sorted(int(f.rhs.value) for f in agg.filters)
+    assert lits == [day_start_utc, now] and agg.tz_offset == -28800
+    d = agg.dimensions[0]
+    assert d.op == A.Floor and d.lhs.op == A.Plus and int(d.lhs.rhs.value) == -28800 and int(d.rhs.value) == 3600
+    utc = aql.compile_query(dict(q, timezone="UTC"), _tz_table(), now)
+    assert sorted(int(f.rhs.value) for f in utc.filters) == [1_726_963_200, now] and utc.tz_offset == 0
+    assert utc.dimensions[0].lhs.__class__ is E.Col
+
+
+def test_named_zone_without_a_switch_in_range_and_with_one():
+    from aresdb_b200 import aql
+    q = {"table": "trips", "timezone": "America/Los_Angeles", "measures": [{"sqlExpression": "count(*)"}],
+         "timeFilter": {"column": "request_at", "from": "2024-09-20", "to": "2024-09-21"},
+         "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "day"}]}
+    try:
+        agg = aql.compile_query(q, _tz_table(), 1_727_000_000)
+    except aql.AQLError:
+        pytest.skip("no tz database on this box")
+    assert agg.tz_offset == -7 * 3600                          # PDT
+    assert sorted(int(f.rhs.value) for f in agg.filters) == [1_726_815_600, 1_726_988_400]   # local midnights 09-20 .. 09-22
+    q["timeFilter"] = {"column": "request_at", "from": "2024-11-01", "to": "2024-11-05"}      # DST ends 2024-11-03
+    with pytest.raises(aql.AQLError):
+        aql.compile_query(q, _tz_table(), 1_731_000_000)
+
+
+def test_numeric_time_dimension_output_is_an_instant_again():
+    from aresdb_b200.postprocess import DimensionMeta, format_time_dimension
+    local_bucket = 1_726_963_200 + 3 * 3600                   # 03:00 on the local clock, produced with offset -8h
+    meta = DimensionMeta(time_bucketizer="hour", time_unit="second", from_offset=-28800)
+    assert format_time_dimension(local_bucket, meta) == str(local_bucket + 28800)
+    assert format_time_dimension(local_bucket, DimensionMeta(time_bucketizer="hour")) == "2024-09-22 03:00"
+
+
+def test_fixed_offset_query_end_to_end_on_the_checker():
+    """The compiled query (shifted time column, local-day time filter) through the reference call sequence on the C
+    restatement against a numpy restatement of what it means."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, synth
+    orc = H.get_backend("oracle")
+    table = aql.Table("trips", [aql.Column(n, t) for n, t in zip(synth.COLUMN_NAMES, synth.COLUMN_TYPES)])
+    hb = synth.generate_batch(0, 6000, num_cities=5, null_rate=0.0)
+    now = synth.BASE_TS + 86400 + 7 * 3600                     # 07:00 UTC of the next day = 23:00 local (UTC-8) of day 0
+    q = {"table": "trips", "timezone": "-8", "measures": [{"sqlExpression": "count(*)"}],
+         "timeFilter": {"column": "request_at", "from": "today"},
+         "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}]}
+    agg = aql.compile_query(q, table, now)
+    got = T.run_legacy(orc, agg, [hb])
+    ts = hb.values[synth.COL_REQUEST_AT].astype(np.int64)
+    lo = synth.BASE_TS + 8 * 3600                               # local midnight of day 0
+    sel = ts[(ts >= lo) & (ts < now)]
+    want = {}
+    for b in ((sel - 28800) // 3600 * 3600):
+        want[int(b)] = want.get(int(b), 0) + 1
+    have = {int(d): int(m) for d, m in zip(got.decoded_dims()[0], got.measures)}
+    assert have == want and len(have) == 16                     # local hours 00 .. 15 of the data's day
