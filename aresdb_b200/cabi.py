@@ -338,6 +338,7 @@ _PLAN_SIGS = {
                             _VP, C.c_int],
     "AggStateReset": [_VP, _VP, C.c_int],
     "AggStateDestroy": [_VP, C.c_int],
+    "ComputeColumnRanges": [C.POINTER(VectorPartySlice), C.c_int, C.POINTER(ColumnRange), _VP, C.c_int],
 }
 _MEM_SIGS = {
     "HostAlloc": [C.c_size_t], "HostFree": [_VP], "HostMemCpy": [_VP, _VP, C.c_size_t],

@@ -559,7 +559,7 @@ constexpr int kCmpTile = kCmpThreads * kCmpItems;
 // Compacts occupied slots: slotOf[g] = slot index, hash[g] = reference hash of the group's row,
 // vals[g] = accumulator (tight `width`-byte elements).
 __global__ void __launch_bounds__(kCmpThreads)
-compactGroupsKernel(DevTable G, size_t cap, uint8_t keyMode, uint8_t hashBits, int rowBytes, int width, ScanTileState st,
+compactGroupsKernel(DevTable G, size_t cap, uint8_t keyMode, uint8_t hashBits, uint64_t hashMask, int rowBytes, int width, ScanTileState st,
                     uint32_t *__restrict__ slotOf, uint64_t *__restrict__ hash, uint8_t *__restrict__ vals,
                     uint32_t *__restrict__ outCount) {
   __shared__ uint32_t sTile, sPrefix;
@@ -598,7 +598,7 @@ compactGroupsKernel(DevTable G, size_t cap, uint8_t keyMode, uint8_t hashBits, i
       h = key;
     }
     slotOf[pos] = (uint32_t)i;
-    hash[pos] = h;
+    hash[pos] = hashBits == 64 ? h & hashMask : h;
     storeMeasure(vals, pos, width, G.acc[i]);
     pos++;
   }
@@ -1305,7 +1305,7 @@ static void denseCarried(AggState *st, cudaStream_t s, DenseCarried &out, bool c
   ScanTileState sst = makeScanState(state.ptr, tiles);
   uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
   Scratch slotOf(sizeof(uint32_t) * (size_t)n, s), hash(sizeof(uint64_t) * (size_t)n, s), vals(sizeof(uint32_t) * (size_t)n, s);
-  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, 64, st->rowLayout.rowBytes, 4, sst,
+  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, 64, ~0ull, st->rowLayout.rowBytes, 4, sst,
                                                    slotOf.as<uint32_t>(), hash.as<uint64_t>(), vals.as<uint8_t>(), dCount);
   checkLastError("compactGroups");
   Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
@@ -1364,7 +1364,7 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
   ScanTileState sst = makeScanState(state.ptr, tiles);
   uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
   Scratch slotOf(sizeof(uint32_t) * (size_t)n, s), hash(sizeof(uint64_t) * (size_t)n, s), vals((size_t)width * n, s);
-  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, (uint8_t)st->hashBits,
+  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, (uint8_t)st->hashBits, testHash64Mask(),
                                                    st->rowLayout.rowBytes, width, sst, slotOf.as<uint32_t>(),
                                                    hash.as<uint64_t>(), vals.as<uint8_t>(), dCount);
   checkLastError("compactGroups");

@@ -21,6 +21,14 @@ int smCount() {
   return c;
 }
 
+uint64_t testHash64Mask() {
+  static const uint64_t mask = [] {
+    const char *e = getenv("ARESDB_B200_TEST_HASH64_MASK");
+    return e && *e ? (uint64_t)strtoull(e, nullptr, 16) : ~0ull;
+  }();
+  return mask;
+}
+
 void Scratch::reset(size_t n, cudaStream_t s) {
   release();
   stream = s;

@@ -63,6 +63,11 @@ inline CGoCallResHandle unsupported(const char *fn, const char *why) {
 // Number of SMs of the current device (cached per device).
 int smCount();
 
+// TEST SEAM: ARESDB_B200_TEST_HASH64_MASK=<hex> ANDs the 64-bit group-identity hash of a dimension row (legacy Sort and
+// the finalize of the fused path), so that the merge rule for colliding hashes can be exercised
+// (tests/test_hash_collisions.py).  ~0 unless the variable is set.
+uint64_t testHash64Mask();
+
 // Stream-ordered scratch from libmem's pool.  Freed when the object dies; the pool defers
 // reuse until the recorded stream has passed this point.
 struct Scratch {

@@ -17,12 +17,12 @@ namespace aresb {
 
 __global__ void __launch_bounds__(256)
 hashRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint32_t *__restrict__ index, int n,
-               uint64_t *__restrict__ hashOut) {
+               uint64_t *__restrict__ hashOut, uint64_t mask) {
   const uint32_t stride = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride) {
     uint64_t w[4];
     packRow(block, L, index[i], w);
-    hashOut[i] = murmur3_128_lo(w, L.rowBytes, 0);
+    hashOut[i] = murmur3_128_lo(w, L.rowBytes, 0) & mask;
   }
 }
 
@@ -163,7 +163,7 @@ static int gridFor(int64_t n, int perBlock, int maxPerSm = 8) {
 void hashRows(const uint8_t *block, const DimLayout &L, const uint32_t *index, int n, uint64_t *hashOut,
               cudaStream_t s) {
   if (n <= 0) return;
-  hashRowsKernel<<<gridFor(n, 256), 256, 0, s>>>(block, L, index, n, hashOut);
+  hashRowsKernel<<<gridFor(n, 256), 256, 0, s>>>(block, L, index, n, hashOut, testHash64Mask());
   checkLastError("hashRows");
 }
 

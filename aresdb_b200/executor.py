@@ -251,6 +251,18 @@ class LegacyBatchExecutor:
                            self.result_size)
 
 
+def compute_zone_map(lib: A.Library, space, columns: list) -> dict:
+    """{column index: (min, max)} of the VALID values of a device-resident batch, computed by the engine
+    (ComputeColumnRanges: one kernel over all columns) — what Batch.ranges / BatchPlan.Ranges take.  Called once when a
+    batch becomes device resident, the way the memstore maintains LiveVectorParty min / max at ingestion
+    (memstore/live_vector_party.go:74-75)."""
+    n = len(columns)
+    vps = (A.VectorPartySlice * n)(*columns)
+    out = (A.ColumnRange * n)()
+    lib.ComputeColumnRanges(vps, n, out, space.stream, space.device)
+    return {i: (int(out[i].Min), int(out[i].Max)) for i in range(n) if out[i].Known}
+
+
 class FusedBatchExecutor:
     """B200-native: one fused kernel per batch into a device-resident group table."""
 

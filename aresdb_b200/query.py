@@ -160,7 +160,6 @@ class QueryResult:
         for w in query.layout_widths:
             value_offs.append(pos)
             pos += w * capacity
-        self.rows = []
         raw_cols = []
         for p, qi in enumerate(query.dim_order):
             w = query.layout_widths[p]
@@ -169,9 +168,21 @@ class QueryResult:
             raw_cols.append((vals, valid))
             self.dim_values[qi] = vals
             self.dim_valid[qi] = valid
-        # packed rows in layout order (values then validity bytes): the reference's group identity
-        for g in range(groups):
-            self.rows.append(b"".join(bytes(v[g]) for v, _ in raw_cols) + bytes(bytearray(int(vd[g]) for _, vd in raw_cols)))
+        self._raw_cols = raw_cols
+        self._rows = None
+
+    def packed_rows(self) -> np.ndarray:
+        """uint8[groups, row_bytes]: the packed dimension rows in layout order (values, then validity bytes)."""
+        if not self._raw_cols:
+            return np.zeros((self.groups, 0), np.uint8)
+        return np.concatenate([v for v, _ in self._raw_cols] + [vd.reshape(-1, 1) for _, vd in self._raw_cols], axis=1)
+
+    @property
+    def rows(self) -> list:
+        """The reference's group identity: one bytes object per group (built on first use)."""
+        if self._rows is None:
+            self._rows = [r.tobytes() for r in self.packed_rows()]
+        return self._rows
 
     def as_dict(self) -> dict:
         """packed dim row (bytes) -> measure value."""

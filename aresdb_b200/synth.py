@@ -33,11 +33,20 @@ class HostBatch:
     day: int
 
 
+def zipf_cdf(num_cities: int, s: float = 1.1) -> np.ndarray:
+    """CDF of P(city = k) ~ k^-s over 1..num_cities (SURVEY.md 8d names a Zipf city distribution: a few hot
+    groups take most rows, which is what stresses same-address atomics)."""
+    w = np.arange(1, num_cities + 1, dtype=np.float64) ** -s
+    return np.cumsum(w / w.sum())
+
+
 def generate_batch(day: int, rows: int, num_cities: int = 100, null_rate: float = 0.01, seed: int = 20260922,
-                   exact_fares: bool = True) -> HostBatch:
+                   exact_fares: bool = True, city_dist: str = "uniform") -> HostBatch:
     rng = np.random.default_rng([seed, day])
     ts = (BASE_TS + day * 86400 + rng.integers(0, 86400, rows, dtype=np.uint32)).astype(np.uint32)
     city = rng.integers(1, num_cities + 1, rows, dtype=np.uint16).astype(np.uint16)
+    if city_dist == "zipf":
+        city = (np.searchsorted(zipf_cdf(num_cities), rng.random(rows), side="right") + 1).clip(1, num_cities).astype(np.uint16)
     status = (rng.integers(0, 2, rows, dtype=np.uint8) * rng.integers(1, 4, rows, dtype=np.uint8)).astype(np.uint8)
     # P(status == 1): half the rows get 0 ("not completed" bucket), the rest split 1..3 -> make 1 dominant
     status = np.where(rng.random(rows) < 0.5, np.uint8(STATUS_COMPLETED), status).astype(np.uint8)
@@ -80,7 +89,7 @@ def zone_map_of_day(day: int, num_cities: int = 100) -> dict:
 
 # ---- large-scale generation on the GPU (bench.py): same schema, torch RNG -------------------------
 def generate_batch_cuda(day: int, rows: int, device, num_cities: int = 100, null_rate: float = 0.01,
-                        seed: int = 20260922, exact_fares: bool = True):
+                        seed: int = 20260922, exact_fares: bool = True, city_dist: str = "uniform"):
     """Returns a list of per-column byte tensors on `device`, each laid out [null bitmap][values]
     with 64-byte aligned parts (mode 2), plus (nulls_offset=0, values_offset) per column.
     Generation is chunked so that temporaries stay small."""
@@ -93,10 +102,14 @@ def generate_batch_cuda(day: int, rows: int, device, num_cities: int = 100, null
     values_off = (bitmap_bytes + 63) // 64 * 64
     bufs = [torch.zeros(values_off + ((rows * w + 64) // 64 * 64), dtype=torch.uint8, device=device) for w in np_bytes]
     weights = (2 ** torch.arange(8, device=device, dtype=torch.int32)).to(torch.uint8)
+    cdf = torch.from_numpy(zipf_cdf(num_cities)).to(device) if city_dist == "zipf" else None
     for c0 in range(0, rows, chunk):
         n = min(chunk, rows - c0)
         ts = (torch.randint(0, 86400, (n,), generator=g, device=device, dtype=torch.int64) + (BASE_TS + day * 86400))
         city = torch.randint(1, num_cities + 1, (n,), generator=g, device=device, dtype=torch.int32)
+        if cdf is not None:
+            u = torch.rand(n, generator=g, device=device, dtype=torch.float64)
+            city = (torch.searchsorted(cdf, u, right=True) + 1).clamp(1, num_cities).to(torch.int32)
         st_other = torch.randint(0, 4, (n,), generator=g, device=device, dtype=torch.int32)
         status = torch.where(torch.rand(n, generator=g, device=device) < 0.5,
                              torch.full_like(st_other, STATUS_COMPLETED), st_other)

@@ -8,8 +8,12 @@ synthetic fact table (BASELINE.json, config "1e9 rows, 3 filters + time-bucketiz
 
 A step = one whole query: every archive batch of the table goes through ExecuteBatchPlan (one fused
 kernel per batch), then AggStateFinalize; with N > 1 the 8 day-batches are dealt round-robin to the
-ranks (strong scaling: the table stays 1e9 rows) and the per-GPU group tables are all-gathered over
-NCCL and merged on every rank.  One JSON line on stdout (rank 0).
+ranks (strong scaling: the table stays 1e9 rows) and the per-GPU group tables are merged over NCCL.
+One JSON line on stdout (rank 0).  Zone maps (BatchPlan.Ranges) are PRODUCED by the engine
+(ComputeColumnRanges, once per batch when it becomes device resident, timed separately); the result of
+every workload is verified once, outside the timed region, against an independent torch restatement
+(tests/independent.py) — `"verified": true`.  At N = 1 the line also carries the other BASELINE
+configurations as `workloads` sub-results (same data, same code, fewer steps).
 """
 from __future__ import annotations
 
@@ -81,24 +85,26 @@ WORKLOADS = {
                       "request_at in [t0+1800, t0+8d-1800); dims floor(request_at,3600) x city_id; SUM(fare) in f64",
                  query=_q_cfg3, bytes_per_row=4 + 2 + 1 + 4 + 4 / 8.0, rows=1_000_000_000, batches=8, expected_groups=0,
                  dtype="u32/u16/u8 filters; f32 fares summed into f64 (exactly, as integers on the 2^-S grid the zone map allows)",
-                 metric="rows/s, 1e9-row time-bucketed SUM group-by (cfg3)"),
+                 metric="rows/s, 1e9-row time-bucketed SUM group-by (cfg3)", check="cfg3"),
     "cfg3_count": dict(desc="cfg3 count(*) variant: filters status==1, fare>5.0, city_id!=0; dims floor(request_at,3600) x "
                             "city_id; COUNT in u32", query=_q_cfg3_count, bytes_per_row=4 + 2 + 1 + 4 + 4 / 8.0,
                        rows=1_000_000_000, batches=8, expected_groups=0, dtype="u32 count",
-                       metric="rows/s, 1e9-row time-bucketed COUNT group-by (cfg3)"),
+                       metric="rows/s, 1e9-row time-bucketed COUNT group-by (cfg3)", check="cfg3_count"),
     "cfg2": dict(desc="cfg2: 1e8-row fact table, one batch; filter status==1; dim city_id; SUM(fare) in f64",
                  query=_q_cfg2, bytes_per_row=1 + 2 + 4 + 3 / 8.0, rows=100_000_000, batches=1, expected_groups=0,
-                 dtype="u8 filter, f32->f64 sum", metric="rows/s, 1e8-row SUM group-by 1 dim (cfg2)"),
-    "cfg4": dict(desc="cfg4: 1e9 rows as 8 day-batches, no filter; dims city_id x floor(request_at,60) (1.15e6 groups); "
+                 dtype="u8 filter, f32->f64 sum", metric="rows/s, 1e8-row SUM group-by 1 dim (cfg2)", check="cfg2"),
+    "cfg4": dict(desc="cfg4: 1e9 rows as 8 day-batches, no filter; dims city_id x floor(request_at,60) (1.16e6 groups); "
                       "SUM(fare) in f64, hash-reduce semantics", query=_q_cfg4, bytes_per_row=4 + 2 + 4 + 3 / 8.0,
                  rows=1_000_000_000, batches=8, expected_groups=1_300_000, dtype="f32->f64 sum, 32-bit hash identity",
-                 metric="rows/s, 1e9-row high-cardinality SUM group-by (cfg4)"),
+                 metric="rows/s, 1e9-row high-cardinality SUM group-by (cfg4)", check="cfg4"),
     "cfg4_hll": dict(desc="cfg4 HLL: 1e9 rows as 8 day-batches; filter status==1; dims floor(request_at,86400) x city_id "
-                          "(800 groups); countdistincthll(request_at), p=14 registers",
+                          "(808 groups); countdistincthll(request_at), p=14 registers",
                      query=_q_cfg4_hll, bytes_per_row=4 + 2 + 1 + 3 / 8.0, rows=1_000_000_000, batches=8,
                      expected_groups=0, dtype="u32 murmur3 -> rho/register max (dense registers per group)",
-                     metric="rows/s, 1e9-row HLL distinct-count group-by (cfg4)"),
+                     metric="rows/s, 1e9-row HLL distinct-count group-by (cfg4)", check="cfg4_hll"),
 }
+WORKLOADS["cfg3_zipf"] = dict(WORKLOADS["cfg3"], desc=WORKLOADS["cfg3"]["desc"] + "; city_id ~ Zipf(1.1)", city_dist="zipf",
+                              metric="rows/s, 1e9-row time-bucketed SUM group-by (cfg3, Zipf cities)")
 WL = WORKLOADS["cfg3"]
 
 
@@ -114,9 +120,29 @@ def build_query():
 # ---------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the reference's own per-node call sequence on host cores
 # ---------------------------------------------------------------------------------------------------
+def _physical_cores() -> list[int]:
+    """One logical CPU per physical core of this process's affinity set (first SMT sibling)."""
+    allowed = sorted(os.sched_getaffinity(0))
+    seen, out = set(), []
+    for c in allowed:
+        try:
+            sib = Path(f"/sys/devices/system/cpu/cpu{c}/topology/thread_siblings_list").read_text().strip()
+        except OSError:
+            sib = str(c)
+        if sib not in seen:
+            seen.add(sib)
+            out.append(c)
+    return out
+
+
 def _cpu_worker(args):
-    """One worker process = one table shard slice: runs the reference call sequence over its rows."""
-    kind, day, rows, reps, wl_name = args
+    """One worker process = one table shard slice, pinned to one core: runs the reference call sequence over its rows,
+    `reps` times, every repetition started together with the other workers (barrier)."""
+    kind, slot, cpu, rows, reps, wl_name, barrier, out_q = args
+    try:
+        os.sched_setaffinity(0, {cpu})
+    except OSError:
+        pass
     select_workload(wl_name)
     sys.path.insert(0, str(ROOT))
     from aresdb_b200 import cabi, columns, synth
@@ -128,7 +154,7 @@ def _cpu_worker(args):
     else:
         lib = cabi.Library(ROOT / "oracle" / "build" / "liboracle.so", None, has_plan_api=False, name="oracle")
     sp = HostSpace()
-    hb = synth.generate_batch(day % WL["batches"], rows, seed=777 + day)
+    hb = synth.generate_batch(slot % WL["batches"], rows, seed=777 + slot, city_dist=WL.get("city_dist", "uniform"))
     cols, keep = [], []
     for dt, v, ok in zip(synth.COLUMN_TYPES, hb.values, hb.valid):
         buf, vp = columns.make_column(sp, dt, v, valid=ok)
@@ -145,6 +171,8 @@ def _cpu_worker(args):
     times, groups = [], 0
     try:
         for _ in range(reps):
+            if barrier is not None:
+                barrier.wait()
             t = time.perf_counter()
             ex = LegacyBatchExecutor(lib, sp, q)
             ex.process_batch(Batch(cols, rows), is_last=True)
@@ -153,34 +181,52 @@ def _cpu_worker(args):
     finally:
         os.dup2(saved, 1)
         os.close(devnull)
-    return times, groups
+    out_q.put((slot, times, groups))
+
+
+def _run_workers(ctx, kind, cpus, rows, reps, wl_name):
+    barrier = ctx.Barrier(len(cpus)) if len(cpus) > 1 else None
+    out_q = ctx.Queue()
+    procs = [ctx.Process(target=_cpu_worker, args=((kind, i, c, rows, reps, wl_name, barrier, out_q),)) for i, c in enumerate(cpus)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=1800) for _ in procs]
+    for p in procs:
+        p.join()
+    return sorted(res)
 
 
 def cpu_reference_run(steps: int, warmup: int, rows_per_worker: int, workers: int | None = None, wl_name: str = "cfg3"):
-    """Times the reference CPU path: `workers` processes, each running the reference's
-    single-threaded batch executor over its own slice (the reference's unit of parallelism is the
-    table shard / batch).  A step = every worker processing its slice once, concurrently."""
+    """Times the reference CPU path.  (i) ONE single-threaded executor on one core (the reference's HOST path is
+    single-threaded per batch).  (ii) One executor per PHYSICAL core, each pinned, each over its own slice (the
+    reference's unit of parallelism is the table shard / batch); every step starts behind a barrier, a step's time is
+    its slowest worker, and the reported value is the MEDIAN over the steps."""
     import multiprocessing as mp
     kind = "reference" if (ROOT / "oracle" / "_ref" / "libalgorithm.so").exists() else "port"
     if kind == "port":
         sys.path.insert(0, str(ROOT / "oracle"))
         import build_oracle
         build_oracle.build()
-    cores = os.cpu_count() or 1
-    workers = workers or max(1, min(cores, 64))   # one per physical core: 128 SMT workers measured 30-45 % slower on the GPU box
+    cores = _physical_cores()
+    workers = max(1, min(workers or len(cores), len(cores), 128))
+    cpus = cores[:workers]
     ctx = mp.get_context("spawn")
-    with ctx.Pool(workers) as pool:
-        t0 = time.perf_counter()
-        res = pool.map(_cpu_worker, [(kind, d, rows_per_worker, steps + warmup, wl_name) for d in range(workers)])
-        wall = time.perf_counter() - t0
-    # per step, the job time is the slowest worker (they run concurrently)
-    per_step = [max(r[0][i] for r in res) for i in range(warmup, warmup + steps)]
-    ms = float(np.mean(per_step)) * 1e3
+    t0 = time.perf_counter()
+    single = _run_workers(ctx, kind, cpus[:1], rows_per_worker, 1 + max(1, min(steps, 3)), wl_name)
+    single_s = float(np.median(single[0][1][1:]))
+    res = _run_workers(ctx, kind, cpus, rows_per_worker, steps + warmup, wl_name)
+    wall = time.perf_counter() - t0
+    per_step = [max(r[1][i] for r in res) for i in range(warmup, warmup + steps)]   # barriered: slowest worker of the step
+    ms = float(np.median(per_step)) * 1e3
     sample_rows = rows_per_worker * workers
     return {"value": sample_rows / (ms / 1e3), "ms_per_step": ms, "kind": kind, "cores": workers,
-            "host_cores": cores, "sample": f"{workers} concurrent single-threaded workers x {rows_per_worker} rows of the "
-                                          f"{wl_name} query per step (reference HOST path is single-threaded per batch)",
-            "groups": int(res[0][1]), "wall_s": wall}
+            "host_cores": os.cpu_count() or 1, "physical_cores": len(cores),
+            "single_core_rows_per_s": rows_per_worker / single_s,
+            "step_ms": [round(x * 1e3, 2) for x in per_step],
+            "sample": f"{workers} pinned single-threaded workers (one per physical core) x {rows_per_worker} rows of the "
+                      f"{wl_name} query per step, barrier per step, median of {steps} steps (reference HOST path is "
+                      "single-threaded per batch)",
+            "groups": int(res[0][2]), "wall_s": wall}
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -228,6 +274,115 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------
 # the B200 arm
 # ---------------------------------------------------------------------------------------------------
+class DeviceTable:
+    """The synthetic fact table of one rank: its day-batches resident in HBM (+ pinned host mirrors for e2e)."""
+
+    def __init__(self, lib, space, dev, days, rows_per_batch, city_dist, mirror_host):
+        import torch
+        from aresdb_b200 import columns, synth
+        from aresdb_b200.executor import compute_zone_map
+        self.days, self.rows_per_batch = days, rows_per_batch
+        self.bufs, self.cols, self.zone_maps, self.host = [], [], [], []
+        self.values_off = None
+        zm_ms = []
+        for d in days:
+            bufs, self.values_off = synth.generate_batch_cuda(d, rows_per_batch, dev, city_dist=city_dist)
+            cols = [columns.slice_of(b.data_ptr(), dt, rows_per_batch, 0, self.values_off, 2) for b, dt in zip(bufs, synth.COLUMN_TYPES)]
+            self.bufs.append(bufs)
+            self.cols.append(cols)
+            # the engine produces the zone map of the batch (ComputeColumnRanges); timed with CUDA events
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            zm = compute_zone_map(lib, space, cols)
+            e.record()
+            torch.cuda.synchronize()
+            zm_ms.append(s.elapsed_time(e))
+            self.zone_maps.append(zm)
+            if mirror_host:
+                hb = []
+                for b in bufs:
+                    h = torch.empty(b.numel(), dtype=torch.uint8, pin_memory=True)
+                    h.copy_(b)
+                    hb.append(h)
+                self.host.append(hb)
+        torch.cuda.synchronize()
+        self.zone_map_ms = float(np.median(zm_ms[1:] or zm_ms)) if zm_ms else None
+
+    def batches(self, zone_maps: bool, rows: int | None = None, count: int | None = None):
+        from aresdb_b200 import columns, synth
+        from aresdb_b200.executor import Batch
+        out = []
+        for i in range(len(self.days) if count is None else min(count, len(self.days))):
+            if rows is None or rows == self.rows_per_batch:
+                cols, n = self.cols[i], self.rows_per_batch
+            else:   # a prefix of the batch (cfg2: 1e8 rows of day 0)
+                n = rows
+                cols = [columns.slice_of(b.data_ptr(), dt, n, 0, self.values_off, 2) for b, dt in zip(self.bufs[i], synth.COLUMN_TYPES)]
+            out.append(Batch(cols, n, ranges=self.zone_maps[i] if zone_maps else None))
+        return out
+
+
+def _verify(name, ex_result, table: "DeviceTable", dev, rows, count, is_hll, world, dist):
+    """Independent check of one workload's result (outside every timed region).  Returns (ok, info)."""
+    sys.path.insert(0, str(ROOT / "tests"))
+    import independent as I
+    from aresdb_b200 import synth
+    t0 = synth.BASE_TS
+    check = WORKLOADS[name]["check"]
+    exp = I.Expected(check, NUM_BATCHES, dev, t0, t0 + 1800, t0 + NUM_BATCHES * 86400 - 1800)
+    for i in range(len(table.days) if count is None else min(count, len(table.days))):
+        exp.add_batch(table.bufs[i], table.values_off, rows)
+    if world > 1:   # every rank holds its own days: the group space is global, sums of exact values are exact
+        dist.all_reduce(exp.vals)
+        p = exp.present.to(exp.vals.dtype)
+        dist.all_reduce(p)
+        exp.present = p != 0
+        import torch
+        k = torch.tensor([exp.rows_kept], device=dev, dtype=torch.int64)
+        dist.all_reduce(k)
+        exp.rows_kept = int(k.item())
+    try:
+        if is_hll:
+            info = exp.check_hll(ex_result)
+        elif name == "cfg4":
+            info = _check_hash_identity(exp, ex_result)
+        else:
+            info = exp.check(ex_result)
+        return True, info
+    except AssertionError as e:
+        return False, {"error": str(e)[:300]}
+
+
+def _check_hash_identity(exp, res):
+    """cfg4 runs with the reference's 32-bit hash identity: groups whose packed rows collide in murmur3-32 are ONE group
+    (query/hash_reduction.cu:216-243); everything else must equal the independent result."""
+    import hashes
+    import independent as I
+    from aresdb_b200 import synth
+    rows = res.packed_rows()
+    h = hashes.murmur3_32(rows)
+    present = exp.present.cpu().numpy()
+    vals = exp.vals.cpu().numpy()
+    gidx = np.nonzero(present)[0]
+    tidx, cidx = gidx // I.CITY_SPACE, gidx % I.CITY_SPACE
+    tnull, cnull = tidx == exp.tn - 1, cidx == I.CITY_SPACE - 1
+    erow = np.zeros((gidx.size, 8), np.uint8)
+    erow[:, 0:4] = np.where(tnull, 0, synth.BASE_TS + tidx * 60).astype("<u4").view(np.uint8).reshape(-1, 4)
+    erow[:, 4:6] = np.where(cnull, 0, cidx).astype("<u2").view(np.uint8).reshape(-1, 2)
+    erow[:, 6] = ~tnull
+    erow[:, 7] = ~cnull
+    eh = hashes.murmur3_32(erow)
+    order = np.argsort(eh, kind="stable")
+    uniq, start = np.unique(eh[order], return_index=True)
+    sums = np.add.reduceat(vals[gidx][order], start)
+    assert res.groups == uniq.size == len(np.unique(h)), f"{res.groups} groups, expected {uniq.size}"
+    pos = np.searchsorted(uniq, h)
+    assert (uniq[pos] == h).all() and (res.measures.view(np.uint64) == sums[pos].view(np.uint64)).all(), "sums differ"
+    return {"groups": int(res.groups), "rows_kept": exp.rows_kept, "distinct_rows": int(gidx.size),
+            "merged_by_murmur3_32": int(gidx.size - uniq.size)}
+
+
 def gpu_run(args):
     # keep stdout clean for the single JSON line: libraries (NCCL prints its version) write to fd 1
     real_stdout = os.dup(1)
@@ -238,6 +393,8 @@ def gpu_run(args):
     from aresdb_b200 import columns, synth
     from aresdb_b200.executor import Batch
     from aresdb_b200.memory import CudaSpace
+    from aresdb_b200.query import QueryResult
+    from aresdb_b200.sharding import ShardedFusedQuery
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -249,185 +406,256 @@ def gpu_run(args):
     lib = A.load_engine()
     stream = torch.cuda.current_stream().cuda_stream
     space = CudaSpace(local, stream)
-    q = build_query()
-    num_batches = WL["batches"]
     rows_total = args.rows or WL["rows"]
+    num_batches = WL["batches"]
     rows_per_batch = rows_total // num_batches
     my_days = [d for d in range(num_batches) if d % world == rank]
-    is_hll = q.is_hll
+    # one table per rank; at N = 1 the sub-workloads reuse it (cfg2 = the first 1e8 rows of day 0)
+    table = DeviceTable(lib, space, dev, my_days, rows_per_batch, WL.get("city_dist", "uniform"), mirror_host=not args.no_e2e)
+    zone_map_ms = table.zone_map_ms
 
-    # ---- data: generated on the GPU, mirrored into pinned host memory for the e2e leg -------------
-    dev_bufs, batches, host_bufs = [], [], []
-    for d in my_days:
-        bufs, values_off = synth.generate_batch_cuda(d, rows_per_batch, dev)
-        dev_bufs.append(bufs)
-        cols = [columns.slice_of(b.data_ptr(), dt, rows_per_batch, 0, values_off, 2) for b, dt in zip(bufs, synth.COLUMN_TYPES)]
-        batches.append(Batch(cols, rows_per_batch, ranges=None if args.no_zone_maps else synth.zone_map_of_day(d, WL.get("num_cities", 100))))
-        if not args.no_e2e:
-            hb = []
-            for b in bufs:
-                h = torch.empty(b.numel(), dtype=torch.uint8, pin_memory=True)
-                h.copy_(b)
-                hb.append(h)
-            host_bufs.append(hb)
-    torch.cuda.synchronize()
+    def run_workload(name, steps, warmup, zone_maps, table, with_kernel=True, with_e2e=False, verify=True):
+        """Times one workload on `table`; returns the sub-result dict (device-resident value, kernel-alone roofline,
+        optional e2e, verification)."""
+        wl = WORKLOADS[name]
+        q = wl["query"]()
+        nb = wl["batches"]
+        rows_b = (args.rows or wl["rows"]) // nb
+        count = len(table.days) if nb > 1 else 1
+        batches = table.batches(zone_maps, rows_b, count)
+        rows_all = (args.rows or wl["rows"])
+        ex = ShardedFusedQuery(lib, space, q, expected_groups=wl["expected_groups"])
 
-    from aresdb_b200.sharding import ShardedFusedQuery
-    ex = ShardedFusedQuery(lib, space, q, expected_groups=WL["expected_groups"])
+        def finish():
+            if q.is_hll:
+                return ex.finalize_hll()
+            return ex.finalize()
 
-    def finish():
-        """(groups, d2h bytes): the query result lands in host memory."""
-        if is_hll:
-            r = ex.finalize_hll()
-            return r.groups, int(r.regs.size + r.counts.size * 2 + r.groups * q.row_bytes)
-        g, out = ex.finalize()
-        return g, out
+        def step_device():
+            ex.reset()
+            for b in batches:
+                ex.process_batch(b)
+            return finish()
 
-    def step_device():
-        ex.reset()
-        for b in batches:
-            ex.process_batch(b)
-        return finish()
+        def timed(fn, steps, warmup):
+            for _ in range(warmup):
+                fn()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            launches0 = lib.kernel_launch_count()
+            evs[0].record()
+            last = None
+            for i in range(steps):
+                last = fn()
+                evs[i + 1].record()
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+            per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
+            ms = evs[0].elapsed_time(evs[steps]) / steps
+            launches = (lib.kernel_launch_count() - launches0) // steps
+            if world > 1:
+                t = torch.tensor([ms] + per, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                ms, per = float(t[0].item()), [float(x) for x in t[1:].tolist()]
+            return ms, per, launches, last
 
-    # e2e: host (pinned) columns -> H2D on a copy stream, double-buffered against the fused kernel
-    copy_stream = torch.cuda.Stream(device=dev)
-    staging = None
-    if not args.no_e2e and batches:
-        staging = [[torch.empty_like(b) for b in dev_bufs[0]] for _ in range(2)]
+        if name == args.workload and args.profile_range:  # `ncu --profile-from-start off`: only these steps are captured
+            torch.cuda.profiler.start()
+        ms, per, launches, last = timed(step_device, steps, warmup)
+        if name == args.workload and args.profile_range:
+            torch.cuda.synchronize()
+            torch.cuda.profiler.stop()
+        out = {"value": rows_all / (ms / 1e3), "unit": "rows/s", "ms_per_step": ms, "p50_query_ms": float(np.median(per)),
+               "steps": steps, "gpu_launches": int(launches), "zone_maps": bool(zone_maps)}
 
-    def step_e2e():
-        ex.reset()
-        main = torch.cuda.current_stream()
-        free_ev = [None, None]
-        h2d = 0
-        for i, hb in enumerate(host_bufs):
-            slot = i & 1
-            with torch.cuda.stream(copy_stream):
-                if free_ev[slot] is not None:
-                    copy_stream.wait_event(free_ev[slot])
-                elif i == 0:
-                    copy_stream.wait_stream(main)
-                for dst, src in zip(staging[slot], hb):
-                    dst.copy_(src, non_blocking=True)
-                    h2d += src.numel()
-                ready = torch.cuda.Event()
-                ready.record(copy_stream)
-            main.wait_event(ready)
-            values_off = (rows_per_batch + 7) // 8 + 1
-            values_off = (values_off + 63) // 64 * 64
-            cols = [columns.slice_of(t.data_ptr(), dt, rows_per_batch, 0, values_off, 2)
-                    for t, dt in zip(staging[slot], synth.COLUMN_TYPES)]
-            ex.process_batch(Batch(cols, rows_per_batch, ranges=batches[i].ranges))
-            free_ev[slot] = torch.cuda.Event()
-            free_ev[slot].record(main)
-        g, out = finish()
-        if is_hll:
-            return g, h2d, out
-        dims_h = out.dims.handle[: max(out.dims.nbytes, 1)].cpu()
-        meas_h = out.measures.handle[: g * q.measure_bytes].cpu()
-        return g, h2d, dims_h.numel() + meas_h.numel()
+        # dominant kernel timed alone (one launch per batch, back to back), L2 cold because a batch >> L2
+        if with_kernel and batches:
+            ex.reset()
+            torch.cuda.synchronize()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = max(2, min(steps, 5))
+            l0 = lib.kernel_launch_count()
+            s.record()
+            for _ in range(reps):
+                for b in batches:
+                    ex.process_batch(b)
+            e.record()
+            torch.cuda.synchronize()
+            kern_ms = s.elapsed_time(e) / (reps * len(batches))
+            algo = wl["bytes_per_row"] * rows_b
+            out["roofline"] = {"bound": "hbm", "kernel": "aresFusedJit (NVRTC-specialised fused scan-filter-aggregate)",
+                               "achieved": algo / (kern_ms / 1e3) / 1e9, "peak": PEAK, "unit": "GB/s",
+                               "frac": algo / (kern_ms / 1e3) / 1e9 / PEAK, "kernel_ms": kern_ms,
+                               "launches_per_batch": (lib.kernel_launch_count() - l0) / (reps * len(batches)),
+                               "algorithmic_bytes_per_launch": algo, "peak_source": PEAK_SRC}
 
-    def timed(fn, steps, warmup):
-        for _ in range(warmup):
-            fn()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        launches0 = lib.kernel_launch_count()
-        s.record()
-        last = None
-        for _ in range(steps):
-            last = fn()
-        e.record()
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        ms = s.elapsed_time(e) / steps
-        launches = (lib.kernel_launch_count() - launches0) // steps
-        if world > 1:
-            t = torch.tensor([ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms, launches, last
+        # result check, once, outside the timed regions
+        if verify:
+            if q.is_hll:
+                res = last
+            else:
+                g, bufs = last
+                res = QueryResult(q, bufs.dims.get(np.uint8), bufs.capacity, bufs.measures.get(np.uint8), g)
+            ok, info = _verify(name, res, table, dev, rows_b, count, q.is_hll, world, dist)
+            out["verified"] = bool(ok)
+            out["check"] = info
+            out["groups"] = int(res.groups)
+        else:
+            out["groups"] = int(last.groups if q.is_hll else last[0])
+
+        if with_e2e and table.host:
+            out["e2e"] = run_e2e(ex, q, table, batches, rows_all, timed, steps)
+        ex.close()
+        return out
+
+    def run_e2e(ex, q, table, batches, rows_all, timed, steps):
+        """The same query from HOST (pinned) columns: every step copies every batch host->device through the boundary's
+        own libmem (AsyncCopyHostToDevice on a copy stream created by CreateCudaStream, WaitForCudaStream — the
+        reference's transferBatch protocol, memstore/batch.go + cgoutils/memory.go), double-buffered against the
+        fused kernels by a copier thread, produces the batch's zone map on the device, and reads the result back."""
+        from aresdb_b200.executor import compute_zone_map
+        copy_stream = lib.CreateCudaStream(local)
+        staging = [[torch.empty_like(b) for b in table.bufs[0]] for _ in range(2)]
+        nb = len(batches)
+        rows_b = batches[0].num_rows
+        stats = {}
+
+        def step_e2e():
+            ex.reset()
+            main = torch.cuda.current_stream()
+            ready = [threading.Event() for _ in range(nb)]
+            freed = [None] * nb
+            freed_set = [threading.Event() for _ in range(nb)]
+            h2d = [0]
+            err = []
+
+            def copier():
+                try:
+                    torch.cuda.set_device(local)
+                    for i in range(nb):
+                        slot = i & 1
+                        if i >= 2:
+                            freed_set[i - 2].wait()
+                            freed[i - 2].synchronize()   # the kernel that read this staging slot is done
+                        for dst, src in zip(staging[slot], table.host[i]):
+                            lib.AsyncCopyHostToDevice(dst.data_ptr(), src.data_ptr(), src.numel(), copy_stream, local)
+                            h2d[0] += src.numel()
+                        lib.WaitForCudaStream(copy_stream, local)
+                        ready[i].set()
+                except Exception as e:   # noqa: BLE001
+                    err.append(e)
+                    for r in ready:
+                        r.set()
+
+            if nb:
+                main.synchronize()      # staging slots of the previous step are free
+            th = threading.Thread(target=copier)
+            th.start()
+            for i in range(nb):
+                ready[i].wait()
+                if err:
+                    raise err[0]
+                slot = i & 1
+                cols = [columns.slice_of(t.data_ptr(), dt, rows_b, 0, table.values_off, 2) for t, dt in zip(staging[slot], synth.COLUMN_TYPES)]
+                zm = compute_zone_map(lib, space, cols) if batches[i].ranges is not None else None
+                ex.process_batch(Batch(cols, rows_b, ranges=zm))
+                ev = torch.cuda.Event()
+                ev.record(main)
+                freed[i] = ev
+                freed_set[i].set()
+            th.join()
+            if q.is_hll:
+                r = ex.finalize_hll()
+                d2h = int(r.regs.size + r.counts.size * 2 + r.groups * q.row_bytes)
+                stats.update(h2d=h2d[0], d2h=d2h)
+                return r
+            g, out = ex.finalize()
+            dims_h = out.dims.handle[: max(out.dims.nbytes, 1)].cpu()
+            meas_h = out.measures.handle[: g * q.measure_bytes].cpu()
+            stats.update(h2d=h2d[0], d2h=int(dims_h.numel() + meas_h.numel()))
+            return g, out
+
+        e_ms, per, _, _ = timed(step_e2e, max(1, steps // 2), 1)
+        lib.DestroyCudaStream(copy_stream, local)
+        return {"value": rows_all / (e_ms / 1e3), "unit": "rows/s", "ms_per_step": e_ms,
+                "h2d_bytes_per_step": int(stats.get("h2d", 0)) * world, "d2h_bytes_per_step": int(stats.get("d2h", 0)),
+                "copy_path": "libmem AsyncCopyHostToDevice + WaitForCudaStream (C ABI), zone map computed on the device per batch"}
 
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    if args.profile_range:  # `ncu --profile-from-start off`: only the timed steps are captured
-        torch.cuda.profiler.start()
-    ms, launches, last = timed(step_device, args.steps, args.warmup)
-    if args.profile_range:
-        torch.cuda.synchronize()
-        torch.cuda.profiler.stop()
-    groups = last[0]
-
-    # dominant kernel (fusedBatchKernel) timed alone, L2 cold because each batch (1.4 GB) >> L2
-    kern_ms = None
-    if batches:
-        ex.reset()
-        torch.cuda.synchronize()
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = max(2, min(args.steps, 5))
-        s.record()
-        for _ in range(reps):
-            for b in batches:
-                ex.process_batch(b)
-        e.record()
-        torch.cuda.synchronize()
-        kern_ms = s.elapsed_time(e) / (reps * len(batches))
-
-    e2e = None
-    if not args.no_e2e and host_bufs:
-        e_ms, _, e_last = timed(step_e2e, max(1, args.steps // 2), 1)
-        e2e = {"value": rows_total / (e_ms / 1e3), "unit": "rows/s", "ms_per_step": e_ms,
-               "h2d_bytes_per_step": int(e_last[1]) * world, "d2h_bytes_per_step": int(e_last[2])}
+    main = run_workload(args.workload, args.steps, args.warmup, not args.no_zone_maps, table, with_e2e=not args.no_e2e)
     clocks = sampler.stop() if rank == 0 else None
+
+    subs = {}
+    if world == 1 and not args.no_sub and args.workload == "cfg3" and not args.rows:
+        sub_steps, sub_warm = max(3, min(args.steps, 5)), 3
+        subs["cfg3_nozm"] = run_workload("cfg3", sub_steps, sub_warm, False, table)
+        for name in ("cfg3_count", "cfg2", "cfg4", "cfg4_hll"):
+            subs[name] = run_workload(name, sub_steps, sub_warm, True, table)
+        if not args.no_zipf:
+            del table
+            torch.cuda.empty_cache()
+            ztable = DeviceTable(lib, space, dev, list(range(NUM_BATCHES)), 125_000_000, "zipf", mirror_host=False)
+            subs["cfg3_zipf"] = run_workload("cfg3_zipf", sub_steps, sub_warm, True, ztable)
+            del ztable
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
-    peaks = {}
-    try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    algo_bytes = WL["bytes_per_row"] * rows_per_batch
     traffic = None
     try:  # DRAM bytes per launch from the committed ncu capture of this workload's kernel, scaled to this batch size
-        t = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text()).get(args.workload)
-        if t:
-            traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * rows_per_batch / t["rows_per_launch"]
+        for f in ("r02_traffic.json", "r01_traffic.json"):
+            if (ROOT / "profiles" / f).exists():
+                t = json.loads((ROOT / "profiles" / f).read_text()).get(args.workload)
+                if t:
+                    traffic = (t["dram_bytes_read"] + t["dram_bytes_write"]) * (rows_total // num_batches) / t["rows_per_launch"]
+                    break
     except Exception:
         pass
-    achieved = algo_bytes / (kern_ms / 1e3) / 1e9 if kern_ms else None
     cpu = None
     if world == 1 and not args.no_cpu:
-        cpu = cpu_reference_run(steps=2, warmup=1, rows_per_worker=args.cpu_rows, wl_name=args.workload)
-        cpu = {k: cpu[k] for k in ("value", "kind", "cores", "host_cores", "sample")}
+        cpu = cpu_reference_run(steps=3, warmup=1, rows_per_worker=args.cpu_rows, wl_name=args.workload)
+        cpu = {k: cpu[k] for k in ("value", "kind", "cores", "host_cores", "physical_cores", "single_core_rows_per_s", "step_ms", "sample")}
         cpu["unit"] = "rows/s"
+    roof = main.get("roofline") or {}
+    roof["traffic"] = traffic
     out = {
-        "metric": WL["metric"], "value": rows_total / (ms / 1e3), "unit": "rows/s",
-        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "p50_query_ms": ms,
+        "metric": WL["metric"], "value": main["value"], "unit": "rows/s",
+        "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
+        "p50_query_ms": main["p50_query_ms"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": WL["dtype"],
-        "data": "synthetic", "groups": int(groups),
-        "config": {"workload": WL["desc"], "rows": rows_total, "batches": num_batches, "rows_per_batch": rows_per_batch,
-                   "parallelism": f"batches round-robin over {world} GPU(s), NCCL all-gather merge" if world > 1 else "1 GPU",
-                   "l2": f"inputs ({algo_bytes / 1e9:.2f} GB per batch) larger than the 126 MB L2; no flush needed",
-                   "zone_maps": "off" if args.no_zone_maps else "per-batch column min/max passed as BatchPlan.Ranges (direct-indexed aggregation where every dimension is bounded)"},
-        "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "aresFusedJit (NVRTC-specialised fused scan-filter-aggregate)", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": traffic,
-                     "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s",
-                     "kernel_ms": kern_ms, "algorithmic_bytes_per_launch": algo_bytes},
-        "e2e": e2e, "cpu_baseline": cpu, "clocks": clocks,
+        "data": "synthetic", "groups": main["groups"], "verified": main.get("verified"), "check": main.get("check"),
+        "config": {"workload": WL["desc"], "rows": rows_total, "batches": num_batches, "rows_per_batch": rows_total // num_batches,
+                   "parallelism": f"batches round-robin over {world} GPU(s), NCCL merge of the per-GPU group tables" if world > 1 else "1 GPU",
+                   "l2": f"inputs ({WL['bytes_per_row'] * (rows_total // num_batches) / 1e9:.2f} GB per batch) larger than the 126 MB L2; no flush needed",
+                   "zone_maps": "off" if args.no_zone_maps else "per-batch column min/max produced by the engine (ComputeColumnRanges, once per "
+                                "resident batch) and passed as BatchPlan.Ranges (direct-indexed aggregation where every dimension is bounded)",
+                   "zone_map_ms_per_batch": zone_map_ms},
+        "gpu_launches": main["gpu_launches"],
+        "roofline": roof, "roofline_nozm": (subs.get("cfg3_nozm") or {}).get("roofline"),
+        "e2e": main.get("e2e"), "cpu_baseline": cpu, "clocks": clocks, "workloads": subs or None,
     }
     os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
+
+
+PEAK, PEAK_SRC = 6650.0, "fallback 6650 GB/s"
+
+
+def _load_peak():
+    global PEAK, PEAK_SRC
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        PEAK, PEAK_SRC = float(peaks["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy bandwidth; the kernel is timed alone)"
+    except Exception:
+        pass
 
 
 def reference_run(args):
@@ -441,7 +669,8 @@ def reference_run(args):
            "data": "synthetic", "config": {"workload": WL["desc"], "rows": r["cores"] * args.cpu_rows,
                                            "note": "bounded sample of the workload; CPU throughput is size-independent"},
            "cpu_baseline": {"value": r["value"], "unit": "rows/s", "kind": r["kind"], "cores": r["cores"],
-                            "host_cores": r["host_cores"], "sample": r["sample"]},
+                            "host_cores": r["host_cores"], "physical_cores": r["physical_cores"],
+                            "single_core_rows_per_s": r["single_core_rows_per_s"], "step_ms": r["step_ms"], "sample": r["sample"]},
            "e2e": {"value": r["value"], "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
     print(json.dumps(out))
@@ -456,15 +685,18 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=sorted(WORKLOADS),
                     help="cfg3 (default) is the headline; the others are the remaining BASELINE configs")
     ap.add_argument("--rows", type=int, default=0, help="override the workload's table size")
-    ap.add_argument("--cpu-rows", type=int, default=2_000_000, help="rows per CPU worker per step (baseline sample)")
+    ap.add_argument("--cpu-rows", type=int, default=4_000_000, help="rows per CPU worker per step (baseline sample)")
     ap.add_argument("--profile-range", action="store_true",
                     help="bracket the device-resident steps (warm-up included) with cudaProfilerStart/Stop for ncu")
     ap.add_argument("--no-zone-maps", action="store_true",
                     help="do not pass the per-batch column min/max (BatchPlan.Ranges): hash-table aggregation only")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-sub", action="store_true", help="N = 1: skip the sub-results of the other BASELINE configs")
+    ap.add_argument("--no-zipf", action="store_true", help="skip the Zipf-city sub-result (a second 11.5 GB table)")
     args = ap.parse_args()
     select_workload(args.workload)
+    _load_peak()
     if args.impl == "reference":
         reference_run(args)
     else:

@@ -165,6 +165,15 @@ CGoCallResHandle AggStateFinalizeHLL(void *state, uint8_t **dimValuesPtr, uint8_
                                      size_t *hllVectorSizePtr, uint16_t **hllDimRegIDCountPtr,
                                      void *cudaStream, int device);
 
+/* Zone-map production: out[i] = min / max of the VALID values of columns[i] (at most 16 per call; Bool / 1- / 2- /
+ * 4-byte integer and Float32 columns in modes 0-3; everything else, columns without a valid value, and columns whose
+ * values the ColumnRange contract cannot describe — negative, >= 2^31, negative or non-finite floats — get Known = 0).
+ * One kernel over all columns, called once when a batch becomes device resident; the result is what BatchPlan.Ranges
+ * takes.  The reference keeps this pair only for live Uint32 vector parties (memstore/live_vector_party.go:74-75).
+ * res = number of columns scanned.  Synchronises cudaStream. */
+CGoCallResHandle ComputeColumnRanges(const VectorPartySlice *columns, int numColumns, ColumnRange *out,
+                                     void *cudaStream, int device);
+
 /* Empties the table, keeping its memory. */
 CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device);
 
