@@ -338,6 +338,8 @@ _PLAN_SIGS = {
                             _VP, C.c_int],
     "AggStateReset": [_VP, _VP, C.c_int],
     "AggStateDestroy": [_VP, C.c_int],
+    "AggStateExportPart": [_VP, _VP, C.c_int, C.c_size_t, C.c_size_t, _VP, C.c_int],
+    "AggStateMergeParts": [_VP, _VP, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, _VP, C.c_int],
     "ComputeColumnRanges": [C.POINTER(VectorPartySlice), C.c_int, C.POINTER(ColumnRange), _VP, C.c_int],
 }
 _MEM_SIGS = {

@@ -26,6 +26,7 @@
 #include "plan_device.cuh"
 #include "radix_sort.cuh"
 #include "scan.cuh"
+#include "small_sort.cuh"
 
 namespace aresb {
 
@@ -42,6 +43,8 @@ int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *mea
 // 4-row vector evaluation
 // ---------------------------------------------------------------------------------------
 constexpr int R = 4;  // rows per quad
+// status word of the single-launch finalize / of an exchange part
+enum SmallFinalizeStatus : uint32_t { SF_OK = 0, SF_TOO_MANY = 1, SF_TABLE_OVERFLOW = 2, SF_OUTPUT_TOO_SMALL = 3, SF_PART_TRUNCATED = 4 };
 
 __device__ __forceinline__ void cvtVec(uint32_t (&v)[R], ValClass from, ValClass to) {
   if (from == to) return;
@@ -491,6 +494,35 @@ mergeRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint8_t *_
   }
 }
 
+// Exchange step of a sharded query, receiving side: all N gathered parts ([groups, status, rows | dimension block of
+// `L.capacity` rows | measures]) are folded by ONE launch; the row counts are read from the parts' headers on the
+// device, so the host never waits for them.  A part whose sender could not fit its rows raises counters[2].
+__global__ void __launch_bounds__(256)
+mergePartsKernel(const uint8_t *__restrict__ parts, int numParts, size_t partStride, size_t dimOff, size_t valOff, DimLayout L,
+                 int width, AggOp op, uint8_t keyMode, uint8_t hashBits, int hll, DevTable G) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (int p = 0; p < numParts; p++) {
+    const uint8_t *part = parts + (size_t)p * partStride;
+    const uint32_t *hdr = reinterpret_cast<const uint32_t *>(part);
+    if (hdr[1] != SF_OK) {
+      if (blockIdx.x == 0 && threadIdx.x == 0) atomicExch(&G.counters[2], 1u);
+      continue;
+    }
+    const uint32_t n = hdr[0];
+    const uint8_t *block = part + dimOff, *measures = part + valOff;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      uint64_t w[4];
+      packRow(block, L, i, w);
+      unsigned long long key = keyMode == KEY_PACKED ? w[0]
+                             : (hashBits == 64 ? murmur3_128_lo(w, L.rowBytes, 0) : (unsigned long long)murmur3_32(w, L.rowBytes, 0));
+      const uint64_t v = loadMeasure(measures, i, width);
+      if (hll == 2) { hllDenseUpdate(G, nullptr, key, keyMode == KEY_HASHED ? w : nullptr, (uint32_t)v); continue; }
+      if (hll == 1) key = (key & 0xFFFFFFFFFFFF0000ull) | (v & 0x3FFFu);
+      globalUpdate(G, op, key, keyMode == KEY_HASHED ? w : nullptr, v);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------
 // dense HLL mode: registers -> the carried (key, value) rows of query/hll.cu, already in key order
 // ---------------------------------------------------------------------------------------
@@ -680,6 +712,143 @@ denseFoldKernel(unsigned long long *__restrict__ acc, DenseFold F, DevTable G) {
 }
 
 // ---------------------------------------------------------------------------------------
+// single-launch finalize for results of up to kSmallFinalizeMax groups
+// ---------------------------------------------------------------------------------------
+// One CTA walks the claim list (no table scan, no compaction), hashes each group's packed row with the reference's
+// murmur3, sorts the (hash, claim ordinal) pairs (smallSortBody), merges runs of equal hashes with the aggregate's
+// rule — the member claimed first names the run — and writes the reference's DimensionVector block + measure vector.
+// The group count goes to a mapped pinned host word, so the host's only interaction is one stream synchronise.
+// `ordered == 0` is the exchange form (AggStateExport): the claimed slots as they are, no sort, no merge.
+constexpr int kSmallFinalizeMax = kSmallSortMax;
+
+struct SmallFinalizeArgs {
+  DevTable G;
+  DimLayout L;              // output block layout (capacity = outputKeys.VectorCapacity)
+  uint64_t hashMask;
+  uint64_t *hashA, *tmpK;   // scratch: kSmallFinalizeMax entries each
+  uint32_t *idxA, *tmpI;
+  uint8_t *outBlock, *outValues;
+  uint64_t *outHash;
+  uint32_t *outIndex;
+  uint32_t *resultDev;      // [0] groups, [1] status, [2] claimed slots
+  volatile uint32_t *resultHost;
+  int32_t rowBytes, width, outCapacity;
+  uint8_t keyMode, hashBits, op, plusZero, ordered;
+};
+
+__global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constant__ SmallFinalizeArgs A) {
+  __shared__ uint32_t cnt[kSmallBuckets], off[kSmallBuckets + 1];
+  __shared__ uint32_t sWarp[1024 / 32 + 1];
+  const DevTable &G = A.G;
+  const uint32_t n = G.counters[0];
+  uint32_t status = SF_OK;
+  if (G.counters[1]) status = SF_TABLE_OVERFLOW;
+  else if (G.counters[2]) status = SF_PART_TRUNCATED;   // AggStateMergeParts met a part that did not hold all its rows
+  else if (n > (uint32_t)kSmallFinalizeMax) status = SF_TOO_MANY;
+  else if (!A.ordered && n > (uint32_t)A.outCapacity) status = SF_OUTPUT_TOO_SMALL;
+  if (status != SF_OK || n == 0) {
+    if (threadIdx.x == 0) {
+      A.resultDev[0] = 0; A.resultDev[1] = status; A.resultDev[2] = n;
+      A.resultHost[0] = 0; A.resultHost[1] = status; A.resultHost[2] = n;
+    }
+    return;
+  }
+  auto rowOf = [&](uint32_t slot, uint64_t (&w)[4]) {
+    if (A.keyMode == KEY_PACKED) { w[0] = G.keys[slot]; w[1] = w[2] = w[3] = 0; }
+    else {
+#pragma unroll
+      for (int i = 0; i < 4; i++) w[i] = G.rows[(size_t)slot * 4 + i];
+    }
+  };
+  if (!A.ordered) {
+    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+      const uint32_t slot = G.claimed[i];
+      uint64_t w[4];
+      rowOf(slot, w);
+      unpackRow(A.outBlock, A.L, i, w);
+      storeMeasure(A.outValues, i, A.width, G.acc[slot]);
+      if (A.outIndex) A.outIndex[i] = i;
+    }
+    if (threadIdx.x == 0) {
+      A.resultDev[0] = n; A.resultDev[1] = SF_OK; A.resultDev[2] = n;
+      A.resultHost[0] = n; A.resultHost[1] = SF_OK; A.resultHost[2] = n;
+    }
+    return;
+  }
+  // 1. (reference hash of the group's row, claim ordinal)
+  for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+    const unsigned long long key = G.keys[G.claimed[i]];
+    uint64_t h;
+    if (A.keyMode == KEY_PACKED) {
+      uint64_t w[4] = {key, 0, 0, 0};
+      h = A.hashBits == 64 ? murmur3_128_lo(w, A.rowBytes, 0) & A.hashMask : (uint64_t)murmur3_32(w, A.rowBytes, 0);
+    } else {
+      h = A.hashBits == 64 ? key & A.hashMask : key;
+    }
+    A.hashA[i] = h;
+    A.idxA[i] = i;
+  }
+  __syncthreads();
+  // 2. sort by (hash, ordinal)
+  smallSortBody(A.hashA, A.idxA, A.tmpK, A.tmpI, (int)n, A.hashBits - kSmallBits, cnt, off, sWarp);
+  // 3. runs of equal hashes: every thread owns a contiguous chunk, counts the run heads in it ...
+  const uint32_t per = (n + 1023) / 1024;
+  const uint32_t begin = threadIdx.x * per < n ? threadIdx.x * per : n, end = begin + per < n ? begin + per : n;
+  uint32_t heads = 0;
+  for (uint32_t j = begin; j < end; j++) heads += j == 0 || A.hashA[j] != A.hashA[j - 1];
+  uint32_t g;
+  uint32_t pos = blockExclusiveScan<1024>(heads, sWarp, &g);
+  if (g > (uint32_t)A.outCapacity) {
+    if (threadIdx.x == 0) {
+      A.resultDev[0] = 0; A.resultDev[1] = SF_OUTPUT_TOO_SMALL; A.resultDev[2] = g;
+      A.resultHost[0] = 0; A.resultHost[1] = SF_OUTPUT_TOO_SMALL; A.resultHost[2] = g;
+    }
+    return;
+  }
+  // ... 4. and folds + emits the runs that start in its chunk (a run may extend into the next chunks)
+  for (uint32_t j = begin; j < end; j++) {
+    const uint64_t h = A.hashA[j];
+    if (!(j == 0 || h != A.hashA[j - 1])) continue;
+    const uint32_t slot = G.claimed[A.idxA[j]];
+    uint64_t acc = G.acc[slot];
+    for (uint32_t k = j + 1; k < n && A.hashA[k] == h; k++) acc = aggCombine((AggOp)A.op, acc, G.acc[G.claimed[A.idxA[k]]]);
+    if (A.plusZero) {   // hash-reduce float sums start from +0.0 (see finalize())
+      if (A.width == 8) acc = (uint64_t)__double_as_longlong(__longlong_as_double((long long)acc) + 0.0);
+      else acc = __float_as_uint(__uint_as_float((uint32_t)acc) + 0.0f);
+    }
+    uint64_t w[4];
+    rowOf(slot, w);
+    unpackRow(A.outBlock, A.L, pos, w);
+    storeMeasure(A.outValues, pos, A.width, acc);
+    if (A.outHash) A.outHash[pos] = h;
+    if (A.outIndex) A.outIndex[pos] = pos;
+    pos++;
+  }
+  if (threadIdx.x == 0) {
+    A.resultDev[0] = g; A.resultDev[1] = SF_OK; A.resultDev[2] = n;
+    A.resultHost[0] = g; A.resultHost[1] = SF_OK; A.resultHost[2] = n;
+  }
+}
+
+// AggStateReset: only the claimed slots are emptied (and, for dense HLL states, only their register arrays).
+__global__ void __launch_bounds__(256)
+resetClaimedKernel(DevTable G, unsigned long long neutral) {
+  const uint32_t n = G.counters[0];
+  if (G.regs != nullptr) {   // one CTA per claimed group at a time: 16384 registers
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+      uint4 *r = reinterpret_cast<uint4 *>(G.regs + (size_t)G.claimed[i] * kHllRegisters);
+      for (uint32_t k = threadIdx.x; k < kHllRegisters / 4; k += blockDim.x) r[k] = make_uint4(0, 0, 0, 0);
+    }
+  }
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t slot = G.claimed[i];
+    G.keys[slot] = kEmptyKey;
+    G.acc[slot] = neutral;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 struct AggState {
@@ -699,6 +868,10 @@ struct AggState {
   void *mem;               // single allocation behind the table
   unsigned long long *ctaAcc;  // [kMaxGridCtas][8192] private accumulator slices of the fused kernel's CTAs
   unsigned long long *denseAcc = nullptr;  // [kGlobalDenseMaxSlots] shared accumulators of the global dense form (lazy)
+  uint8_t *smallScratch = nullptr;         // single-launch finalize: hash / index ping-pong arrays (in `mem`)
+  uint32_t *resultDev = nullptr;           // [0] groups, [1] status, [2] claimed slots of the last single-launch finalize
+  uint32_t *resultHost = nullptr;          // the same three words in mapped pinned host memory
+  uint32_t *resultHostDev = nullptr;       // device alias of resultHost
 };
 
 constexpr uint32_t kHllDenseMaxGroups = 4096;   // dense HLL: directory of 8192 slots, 64 KB of registers per slot
@@ -732,7 +905,9 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   const bool rows = st->keyMode == KEY_HASHED;
   const size_t ctaAccBytes = (size_t)kMaxGridCtas * 8192 * sizeof(unsigned long long);
   const size_t regBytes = st->hllDense ? cap * kHllRegisters * sizeof(uint32_t) : 0;
-  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes + regBytes;
+  const size_t claimedBytes = (cap * 4 + 255) / 256 * 256;
+  const size_t smallBytes = (size_t)kSmallFinalizeMax * (8 + 8 + 4 + 4);
+  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes + regBytes + claimedBytes + smallBytes;
   void *mem = nullptr;
   CGoCallResHandle h = deviceMalloc(&mem, bytes);
   if (h.pStrErr) { std::string m(h.pStrErr); free((void *)h.pStrErr); throw EngineError(m); }
@@ -746,6 +921,15 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   st->ctaAcc = reinterpret_cast<unsigned long long *>(p + 256 + cap * 16 + (rows ? cap * 32 : 0));
   st->table.mask = (uint32_t)(cap - 1);
   st->table.regs = st->hllDense ? reinterpret_cast<uint32_t *>(p + 256 + cap * 16 + (rows ? cap * 32 : 0) + ctaAccBytes) : nullptr;
+  uint8_t *tail = p + 256 + cap * 16 + (rows ? cap * 32 : 0) + ctaAccBytes + regBytes;
+  st->table.claimed = reinterpret_cast<uint32_t *>(tail);
+  st->smallScratch = tail + claimedBytes;
+  st->resultDev = st->table.counters + 8;   // inside the 256-byte header
+  if (!st->resultHost) {
+    ARES_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&st->resultHost), 64, cudaHostAllocMapped));
+    ARES_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&st->resultHostDev), st->resultHost, 0));
+    memset(st->resultHost, 0, 64);
+  }
   if (st->hllDense) ARES_CUDA(cudaMemsetAsync(st->table.regs, 0, regBytes, s));
   ARES_CUDA(cudaMemsetAsync(p, 0, 256, s));
   fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, cap, st->accNeutral);
@@ -1353,10 +1537,38 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
     ARES_CUDA(cudaStreamSynchronize(s));
     return dc.entries;
   }
+  const int width = st->measWidth;
+  const bool plusZero = st->spec.ReduceMode == ARES_REDUCE_HASH && (st->op == OP_SUM_F64 || st->op == OP_SUM_F32);
+  if (st->spec.ExpectedGroups <= (uint32_t)kSmallFinalizeMax && out.VectorCapacity > 0) {
+    // results of up to 32768 groups: ONE launch (claim list -> hash -> sort -> merge -> emit) and ONE synchronise;
+    // the group count comes back through mapped pinned memory
+    SmallFinalizeArgs A;
+    memset(&A, 0, sizeof(A));
+    A.G = st->table;
+    A.L = makeDimLayout(out.NumDimsPerDimWidth, out.VectorCapacity);
+    A.hashMask = testHash64Mask();
+    A.hashA = reinterpret_cast<uint64_t *>(st->smallScratch);
+    A.tmpK = A.hashA + kSmallFinalizeMax;
+    A.idxA = reinterpret_cast<uint32_t *>(A.tmpK + kSmallFinalizeMax);
+    A.tmpI = A.idxA + kSmallFinalizeMax;
+    A.outBlock = out.DimValues; A.outValues = outValues;
+    A.outHash = ordered ? out.HashValues : nullptr; A.outIndex = out.IndexVector;
+    A.resultDev = st->resultDev; A.resultHost = st->resultHostDev;
+    A.rowBytes = st->rowLayout.rowBytes; A.width = width; A.outCapacity = out.VectorCapacity;
+    A.keyMode = st->keyMode; A.hashBits = (uint8_t)st->hashBits; A.op = st->op; A.plusZero = plusZero; A.ordered = ordered;
+    finalizeSmallKernel<<<1, 1024, 0, s>>>(A);
+    checkLastError("finalizeSmall");
+    ARES_CUDA(cudaStreamSynchronize(s));
+    const uint32_t status = st->resultHost[1];
+    if (status == SF_OK) return st->resultHost[0];
+    if (status == SF_TABLE_OVERFLOW) { const uint32_t c[2] = {st->resultHost[2], 1}; checkOverflow(st, c); }
+    if (status == SF_OUTPUT_TOO_SMALL) throw EngineError("output DimensionVector capacity is smaller than the number of groups");
+    if (status == SF_PART_TRUNCATED) throw EngineError("exchange part truncated: a rank held more rows than the fixed part carries; repeat the exchange with exact sizes");
+    // SF_TOO_MANY: more groups than one CTA sorts — the multi-launch path below
+  }
   const int64_t occupied = groupCount(st, s);
   if (occupied == 0) return 0;
   const int n = (int)occupied;
-  const int width = st->measWidth;
   // 1. compact occupied slots (table order) with their reference hash and accumulator
   const int tiles = divUp((int64_t)st->capacity, kCmpTile);
   Scratch state(scanStateBytes(tiles) + sizeof(uint32_t), s);
@@ -1396,7 +1608,7 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
   emitGroupsKernel<<<blocks, 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), rep.as<uint32_t>(), (uint32_t)g,
                                           out.DimValues, L, out.IndexVector);
   checkLastError("emitGroups");
-  if (st->spec.ReduceMode == ARES_REDUCE_HASH && (st->op == OP_SUM_F64 || st->op == OP_SUM_F32)) {
+  if (plusZero) {
     // The reference's hash map folds every value into a slot that starts at the identity +0.0
     // (query/hash_reduction.cu:246-249 + the map's unused element), so a group whose values are all -0.0 ends
     // at +0.0 there, while its sort-reduce (and this table, whose neutral element is -0.0) keeps -0.0.
@@ -1528,6 +1740,46 @@ CGoCallResHandle AggStateExport(void *state, DimensionVector outputKeys, uint8_t
   });
 }
 
+// Exchange form without host involvement (sharded queries): the claimed slots go to `part` = [uint32 rows, status,
+// claimed | ... | dimension block of capRows rows at dimOffset | measures at valuesOffset]; nothing is synchronised and
+// the row count stays on the device.  More rows than capRows (or than one CTA handles): status != 0, no rows.
+CGoCallResHandle AggStateExportPart(void *state, uint8_t *part, int capRows, size_t dimOffset, size_t valuesOffset,
+                                    void *cudaStream, int device) {
+  return guarded("AggStateExportPart", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    if (st->hll) throw EngineError("AggStateExportPart: HLL states exchange through AggStateExport");
+    if (capRows <= 0 || capRows > kSmallFinalizeMax) throw EngineError("AggStateExportPart: capRows must be in [1, 32768]");
+    SmallFinalizeArgs A;
+    memset(&A, 0, sizeof(A));
+    A.G = st->table;
+    A.L = makeDimLayout(st->spec.NumDimsPerDimWidth, capRows);
+    A.hashMask = ~0ull;
+    A.outBlock = part + dimOffset; A.outValues = part + valuesOffset;
+    A.resultDev = reinterpret_cast<uint32_t *>(part); A.resultHost = st->resultHostDev + 4;   // host copy unused
+    A.rowBytes = st->rowLayout.rowBytes; A.width = st->measWidth; A.outCapacity = capRows;
+    A.keyMode = st->keyMode; A.hashBits = (uint8_t)st->hashBits; A.op = st->op; A.plusZero = 0; A.ordered = 0;
+    finalizeSmallKernel<<<1, 1024, 0, (cudaStream_t)cudaStream>>>(A);
+    checkLastError("AggStateExportPart");
+    return 0;
+  });
+}
+
+// Receiving side: folds `numParts` parts laid out `partStride` bytes apart (as all_gather leaves them) into `state` with
+// one launch; asynchronous.  A truncated part is reported by the next AggStateFinalize ("exchange part truncated").
+CGoCallResHandle AggStateMergeParts(void *state, const uint8_t *parts, int numParts, size_t partStride, int capRows,
+                                    size_t dimOffset, size_t valuesOffset, void *cudaStream, int device) {
+  return guarded("AggStateMergeParts", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    if (numParts <= 0) return 0;
+    DimLayout L = makeDimLayout(st->spec.NumDimsPerDimWidth, capRows);
+    mergePartsKernel<<<smCount() * 2, 256, 0, (cudaStream_t)cudaStream>>>(parts, numParts, partStride, dimOffset, valuesOffset, L,
+                                                                         st->measWidth, st->op, st->keyMode, (uint8_t)st->hashBits,
+                                                                         st->hll ? (st->hllDense ? 2 : 1) : 0, st->table);
+    checkLastError("AggStateMergeParts");
+    return 0;
+  });
+}
+
 CGoCallResHandle AggStateFinalizeHLL(void *state, uint8_t **dimValuesPtr, uint8_t **hllVectorPtr, size_t *hllVectorSizePtr,
                                      uint16_t **hllDimRegIDCountPtr, void *cudaStream, int device) {
   return guarded("AggStateFinalizeHLL", device, [&]() -> int64_t {
@@ -1540,10 +1792,11 @@ CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device) {
   return guarded("AggStateReset", device, [&]() -> int64_t {
     AggState *st = asState(state);
     cudaStream_t s = (cudaStream_t)cudaStream;
-    ARES_CUDA(cudaMemsetAsync(st->table.counters, 0, 256, s));
-    if (st->hllDense) ARES_CUDA(cudaMemsetAsync(st->table.regs, 0, st->capacity * kHllRegisters * sizeof(uint32_t), s));
-    fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, st->capacity, st->accNeutral);
+    // only what was claimed is emptied (claim list): a 2^21-slot table with 19,200 groups resets 0.3 MB, not 32 MB,
+    // and a dense HLL state clears the register arrays of its groups, not all 512 MB
+    resetClaimedKernel<<<smCount() * 4, 256, 0, s>>>(st->table, st->accNeutral);
     checkLastError("AggStateReset");
+    ARES_CUDA(cudaMemsetAsync(st->table.counters, 0, 256, s));
     return 0;
   });
 }
@@ -1576,6 +1829,7 @@ CGoCallResHandle AggStateDestroy(void *state, int device) {
   return guarded("AggStateDestroy", device, [&]() -> int64_t {
     AggState *st = asState(state);
     if (st->mem) deviceFree(st->mem);
+    if (st->resultHost) cudaFreeHost(st->resultHost);
     if (st->denseAcc) deviceFree(st->denseAcc);
     delete st;
     return 0;

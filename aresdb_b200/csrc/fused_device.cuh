@@ -18,6 +18,8 @@ struct DevTable {
   unsigned long long *acc;
   uint64_t *rows;        // [capacity][4] packed rows, wide (hashed) keys only
   uint32_t *counters;    // [0] occupied slots, [1] overflow flag
+  uint32_t *claimed;     // [capacity] slot index of the i-th claimed group (claim order): finalize / reset / export
+                         // walk this list instead of scanning the table
   uint32_t mask;
   uint32_t *regs;        // dense HLL mode: [capacity][16384] registers, value + 1 (0 = never hit); else null
 };
@@ -79,7 +81,7 @@ static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, uns
     if (k == kEmptyKey) {
       unsigned long long old = atomicCAS(&G.keys[slot], kEmptyKey, key);
       if (old == kEmptyKey) {
-        atomicAdd(&G.counters[0], 1u);
+        G.claimed[atomicAdd(&G.counters[0], 1u)] = slot;   // every slot is claimed once: the ordinal is < capacity
         if (roww != nullptr && G.rows != nullptr) {
 #pragma unroll
           for (int i = 0; i < 4; i++) G.rows[(size_t)slot * 4 + i] = roww[i];
@@ -105,8 +107,9 @@ __device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsign
 // registers in G.regs.  `mirror` (optional) is a shared-memory copy of G.keys with the same
 // geometry, filled on demand, so that steady-state lookups never leave the SM.
 // ---------------------------------------------------------------------------------------
-__device__ __forceinline__ void hllDenseUpdate(const DevTable &G, unsigned long long *mirror, unsigned long long key,
-                                               const uint64_t *roww, uint32_t value) {
+// Directory slot of `key` (claimed on first sight), 0xFFFFFFFF when the directory is full.
+__device__ __forceinline__ uint32_t hllDenseLocate(const DevTable &G, unsigned long long *mirror, unsigned long long key,
+                                                   const uint64_t *roww) {
   uint32_t slot = globalHome(G, key);
   bool found = false;
   if (mirror != nullptr) {
@@ -121,7 +124,7 @@ __device__ __forceinline__ void hllDenseUpdate(const DevTable &G, unsigned long 
   if (!found) {
     const uint32_t home = globalHome(G, key);
     slot = globalFindOrClaim(G, key, roww);
-    if (slot == 0xFFFFFFFFu) return;      // directory full: flagged in G.counters[1], reported at finalize
+    if (slot == 0xFFFFFFFFu) return slot;  // directory full: flagged in G.counters[1], reported at finalize
     if (mirror != nullptr) {
       // every directory slot from the key's home up to where it lives is occupied (linear probing):
       // copy them so that the next probe sequence reaches the key without leaving shared memory
@@ -131,7 +134,21 @@ __device__ __forceinline__ void hllDenseUpdate(const DevTable &G, unsigned long 
       }
     }
   }
-  atomicMax(&G.regs[(size_t)slot * kHllRegisters + (value & (kHllRegisters - 1))], value + 1u);
+  return slot;
+}
+
+// Register update: registers only grow, so a (possibly stale) plain read that already shows a value >= ours makes the
+// atomic unnecessary — after the first few thousand rows of a group that is the common case (a register sees a new
+// maximum H(n) ~ ln n times in n rows), and an L2 read is far cheaper than an L2 atomic.
+__device__ __forceinline__ void hllRegisterMax(uint32_t *reg, uint32_t want) {
+  if (__ldcg(reg) < want) atomicMax(reg, want);
+}
+
+__device__ __forceinline__ void hllDenseUpdate(const DevTable &G, unsigned long long *mirror, unsigned long long key,
+                                               const uint64_t *roww, uint32_t value) {
+  const uint32_t slot = hllDenseLocate(G, mirror, key, roww);
+  if (slot == 0xFFFFFFFFu) return;
+  hllRegisterMax(&G.regs[(size_t)slot * kHllRegisters + (value & (kHllRegisters - 1))], value + 1u);
 }
 
 // ---------------------------------------------------------------------------------------

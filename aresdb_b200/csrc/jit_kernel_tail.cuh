@@ -190,12 +190,22 @@ __device__ __forceinline__ void jitAggregate(const SmemTable &T, const JitParams
                                              bool bypass, uint32_t *misses) {
   constexpr AggOp op = (AggOp)JIT_AGG_OP;
   if (JIT_HLL == 2) {  // dense registers: the shared table mirrors the directory of groups
+    // locate the four registers, read them back to back (the latencies overlap), then raise only those that grow
+    uint32_t *reg[4];
+    uint32_t cur[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
+      reg[r] = nullptr;
       if (!((alive >> r) & 1)) continue;
-      hllDenseUpdate(P.G, JIT_SMEM_SLOTS == JIT_DENSE_SLOTS ? T.keys : nullptr, jitKeyOf(key, meas, r),
-                     JIT_KW == 1 ? nullptr : key[r], (uint32_t)meas[r]);
+      const uint32_t slot = hllDenseLocate(P.G, JIT_SMEM_SLOTS == JIT_DENSE_SLOTS ? T.keys : nullptr, jitKeyOf(key, meas, r),
+                                           JIT_KW == 1 ? nullptr : key[r]);
+      if (slot != 0xFFFFFFFFu) reg[r] = &P.G.regs[(size_t)slot * kHllRegisters + ((uint32_t)meas[r] & (kHllRegisters - 1))];
     }
+#pragma unroll
+    for (int r = 0; r < 4; r++) cur[r] = reg[r] ? __ldcg(reg[r]) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (cur[r] < (uint32_t)meas[r] + 1u) atomicMax(reg[r], (uint32_t)meas[r] + 1u);
     return;
   }
   if (JIT_BYPASS && bypass) {

@@ -278,6 +278,7 @@ class FusedBatchExecutor:
             self._plan.Insts[i] = pi
         self.calls = 0
         self.skipped = 0   # batches whose zone map contradicts a filter (skipping.py): never launched
+        self.expected_groups = expected_groups
 
     def process_batch(self, batch: Batch, stream=None):
         if should_skip_batch(self.q, batch.ranges):
@@ -298,6 +299,8 @@ class FusedBatchExecutor:
         self.lib.ExecuteBatchPlan(self.state, C.byref(p), self.space.stream if stream is None else stream,
                                   self.space.device)
 
+    SMALL_RESULT = 32768   # kSmallFinalizeMax of the engine
+
     def merge(self, dim_vector: A.DimensionVector, measures_ptr: int, length: int):
         self.lib.AggStateMerge(self.state, dim_vector, measures_ptr, length, self.space.stream, self.space.device)
 
@@ -306,11 +309,20 @@ class FusedBatchExecutor:
 
     def finalize_into(self, capacity: int | None = None):
         """Returns (groups, _ResultBuffers) with the result left in device memory."""
-        cap = max(capacity if capacity is not None else self.group_count(), 1)
-        out = _ResultBuffers(self.space, self.q, cap, zero=not getattr(self.space, "is_cuda", False))
-        g = self.lib.AggStateFinalize(self.state, out.dimension_vector(self.q), out.measures.ptr, self.space.stream,
-                                      self.space.device)
-        return g, out
+        # Results of up to SMALL_RESULT groups need no count first: AggStateFinalize is one launch + one synchronise
+        # and reports a too-small output as an error, after which the exact count is asked for.
+        guess = capacity is None and self.expected_groups <= self.SMALL_RESULT and not self.q.is_hll
+        cap = self.SMALL_RESULT if guess else max(capacity if capacity is not None else self.group_count(), 1)
+        for attempt in (0, 1):
+            out = _ResultBuffers(self.space, self.q, cap, zero=not getattr(self.space, "is_cuda", False))
+            try:
+                g = self.lib.AggStateFinalize(self.state, out.dimension_vector(self.q), out.measures.ptr, self.space.stream,
+                                              self.space.device)
+                return g, out
+            except A.AresError as e:
+                if attempt or "capacity is smaller" not in str(e):
+                    raise
+                cap = max(self.group_count(), 1)
 
     def result(self) -> QueryResult:
         g, out = self.finalize_into()

@@ -61,11 +61,13 @@ class ShardedFusedQuery:
     def process_batch(self, batch, stream=None):
         self.local.process_batch(batch, stream)
 
-    EXCHANGE_ROWS = 65536
+    EXCHANGE_ROWS = 32768   # rows of a fixed part (= what the engine's single-launch export handles)
     _HDR = 64
 
     def _exchange_fixed(self):
-        """Returns the number of rows gathered, or None when some rank holds more than EXCHANGE_ROWS rows."""
+        """Device-only exchange: AggStateExportPart (one launch, the row count stays on the device) -> ONE all-gather of
+        the fixed parts -> AggStateMergeParts (one launch over all parts).  The host waits for nothing here; a rank with
+        more rows than a part holds marks its header and the merged state's finalize reports it (-> exact protocol)."""
         import torch
         q, sp, dist, lib = self.q, self.space, self.dist, self.lib
         cap = self._fixed_cap
@@ -75,31 +77,16 @@ class ShardedFusedQuery:
         if self._send is None:
             self._send = torch.zeros(part, dtype=torch.uint8, device=sp.dev)
             self._recv = torch.empty(self.world * part, dtype=torch.uint8, device=sp.dev)
-        send, recv = self._send, self._recv
-        base = send.data_ptr() + self._HDR
-        try:
-            dv = A.make_dimension_vector(base, None, None, q.num_dims_per_width, cap)
-            n = lib.AggStateExport(self.local.state, dv, base + dim_bytes, sp.stream, sp.device)
-        except A.AresError:
-            n = cap + 1   # more rows than the fixed part holds
-        send[:8].view(torch.int64).fill_(n)
-        dist.all_gather_into_tensor(recv, send)
-        counts = recv.view(self.world, part)[:, :8].contiguous().view(torch.int64).flatten().tolist()
-        if max(counts) > cap:
-            return None
+        lib.AggStateExportPart(self.local.state, self._send.data_ptr(), cap, self._HDR, self._HDR + dim_bytes, sp.stream, sp.device)
+        dist.all_gather_into_tensor(self._recv, self._send)
         self.merged.reset()
-        rbase = recv.data_ptr()
-        for r in range(self.world):
-            if counts[r]:
-                dv = A.make_dimension_vector(rbase + r * part + self._HDR, None, None, q.num_dims_per_width, cap)
-                self.merged.merge(dv, rbase + r * part + self._HDR + dim_bytes, counts[r])
-        return int(sum(counts))
+        lib.AggStateMergeParts(self.merged.state, self._recv.data_ptr(), self.world, part, cap, self._HDR, self._HDR + dim_bytes,
+                               sp.stream, sp.device)
+        return self.world * cap
 
     def _exchange(self):
         if self._fixed_cap:
-            rows = self._exchange_fixed()
-            if rows is not None:
-                return rows
+            return self._exchange_fixed()
         return self._exchange_exact()
 
     def _exchange_exact(self):
@@ -137,7 +124,14 @@ class ShardedFusedQuery:
         """(groups, result buffers) of the WHOLE query, identical on every rank."""
         if self.world == 1:
             return self.local.finalize_into()
-        return self.merged.finalize_into(self._exchange())
+        if self._fixed_cap:
+            self._exchange_fixed()
+            try:
+                return self.merged.finalize_into()
+            except A.AresError as e:
+                if "exchange part truncated" not in str(e):
+                    raise
+        return self.merged.finalize_into(self._exchange_exact())
 
     def finalize_hll(self):
         """hll queries: the HLLResult of the WHOLE query, identical on every rank."""

@@ -153,6 +153,18 @@ CGoCallResHandle AggStateFinalize(void *state, DimensionVector outputKeys, uint8
 CGoCallResHandle AggStateExport(void *state, DimensionVector outputKeys, uint8_t *outputValues,
                                 void *cudaStream, int device);
 
+/* The exchange step of a sharded query without host involvement.  AggStateExportPart writes this state's rows as ONE
+ * fixed-capacity part — [uint32 rows, uint32 status, uint32 claimed, pad | DimensionVector block of capRows rows at
+ * dimOffset | measures at valuesOffset] — with one launch and no synchronisation (the row count stays on the device);
+ * the parts of all ranks are all-gathered; AggStateMergeParts folds every gathered part into the receiving state with one
+ * launch, reading the counts from the part headers.  capRows <= 32768.  A state with more rows marks its part
+ * (status != 0, no rows) and the receiver's next AggStateFinalize fails with "exchange part truncated": repeat the step
+ * with AggStateGroupCount / AggStateExport / AggStateMerge (exact sizes).  Not for AGGR_HLL states. */
+CGoCallResHandle AggStateExportPart(void *state, uint8_t *part, int capRows, size_t dimOffset, size_t valuesOffset,
+                                    void *cudaStream, int device);
+CGoCallResHandle AggStateMergeParts(void *state, const uint8_t *parts, int numParts, size_t partStride, int capRows,
+                                    size_t dimOffset, size_t valuesOffset, void *cudaStream, int device);
+
 /* AGGR_HLL states: the final outputs of the reference's last-batch HyperLogLog call
  * (query/hll.cu:262-290, adopted by query/time_series_aggregate.go:661-681).  res = number of dimension
  * groups g.  *dimValuesPtr = a DimensionVector block of VectorCapacity g (groups in key order),

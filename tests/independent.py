@@ -75,7 +75,10 @@ def hll_value(ts):
     reg = h & (HLL_REGS - 1)
     x = (h >> 14) & 0x3FFFF
     lsb = x & (-x)
-    rho = torch.where(x == 0, torch.full_like(x, 50), torch.log2(lsb.clamp(min=1).to(torch.float64)).to(torch.int64))
+    # count of trailing zeros = exponent of the (exactly representable) lowest set bit; no log2: its CUDA form is not
+    # exact on powers of two
+    ctz = (lsb.clamp(min=1).to(torch.float32).view(torch.int32) >> 23).to(torch.int64) - 127
+    rho = torch.where(x == 0, torch.full_like(x, 50), ctz)
     return reg, rho + 1
 
 

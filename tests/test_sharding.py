@@ -86,3 +86,51 @@ def test_agg_state_merge_on_device():
         merged.close()
         exp = T.run_legacy(orc, q, hbs)
         T.assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=name)
+
+
+@pytest.mark.gpu
+def test_export_part_merge_parts_on_device():
+    """The device-only exchange of a sharded query (AggStateExportPart -> [all-gather] -> AggStateMergeParts): two
+    states' parts laid out as an all-gather leaves them are folded by one launch; counts never visit the host.
+    A part that cannot hold its sender's rows is reported by the receiver's finalize."""
+    import torch
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import cabi as A
+    from aresdb_b200 import synth
+    from aresdb_b200.executor import FusedBatchExecutor, dim_offsets
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    hbs = [synth.generate_batch(d, 20000, num_cities=30) for d in range(4)]
+    dev = eng.space.dev
+    for name in ("cfg3_sum", "cfg3_count", "cfg4_hash", "min_city", "no_dims_wide"):
+        q = T.queries()[name]
+        exp = T.run_legacy(orc, q, hbs)
+        for cap in (32768, 64):
+            _, _, _, dim_bytes = dim_offsets(q.num_dims_per_width, cap)
+            dim_bytes = (dim_bytes + 15) // 16 * 16
+            part = (64 + dim_bytes + q.measure_bytes * cap + 63) // 64 * 64
+            recv = torch.zeros(2 * part, dtype=torch.uint8, device=dev)
+            keep = []
+            for r, half in enumerate((hbs[:2], hbs[2:])):
+                ex = FusedBatchExecutor(eng.lib, eng.space, q)
+                for hb in half:
+                    b = T.upload(eng, hb)
+                    keep.append(b)
+                    ex.process_batch(b)
+                eng.lib.AggStateExportPart(ex.state, recv.data_ptr() + r * part, cap, 64, 64 + dim_bytes, eng.space.stream, 0)
+                keep.append(ex)
+            merged = FusedBatchExecutor(eng.lib, eng.space, q)
+            eng.lib.AggStateMergeParts(merged.state, recv.data_ptr(), 2, part, cap, 64, 64 + dim_bytes, eng.space.stream, 0)
+            hdr = recv.view(2, part)[:, :12].contiguous().view(torch.int32).cpu().numpy()
+            if (hdr[:, 2] <= cap).all():
+                assert (hdr[:, 1] == 0).all() and (hdr[:, 0] == hdr[:, 2]).all()
+                got = merged.result()
+                T.assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"{name}/cap{cap}")
+            else:
+                assert (hdr[:, 1] != 0).any()
+                with pytest.raises(A.AresError, match="exchange part truncated"):
+                    merged.result()
+            merged.close()
+            for k in keep:
+                if isinstance(k, FusedBatchExecutor):
+                    k.close()
