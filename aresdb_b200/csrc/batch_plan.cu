@@ -636,6 +636,27 @@ compactGroupsKernel(DevTable G, size_t cap, uint8_t keyMode, uint8_t hashBits, u
   }
 }
 
+// Large results: the claim list replaces the table scan — slotOf / hash / vals of the n claimed groups, claim order.
+__global__ void __launch_bounds__(256)
+gatherClaimedKernel(DevTable G, uint32_t n, uint8_t keyMode, uint8_t hashBits, uint64_t hashMask, int rowBytes, int width,
+                    uint32_t *__restrict__ slotOf, uint64_t *__restrict__ hash, uint8_t *__restrict__ vals) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t slot = G.claimed[i];
+    const unsigned long long key = G.keys[slot];
+    uint64_t h;
+    if (keyMode == KEY_PACKED) {
+      uint64_t w[4] = {key, 0, 0, 0};
+      h = hashBits == 64 ? murmur3_128_lo(w, rowBytes, 0) : (uint64_t)murmur3_32(w, rowBytes, 0);
+    } else {
+      h = key;
+    }
+    slotOf[i] = slot;
+    hash[i] = hashBits == 64 ? h & hashMask : h;
+    storeMeasure(vals, i, width, G.acc[slot]);
+  }
+}
+
 __global__ void __launch_bounds__(256)
 emitGroupsKernel(DevTable G, uint8_t keyMode, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ repIndex,
                  uint32_t g, uint8_t *__restrict__ outBlock, DimLayout L, uint32_t *__restrict__ outIndex) {
@@ -1569,17 +1590,16 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
   const int64_t occupied = groupCount(st, s);
   if (occupied == 0) return 0;
   const int n = (int)occupied;
-  // 1. compact occupied slots (table order) with their reference hash and accumulator
-  const int tiles = divUp((int64_t)st->capacity, kCmpTile);
-  Scratch state(scanStateBytes(tiles) + sizeof(uint32_t), s);
-  ARES_CUDA(cudaMemsetAsync(state.ptr, 0, state.bytes, s));
-  ScanTileState sst = makeScanState(state.ptr, tiles);
-  uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
+  // 1. the claimed slots (claim order) with their reference hash and accumulator
   Scratch slotOf(sizeof(uint32_t) * (size_t)n, s), hash(sizeof(uint64_t) * (size_t)n, s), vals((size_t)width * n, s);
-  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, (uint8_t)st->hashBits, testHash64Mask(),
-                                                   st->rowLayout.rowBytes, width, sst, slotOf.as<uint32_t>(),
-                                                   hash.as<uint64_t>(), vals.as<uint8_t>(), dCount);
-  checkLastError("compactGroups");
+  {
+    int blocks = divUp(n, 256);
+    if (blocks > smCount() * 8) blocks = smCount() * 8;
+    gatherClaimedKernel<<<blocks, 256, 0, s>>>(st->table, (uint32_t)n, st->keyMode, (uint8_t)st->hashBits, testHash64Mask(),
+                                               st->rowLayout.rowBytes, width, slotOf.as<uint32_t>(), hash.as<uint64_t>(),
+                                               vals.as<uint8_t>());
+  }
+  checkLastError("gatherClaimed");
   // 2. sort the groups by hash (stable), 3. merge equal hashes (reference group identity)
   Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
   iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);

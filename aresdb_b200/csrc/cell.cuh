@@ -160,6 +160,15 @@ ARES_HD uint32_t weekStart(uint32_t ts) {
 // restatement can be validated against the reference's HOST build.
 ARES_HD uint32_t hllValueOfHash(uint64_t hashed, bool hostShift = false) {
   uint32_t group = (uint32_t)(hashed & 0x3FFF);
+#ifdef __CUDA_ARCH__
+  if (!hostShift) {
+    // CUDA semantics of the reference's int shift, closed form of the loop below: the lowest set bit among bits 14..31
+    // decides; none set: the loop runs to bit 64 (rho = 50)
+    const uint32_t x = (uint32_t)(hashed >> 14) & 0x3FFFFu;
+    const uint32_t r = x ? (uint32_t)__ffs((int)x) - 1u : 50u;
+    return (r << 16) | group;
+  }
+#endif
   uint32_t rho = 0;
   while (true) {
     uint32_t sh = rho + 14;

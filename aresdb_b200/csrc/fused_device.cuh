@@ -81,7 +81,12 @@ static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, uns
     if (k == kEmptyKey) {
       unsigned long long old = atomicCAS(&G.keys[slot], kEmptyKey, key);
       if (old == kEmptyKey) {
-        G.claimed[atomicAdd(&G.counters[0], 1u)] = slot;   // every slot is claimed once: the ordinal is < capacity
+        // claim ordinal: the lanes of the warp that claim in the same step share ONE add on the (single-address) counter
+        const uint32_t peers = __activemask(), lane = threadIdx.x & 31u, leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) base = atomicAdd(&G.counters[0], (uint32_t)__popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        G.claimed[base + __popc(peers & ((1u << lane) - 1u))] = slot;   // every slot is claimed once: the ordinal is < capacity
         if (roww != nullptr && G.rows != nullptr) {
 #pragma unroll
           for (int i = 0; i < 4; i++) G.rows[(size_t)slot * 4 + i] = roww[i];

@@ -44,21 +44,46 @@ digitHistogram(const uint64_t *__restrict__ keys, int n, int shift, int chunk, u
   hist[(size_t)threadIdx.x * gridDim.x + blockIdx.x] = sh[threadIdx.x];
 }
 
-// Exclusive scan of `m` counters in place (one block).
-__global__ void __launch_bounds__(1024) scanHistograms(uint32_t *hist, int m) {
+// Exclusive scan, in place, of the digit-major kRadix x G counter table (one block).  A warp owns digits w, w + 32, ...:
+// it first sums each of its digits over the G blocks (coalesced rows), the block scans the kRadix digit totals, and the
+// warp then walks its rows again turning counts into exclusive prefixes (32 blocks per step, warp scan + carry).
+// (The first version gave every thread a contiguous slice of the flattened table: uncoalesced, 137 us for 1.5e5 counters.)
+__global__ void __launch_bounds__(1024) scanHistograms(uint32_t *hist, int G) {
   __shared__ uint32_t sWarp[1024 / 32 + 1];
-  const int per = (m + 1023) / 1024;
-  const int begin = threadIdx.x * per;
-  int end = begin + per;
-  if (end > m) end = m;
-  uint32_t sum = 0;
-  for (int i = begin; i < end; i++) sum += hist[i];
-  uint32_t total;
-  uint32_t run = blockExclusiveScan<1024>(sum, sWarp, &total);
-  for (int i = begin; i < end; i++) {
-    uint32_t c = hist[i];
-    hist[i] = run;
-    run += c;
+  __shared__ uint32_t digitBase[kRadix];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int d = warp; d < kRadix; d += 32) {
+    const uint32_t *row = hist + (size_t)d * G;
+    uint32_t s = 0;
+    for (int b = lane; b < G; b += 32) s += row[b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) digitBase[d] = s;
+  }
+  __syncthreads();
+  {
+    uint32_t total;
+    const uint32_t v = threadIdx.x < kRadix ? digitBase[threadIdx.x] : 0u;
+    const uint32_t excl = blockExclusiveScan<1024>(v, sWarp, &total);
+    __syncthreads();
+    if (threadIdx.x < kRadix) digitBase[threadIdx.x] = excl;
+  }
+  __syncthreads();
+  for (int d = warp; d < kRadix; d += 32) {
+    uint32_t *row = hist + (size_t)d * G;
+    uint32_t carry = digitBase[d];
+    for (int b0 = 0; b0 < G; b0 += 32) {
+      const int b = b0 + lane;
+      const uint32_t c = b < G ? row[b] : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+      }
+      if (b < G) row[b] = carry + incl - c;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
   }
 }
 
@@ -166,7 +191,7 @@ void radixSortPairs(uint64_t *keys, V *vals, uint64_t *keysTmp, V *valsTmp, int 
   for (int p = 0; p < passes; p++) {
     int shift = beginBit + p * kRadixBits;
     digitHistogram<<<g.blocks, kSortThreads, 0, s>>>(kin, n, shift, g.chunk, hist.as<uint32_t>());
-    scanHistograms<<<1, 1024, 0, s>>>(hist.as<uint32_t>(), kRadix * g.blocks);
+    scanHistograms<<<1, 1024, 0, s>>>(hist.as<uint32_t>(), g.blocks);
     scatterByDigit<V><<<g.blocks, kSortThreads, 0, s>>>(kin, vin, kout, vout, n, shift, g.chunk, hist.as<uint32_t>());
     noteLaunches(2);
     checkLastError("radixSortPairs");

@@ -78,10 +78,13 @@ __global__ void __launch_bounds__(256)
 segmentReduceKernel(const uint32_t *__restrict__ index, const uint8_t *__restrict__ measures, int width, AggOp op,
                     const uint32_t *__restrict__ segStart, uint32_t g, uint32_t *__restrict__ outIndex,
                     uint8_t *__restrict__ outValues, uint32_t *__restrict__ longList, uint32_t *__restrict__ longCount,
-                    const uint64_t *__restrict__ hash, uint64_t *__restrict__ outHash) {
+                    const uint64_t *__restrict__ hash, uint64_t *__restrict__ outHash,
+                    const uint32_t *__restrict__ runList = nullptr, const uint32_t *__restrict__ runCount = nullptr) {
   const uint32_t lane = threadIdx.x & 31;
   const uint32_t warpsPerGrid = (gridDim.x * blockDim.x) >> 5;
-  for (uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; s < g; s += warpsPerGrid) {
+  if (runList != nullptr) g = *runCount;   // only the runs segmentReduceShortKernel left over
+  for (uint32_t q = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; q < g; q += warpsPerGrid) {
+    const uint32_t s = runList != nullptr ? runList[q] : q;
     const uint32_t begin = segStart[s], end = segStart[s + 1];
     if (outHash != nullptr && lane == 0) outHash[s] = hash[begin];
     if (end - begin > kLongRun) {
@@ -108,6 +111,27 @@ segmentReduceKernel(const uint32_t *__restrict__ index, const uint8_t *__restric
       outIndex[s] = index[begin];
       storeMeasure(outValues, s, width, acc);
     }
+  }
+}
+
+// Mostly-distinct hashes (g close to n, e.g. the 1.16e6 groups of cfg4 at finalize): one THREAD per run.  Runs of one or
+// two elements are finished here (for two elements the shuffle tree above is combine(first, second) as well); longer
+// runs are listed for the warp kernel.  (One warp per one-element run cost 404 us for 1.16e6 runs.)
+__global__ void __launch_bounds__(256)
+segmentReduceShortKernel(const uint32_t *__restrict__ index, const uint8_t *__restrict__ measures, int width, AggOp op,
+                         const uint32_t *__restrict__ segStart, uint32_t g, uint32_t *__restrict__ outIndex,
+                         uint8_t *__restrict__ outValues, uint32_t *__restrict__ runList, uint32_t *__restrict__ runCount,
+                         const uint64_t *__restrict__ hash, uint64_t *__restrict__ outHash) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < g; s += stride) {
+    const uint32_t begin = segStart[s], end = segStart[s + 1];
+    if (end - begin > 2) { runList[atomicAdd(runCount, 1u)] = s; continue; }
+    if (outHash != nullptr) outHash[s] = hash[begin];
+    const uint32_t first = index[begin];
+    uint64_t acc = loadMeasure(measures, first, width);
+    if (end - begin == 2) acc = aggCombine(op, acc, loadMeasure(measures, index[begin + 1], width));
+    outIndex[s] = first;
+    storeMeasure(outValues, s, width, acc);
   }
 }
 
@@ -179,7 +203,7 @@ int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *mea
                  int n, uint32_t *outIndex, uint8_t *outValues, cudaStream_t s, uint64_t *outHash = nullptr) {
   if (n <= 0) return 0;
   const int tiles = divUp(n, kHeadTile);
-  Scratch state(scanStateBytes(tiles) + 2 * sizeof(uint32_t), s);
+  Scratch state(scanStateBytes(tiles) + 4 * sizeof(uint32_t), s);
   ARES_CUDA(cudaMemsetAsync(state.ptr, 0, state.bytes, s));
   ScanTileState st = makeScanState(state.ptr, tiles);
   uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
@@ -192,10 +216,22 @@ int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *mea
   ARES_CUDA(cudaStreamSynchronize(s));
   const uint32_t maxLong = (uint32_t)(n / kLongRun) + 1;
   Scratch longList(sizeof(uint32_t) * maxLong, s);
-  segmentReduceKernel<<<gridFor((int64_t)g * 32, 256), 256, 0, s>>>(index, measures, width, op, segStart.as<uint32_t>(), g,
-                                                                   outIndex, outValues, longList.as<uint32_t>(), dLongCount,
-                                                                   hash, outHash);
-  checkLastError("segmentReduce");
+  if ((int64_t)g * 4 > n) {   // average run shorter than 4: thread per run, the few longer runs go to the warp kernel
+    uint32_t *dRunCount = dCount + 2;
+    Scratch runList(sizeof(uint32_t) * ((size_t)n / 3 + 1), s);   // runs of >= 3 elements
+    segmentReduceShortKernel<<<gridFor(g, 256), 256, 0, s>>>(index, measures, width, op, segStart.as<uint32_t>(), g, outIndex,
+                                                            outValues, runList.as<uint32_t>(), dRunCount, hash, outHash);
+    checkLastError("segmentReduceShort");
+    segmentReduceKernel<<<gridFor((int64_t)(n / 3 + 1) * 32, 256, 2), 256, 0, s>>>(index, measures, width, op, segStart.as<uint32_t>(), g,
+                                                                                  outIndex, outValues, longList.as<uint32_t>(), dLongCount,
+                                                                                  hash, outHash, runList.as<uint32_t>(), dRunCount);
+    checkLastError("segmentReduce");
+  } else {
+    segmentReduceKernel<<<gridFor((int64_t)g * 32, 256), 256, 0, s>>>(index, measures, width, op, segStart.as<uint32_t>(), g,
+                                                                     outIndex, outValues, longList.as<uint32_t>(), dLongCount,
+                                                                     hash, outHash);
+    checkLastError("segmentReduce");
+  }
   if ((uint32_t)n > kLongRun) {
     int blocks = (int)(maxLong < (uint32_t)smCount() * 2 ? maxLong : (uint32_t)smCount() * 2);
     longRunKernel<<<blocks, 512, 0, s>>>(index, measures, width, op, segStart.as<uint32_t>(), longList.as<uint32_t>(),

@@ -126,20 +126,45 @@ def nested_result(result: QueryResult, metas: list | None = None) -> dict:
 
 # ---- HyperLogLog estimate ----------------------------------------------------------------------------
 HLL_THRESHOLD = 15500.0
+HLL_DENSE_THRESHOLD = HLL_REGISTERS // 4   # query/common/hll.go DenseThreshold
+
+
+def hll_estimate_bias(estimate: float) -> float:
+    """getEstimateBias (reference query/common/hll.go:639-667): mean bias of the k = 6 raw estimates nearest to
+    `estimate` among the (up to 2k + 1) table entries around its insertion point; ties keep table order, as Go's
+    sort.Sort does on an already ordered window of distinct distances."""
+    import bisect
+    from .hll_bias_p14 import BIASES, RAW_ESTIMATES
+    i = bisect.bisect_right(RAW_ESTIMATES, estimate)        # first index with estimate < RAW_ESTIMATES[i]
+    k = 6
+    lo, hi = max(i - 1 - k, 0), min(i + k, len(RAW_ESTIMATES))
+    window = sorted(((RAW_ESTIMATES[j] - estimate) ** 2, j) for j in range(lo, hi))
+    return sum(BIASES[j] for _, j in window[:k]) / float(k)
 
 
 def hll_estimate(dense: np.ndarray) -> float:
-    """HLL.Compute on one register set (uint8[16384] of rho+1, 0 = empty).
-
-    The reference corrects the raw estimate with Google's empirical bias table when it lies in
-    (15500, 5 * 16384]; that table is data of the reference and is not reproduced here — in that range the
-    uncorrected estimate is returned (within ~1 % of the corrected one).  Below the threshold (linear
-    counting) and above 5m the value is exactly the reference's."""
+    """HLL.Compute on one register set (uint8[16384] of rho+1, 0 = empty) — reference query/common/hll.go:735-775:
+    raw estimate alpha m^2 / sum 2^-rho, empirical bias correction up to 5m, linear counting below the threshold,
+    truncation to an integer."""
     m = float(HLL_REGISTERS)
     nonzero = float(np.count_nonzero(dense))
-    rho = dense[dense != 0].astype(np.float64)          # registers store rho + 1 ... as the reference's Rho field
-    s = float(np.sum(np.exp2(-rho))) + (m - nonzero)
+    # float64 accumulation in the order of the Go loops (the sum is order-sensitive in its last bits and the result is
+    # truncated): a sparse register set (fewer than DenseThreshold = 4096 registers, readHLL :547-581) adds its registers
+    # in vector order (ascending register id) and then m - nonzero; a dense one walks all 16384 bytes (an empty
+    # register's byte 0 contributes 1 / 2^0)
+    s = 0.0
+    regs = dense.tolist()
+    if nonzero < HLL_DENSE_THRESHOLD:
+        for r in regs:
+            if r:
+                s += 1.0 / float(1 << r)
+        s += m - nonzero
+    else:
+        for r in regs:
+            s += 1.0 / float(1 << r)
     estimate = 0.7213 / (1 + 1.079 / m) * m * m / s
+    if estimate <= 5.0 * m:
+        estimate -= hll_estimate_bias(estimate)
     estimate_h = estimate
     if nonzero < m:
         estimate_h = m * math.log(m / (m - nonzero))

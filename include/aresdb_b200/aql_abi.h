@@ -9,7 +9,7 @@
  * whole-batch API that replaces the per-AST-node call sequence lives in batch_plan.h.
  *
  * Layout facts relied upon (verified with ctypes against the reference build,
- * tests/test_abi_layout.py): natural x86-64 alignment, enums are 4-byte ints,
+ * tests/test_abi_vs_reference_headers.py): natural x86-64 alignment, enums are 4-byte ints,
  * sizeof(DefaultValue)=24, VectorPartySlice=56, ScratchSpaceVector=16, ConstantVector=24,
  * ForeignColumnVector=72, ArrayVectorPartySlice=24, InputVector=80, OutputVector=32,
  * DimensionVector=40.  All structs are passed BY VALUE.

@@ -8,7 +8,7 @@
  * may load this library.  The product (aresdb_b200/) never does.
  *
  * Parity is PINNED: tests/test_golden_vectors.py checks this file against every known-answer
- * vector of the reference's native unit tests for the path, and tests/test_oracle_vs_ref.py
+ * vector of the reference's native unit tests for the path, and tests/test_node_parity.py, tests/test_pipeline_parity.py
  * checks it against the reference's own HOST build on seeded random inputs.
  *
  * Each function cites the reference code whose behaviour it restates (paths relative to the

@@ -93,3 +93,26 @@ def test_hll_nested_result():
                            np.array([(2 << 16) | 1], np.uint32).view(np.uint8)])                    # group 9: 1 register
     r = HLLResult(q, 2, block, 2, regs, np.array([2, 1], np.uint16))
     assert PP.hll_nested_result(r) == {"7": 2.0, "9": 1.0}
+
+
+def test_hll_estimate_reference_known_answer_and_bias_range():
+    """`Computes hll correctly` (reference query/common/hll_test.go:157-170): two registers -> 2.0; and the mid range
+    (15.5k < n <= 5m) goes through the empirical bias table exactly as getEstimateBias does."""
+    import bisect
+    from aresdb_b200 import hll_bias_p14 as B
+    dense = np.zeros(16384, np.uint8)
+    dense[100], dense[200] = 1, 2
+    assert PP.hll_estimate(dense) == 2.0
+    # a register set whose raw estimate lies inside the table: every register hit once with rho+1 = 2
+    dense[:] = 2
+    m = 16384.0
+    raw = 0.7213 / (1 + 1.079 / m) * m * m / sum(1.0 / 4.0 for _ in range(16384))
+    assert B.RAW_ESTIMATES[0] < raw < B.RAW_ESTIMATES[-1] and raw <= 5 * m
+    # independent restatement of the neighbour rule: 6 nearest by squared distance
+    near = sorted(range(len(B.RAW_ESTIMATES)), key=lambda j: (B.RAW_ESTIMATES[j] - raw) ** 2)[:6]
+    want = raw - sum(B.BIASES[j] for j in near) / 6.0
+    assert PP.hll_estimate(dense) == float(int(want))
+    assert abs(PP.hll_estimate_bias(raw) - sum(B.BIASES[j] for j in near) / 6.0) < 1e-9
+    # table edges: below the first and beyond the last raw estimate the window shrinks but k stays 6
+    assert PP.hll_estimate_bias(1000.0) == sum(B.BIASES[:6]) / 6.0
+    assert PP.hll_estimate_bias(1e6) == sum(B.BIASES[-6:]) / 6.0
