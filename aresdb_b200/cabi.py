@@ -48,7 +48,7 @@ ConstInt, ConstFloat, ConstGeoPoint, ConstUUID = range(4)
 VectorPartyInput, ScratchSpaceInput, ConstantInput, ForeignColumnInput, ArrayVectorPartyInput = range(5)
 ScratchSpaceOutput, MeasureOutput, DimensionOutput = range(3)
 
-PLAN_OPERAND_NONE, PLAN_OPERAND_COLUMN, PLAN_OPERAND_CONST, PLAN_OPERAND_STACK = range(4)
+PLAN_OPERAND_NONE, PLAN_OPERAND_COLUMN, PLAN_OPERAND_CONST, PLAN_OPERAND_STACK, PLAN_OPERAND_FOREIGN = range(5)
 PLAN_SINK_STACK, PLAN_SINK_FILTER, PLAN_SINK_DIMENSION, PLAN_SINK_MEASURE = range(4)
 ARES_REDUCE_SORT, ARES_REDUCE_HASH = range(2)
 ARES_MAX_PLAN_COLUMNS = 32
@@ -178,11 +178,24 @@ class ColumnRange(C.Structure):
     _fields_ = [("Known", C.c_uint8), ("Reserved", C.c_uint8 * 3), ("Min", C.c_uint32), ("Max", C.c_uint32)]
 
 
+ARES_MAX_FOREIGN_TABLES, ARES_MAX_FOREIGN_COLUMNS = 4, 8
+
+
+class PlanForeignTable(C.Structure):
+    _fields_ = [("JoinColumn", C.c_int32), ("Index", CuckooHashIndex)]
+
+
+class PlanForeignColumn(C.Structure):
+    _fields_ = [("Table", C.c_int32), ("Column", ForeignColumnVector)]
+
+
 class BatchPlan(C.Structure):
     _fields_ = [("Columns", VectorPartySlice * ARES_MAX_PLAN_COLUMNS), ("NumColumns", C.c_int32),
                 ("Insts", PlanInst * ARES_MAX_PLAN_INSTS), ("NumInsts", C.c_int32),
                 ("BaseCounts", C.c_void_p), ("StartCount", C.c_uint32), ("NumRows", C.c_uint32),
-                ("Ranges", ColumnRange * ARES_MAX_PLAN_COLUMNS)]
+                ("Ranges", ColumnRange * ARES_MAX_PLAN_COLUMNS),
+                ("ForeignTables", PlanForeignTable * ARES_MAX_FOREIGN_TABLES), ("NumForeignTables", C.c_int32),
+                ("ForeignColumns", PlanForeignColumn * ARES_MAX_FOREIGN_COLUMNS), ("NumForeignColumns", C.c_int32)]
 
 
 class AggSpec(C.Structure):

@@ -30,6 +30,8 @@
 
 namespace aresb {
 
+// from legacy_nodes.cu
+ForeignDesc makeForeignDesc(const ForeignColumnVector &f);
 // from sort_reduce.cu
 void gatherDims(const uint8_t *in, const DimLayout &Lin, const uint32_t *rows, int g, uint8_t *out,
                 const DimLayout &Lout, cudaStream_t s);
@@ -221,6 +223,29 @@ __device__ __forceinline__ void getOperand(const DevPlan &P, const DevInst &I, b
 #pragma unroll
     for (int r = 0; r < R; r++) v[r] = k;
     valid = (second ? I.bvalid : I.avalid) ? 0xF : 0;
+  } else if (kind == OPK_FOREIGN) {
+    // joined dimension table: probe its index with the row's join key, read the foreign column at the RecordID
+    const uint8_t fc = second ? I.bcol : I.acol;
+    const uint8_t t = P.foreignTableOf[fc];
+    const DevColumn &jc = P.cols[P.joinCol[t]];
+    uint32_t key[R], kvalid;
+    if (jc.in.mode == 0) {
+#pragma unroll
+      for (int r = 0; r < R; r++) key[r] = (uint32_t)jc.in.constLo;
+      kvalid = jc.in.constValid ? 0xF : 0;
+    } else if (STAGED) {
+      fetchStaged(jc, stage, q, key, kvalid);
+    } else {
+      fetchDirect(P, jc, row0, nrows, key, kvalid);
+    }
+    valid = 0;
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      const unsigned long long rid = ((kvalid >> r) & 1) && (uint32_t)r < nrows ? cuckooLookup(P.join->tables[t], key[r], 0) : 0ull;
+      const Cell f = foreignLoad(P.join->cols[fc], rid, nullptr);
+      v[r] = (uint32_t)f.v;
+      valid |= (f.valid ? 1u : 0u) << r;
+    }
   } else {  // stack pop (static unrolled select keeps the stack in registers)
     sp--;
 #pragma unroll
@@ -1028,6 +1053,16 @@ static uint8_t operandClassOf(const PlanOperand &o, const BatchPlan &bp, const s
     case PLAN_OPERAND_STACK:
       if (stackClasses.empty()) throw EngineError("plan pops an empty evaluation stack");
       return stackClasses.back();
+    case PLAN_OPERAND_FOREIGN: {
+      if (o.Column >= bp.NumForeignColumns) throw EngineError("plan operand references a column outside BatchPlan.ForeignColumns");
+      switch (bp.ForeignColumns[o.Column].Column.DataType) {
+        case Bool: return VC_BOOL;
+        case Int8: case Int16: case Int32: return VC_I32;
+        case Uint8: case Uint16: case Uint32: return VC_U32;
+        case Float32: return VC_F32;
+        default: throw EngineError("foreign columns of the fused path are Bool / 1-, 2-, 4-byte integers / Float32");
+      }
+    }
     default: throw EngineError("plan instruction has a missing operand");
   }
 }
@@ -1084,6 +1119,23 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
     P.cols[c].staged = 0;
     P.cols[c].hasNulls = 0;
   }
+  // joined dimension tables
+  if (bp.NumForeignTables < 0 || bp.NumForeignTables > kMaxForeignTables || bp.NumForeignColumns < 0 ||
+      bp.NumForeignColumns > kMaxForeignCols)
+    throw EngineError("invalid number of foreign tables / columns");
+  P.numForeignTables = (uint8_t)bp.NumForeignTables;
+  P.numForeignCols = (uint8_t)bp.NumForeignColumns;
+  for (int t = 0; t < bp.NumForeignTables; t++) {
+    const int jc = bp.ForeignTables[t].JoinColumn;
+    if (jc < 0 || jc >= bp.NumColumns) throw EngineError("foreign table joins on a column outside BatchPlan.Columns");
+    if (P.cols[jc].width > 4) throw EngineError("join keys of the fused path are 1-, 2- or 4-byte columns");
+    P.joinCol[t] = (uint8_t)jc;
+  }
+  for (int k = 0; k < bp.NumForeignColumns; k++) {
+    const int t = bp.ForeignColumns[k].Table;
+    if (t < 0 || t >= bp.NumForeignTables) throw EngineError("foreign column of a table outside BatchPlan.ForeignTables");
+    P.foreignTableOf[k] = (uint8_t)t;
+  }
   const DimLayout &RL = st->rowLayout;
   std::vector<uint8_t> stack;
   std::vector<bool> dimSeen(RL.numDims, false);
@@ -1105,6 +1157,7 @@ static void compilePlan(const AggState *st, const BatchPlan &bp, DevPlan &P) {
     auto fill = [&](const PlanOperand &o, uint8_t &kind, uint8_t &col, uint8_t &valid, uint32_t &k) {
       kind = o.Kind; col = o.Column; valid = o.ConstValid;
       if (o.Kind == PLAN_OPERAND_COLUMN) P.cols[o.Column].used = 1;
+      if (o.Kind == PLAN_OPERAND_FOREIGN) P.cols[P.joinCol[P.foreignTableOf[o.Column]]].used = 1;   // the join key is staged
       if (o.Kind == PLAN_OPERAND_CONST) {
         if (o.ConstType == ConstFloat) memcpy(&k, &o.Const.FloatVal, 4); else k = (uint32_t)o.Const.IntVal;
       }
@@ -1399,6 +1452,26 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
       col.in.mode = 2;
       col.in.startBit = 0;
     }
+  }
+  // joined dimension tables: indexes + foreign-column batches go to device memory for the kernel's lifetime
+  std::unique_ptr<Scratch> joinMem;
+  P.join = nullptr;
+  if (P.numForeignCols > 0 || P.numForeignTables > 0) {
+    static thread_local DevJoin J;
+    memset(&J, 0, sizeof(J));
+    for (int t = 0; t < bp.NumForeignTables; t++) {
+      const CuckooHashIndex &h = bp.ForeignTables[t].Index;
+      if (h.buckets == nullptr || h.numBuckets <= 0 || h.keyBytes <= 0 || h.keyBytes > 4 || h.numHashes < 0 || h.numHashes > 4)
+        throw EngineError("invalid CuckooHashIndex in BatchPlan.ForeignTables (fused path: keys of at most 4 bytes)");
+      J.tables[t].buckets = h.buckets;
+      for (int i = 0; i < 4; i++) J.tables[t].seeds[i] = h.seeds[i];
+      J.tables[t].keyBytes = h.keyBytes; J.tables[t].numHashes = h.numHashes; J.tables[t].numBuckets = h.numBuckets;
+    }
+    for (int k = 0; k < bp.NumForeignColumns; k++) J.cols[k] = makeForeignDesc(bp.ForeignColumns[k].Column);
+    joinMem.reset(new Scratch(sizeof(DevJoin), s));
+    ARES_CUDA(cudaMemcpyAsync(joinMem->ptr, &J, sizeof(DevJoin), cudaMemcpyHostToDevice, s));
+    ARES_CUDA(cudaStreamSynchronize(s));   // J is reused by the next call of this thread
+    P.join = joinMem->as<DevJoin>();
   }
   size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
   static bool attrSet[64] = {false};

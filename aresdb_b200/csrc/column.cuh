@@ -12,7 +12,7 @@
 
 namespace aresb {
 
-enum InputKind : uint8_t { IN_COLUMN = 0, IN_SCRATCH = 1, IN_CONST = 2 };
+enum InputKind : uint8_t { IN_COLUMN = 0, IN_SCRATCH = 1, IN_CONST = 2, IN_FOREIGN = 3 /* ForeignColumnInput: see join.cuh */ };
 
 struct InputDesc {
   const uint8_t *base;     // column: BasePtr; scratch: Values
@@ -29,9 +29,11 @@ struct InputDesc {
   uint8_t constValid;
 };
 
+#ifndef __CUDACC_RTC__
 // Host: ABI struct -> descriptor; throws EngineError for inputs outside the hot path.
 InputDesc makeInputDesc(const InputVector &in, bool allowWide);
 InputDesc makeColumnDesc(const VectorPartySlice &vp, bool allowWide);
+#endif
 
 #ifdef __CUDACC__
 __device__ __forceinline__ bool bitAt(const uint8_t *p, uint32_t bit) {

@@ -13,6 +13,14 @@ constexpr int kJitMaxWide = 8;
 constexpr int kJitMaxMagic = 16;
 constexpr int kJitMaxDenseDims = 8;
 
+// mirrors plan_device.cuh
+constexpr int kMaxForeignTables = 4;
+constexpr int kMaxForeignCols = 8;
+struct DevJoin {
+  CuckooDesc tables[kMaxForeignTables];
+  ForeignDesc cols[kMaxForeignCols];
+};
+
 struct JitParams {
   const uint8_t *partSrc[kJitMaxParts];   // global base address of every staged part
   const uint8_t *wideValues[kJitMaxWide]; // 8/16-byte dimension columns read straight from global
@@ -33,7 +41,9 @@ struct JitParams {
   double fxInv;                           // JIT_DENSE_ACC == 4: 2^-S
   float fxScale;                          //                     2^S (a float sum's rows are added as integers x * 2^S)
   uint32_t fxPad;
+  const DevJoin *join;                    // joined dimension tables (join.cuh), null without joins
 };
+
 
 // rows 4q .. 4q+3 of a staged value column of W bytes per value
 template <int W, bool SIGNED>

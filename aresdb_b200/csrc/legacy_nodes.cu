@@ -8,6 +8,7 @@
 
 #include "column.cuh"
 #include "common.cuh"
+#include "join.cuh"
 #include "scan.cuh"
 
 namespace aresb {
@@ -81,11 +82,42 @@ InputDesc makeInputDesc(const InputVector &in, bool allowWide) {
     }
     case VectorPartyInput:
       return makeColumnDesc(in.Vector.VP, allowWide);
-    case ForeignColumnInput:
-      throw EngineError("ForeignColumnInput (dimension-table join) is outside the B200 hot path");
+    case ForeignColumnInput: {   // the descriptor proper (batches, RecordIDs, timezone table) is a ForeignDesc: makeForeignDesc
+      const ForeignColumnVector &f = in.Vector.ForeignVP;
+      d.kind = IN_FOREIGN;
+      d.dtype = (uint8_t)f.DataType;
+      d.vclass = columnClass(f.DataType);
+      if ((d.vclass == VC_I64 || d.vclass == VC_UUID) && !allowWide)
+        throw EngineError("int64/UUID data types are only supported in UnaryTransform");
+      return d;
+    }
     default:
       throw EngineError("ArrayVectorPartyInput (array columns) is outside the B200 hot path");
   }
+}
+
+// ForeignColumnInput -> device descriptor.  `Batches` points to HOST memory valid for the duration of the call (Go heap,
+// query/time_series_aggregate.go:100-112): the slices are copied by value into the kernel parameters.
+ForeignDesc makeForeignDesc(const ForeignColumnVector &f) {
+  ForeignDesc F;
+  memset(&F, 0, sizeof(F));
+  if (f.NumBatches < 0 || f.NumBatches > kMaxForeignBatches)
+    throw EngineError("a joined dimension table may hold at most " + std::to_string(kMaxForeignBatches) + " batches");
+  if (f.NumBatches > 0 && f.Batches == nullptr) throw EngineError("ForeignColumnVector.Batches is NULL");
+  F.recordIDs = reinterpret_cast<const unsigned long long *>(f.RecordIDs);
+  F.tzLookup = f.TimezoneLookup;
+  F.tzSize = f.TimezoneLookupSize;
+  F.numBatches = f.NumBatches; F.baseBatchID = f.BaseBatchID; F.numRecordsInLastBatch = f.NumRecordsInLastBatch;
+  for (int b = 0; b < f.NumBatches; b++) {
+    VectorPartySlice vp = f.Batches[b];
+    if (vp.BasePtr == nullptr) {   // mode 0: the COLUMN's default (prepareForeignTableIterators passes hasDefault / defaultValue)
+      vp.DefaultValue = f.DefaultValue;
+    }
+    vp.DataType = f.DataType;
+    F.batches[b] = makeColumnDesc(vp, /*allowWide=*/true);
+    if (F.batches[b].mode == 3) throw EngineError("dimension-table columns are not compressed (mode 3 foreign batch)");
+  }
+  return F;
 }
 
 enum SinkKind : uint8_t { SINK_SCRATCH, SINK_DIMENSION, SINK_MEASURE, SINK_PREDICATE };
@@ -167,6 +199,7 @@ static SinkDesc makeSink(const OutputVector &out) {
 
 struct NodeDesc {
   InputDesc in[2];
+  ForeignDesc fd[2];       // in[k].kind == IN_FOREIGN: its batches / RecordIDs
   const uint32_t *index;
   const uint32_t *baseCounts;
   uint32_t startCount;
@@ -202,9 +235,16 @@ __device__ __forceinline__ Cell evalUnaryI64(int fn, Cell a, ValClass *rc) {
   }
 }
 
+// Operand k of row position i: a foreign column is read at the RecordID the join left for THIS position
+// (RecordIDJoinIterator is positional over the RecordID vector, zipped with the index vector: query/binder.hpp:147-176).
+__device__ __forceinline__ Cell loadNodeInput(const NodeDesc &nd, int k, uint32_t i, uint64_t *hi) {
+  if (nd.in[k].kind == IN_FOREIGN) return foreignLoad(nd.fd[k], nd.fd[k].recordIDs[i], hi);
+  return loadInput(nd.in[k], i, nd.index, nd.baseCounts, nd.startCount, hi);
+}
+
 __device__ __forceinline__ Cell evalNode(const NodeDesc &nd, uint32_t i, ValClass *rc, uint64_t *hi) {
   if (nd.nin == 1) {
-    Cell a = loadInput(nd.in[0], i, nd.index, nd.baseCounts, nd.startCount, hi);
+    Cell a = loadNodeInput(nd, 0, i, hi);
     ValClass ic = (ValClass)nd.in[0].vclass;
     if (ic == VC_I64) return evalUnaryI64(nd.fn, a, rc);
     if (ic == VC_UUID) {
@@ -215,8 +255,8 @@ __device__ __forceinline__ Cell evalNode(const NodeDesc &nd, uint32_t i, ValClas
     }
     return evalUnary(nd.fn, a, ic, rc);
   }
-  Cell a = loadInput(nd.in[0], i, nd.index, nd.baseCounts, nd.startCount, nullptr);
-  Cell b = loadInput(nd.in[1], i, nd.index, nd.baseCounts, nd.startCount, nullptr);
+  Cell a = loadNodeInput(nd, 0, i, nullptr);
+  Cell b = loadNodeInput(nd, 1, i, nullptr);
   ValClass tc = (ValClass)nd.tclass;
   a.v = cvt(a.v, (ValClass)nd.in[0].vclass, tc);
   b.v = cvt(b.v, (ValClass)nd.in[1].vclass, tc);
@@ -339,6 +379,19 @@ filterKernel(NodeDesc nd, uint32_t *index, uint8_t *predicate, ScanTileState st,
   }
 }
 
+// HashLookup (reference query/hash_lookup.cu:70-157): RecordID of the dimension-table row whose primary key equals the
+// main-table join column at index position i; {0, 0} for NULL keys and keys the table does not hold.
+__global__ void __launch_bounds__(256)
+hashLookupKernel(InputDesc in, const uint32_t *__restrict__ index, const uint32_t *__restrict__ baseCounts, uint32_t startCount,
+                 int n, CuckooDesc H, unsigned long long *__restrict__ out) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < (uint32_t)n; i += stride) {
+    uint64_t hi = 0;
+    const Cell c = loadInput(in, i, index, baseCounts, startCount, &hi);
+    out[i] = c.valid ? cuckooLookup(H, c.v, hi) : 0ull;
+  }
+}
+
 __global__ void initIndexKernel(uint32_t *index, uint32_t start, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) index[i] = start + (uint32_t)i;
@@ -359,7 +412,10 @@ static NodeDesc makeNode(const InputVector *ins, int nin, int fn, uint32_t *inde
   memset(&nd, 0, sizeof(nd));
   nd.nin = (uint8_t)nin; nd.fn = fn; nd.index = index; nd.n = n;
   nd.baseCounts = baseCounts; nd.startCount = startCount;
-  for (int k = 0; k < nin; k++) nd.in[k] = makeInputDesc(ins[k], /*allowWide=*/nin == 1);
+  for (int k = 0; k < nin; k++) {
+    nd.in[k] = makeInputDesc(ins[k], /*allowWide=*/nin == 1);
+    if (nd.in[k].kind == IN_FOREIGN) nd.fd[k] = makeForeignDesc(ins[k].Vector.ForeignVP);
+  }
   if (nin == 2) nd.tclass = commonClass((ValClass)nd.in[0].vclass, (ValClass)nd.in[1].vclass);
   else nd.tclass = nd.in[0].vclass;
   for (int k = 0; k < nin; k++)
@@ -479,9 +535,25 @@ CGoCallResHandle BinaryFilter(InputVector lhs, InputVector rhs, uint32_t *indexV
 }
 
 // ---- symbols outside the hot path (must exist, may return an error) -------
-CGoCallResHandle HashLookup(InputVector, RecordID *, uint32_t *, int, uint32_t *, uint32_t,
-                            CuckooHashIndex, void *, int) {
-  return unsupported("HashLookup", "dimension-table joins are out of scope (SURVEY.md §8f4)");
+CGoCallResHandle HashLookup(InputVector input, RecordID *output, uint32_t *indexVector, int indexVectorLength,
+                            uint32_t *baseCounts, uint32_t startCount, CuckooHashIndex hashIndex, void *cudaStream,
+                            int device) {
+  return guarded("HashLookup", device, [&]() -> int64_t {
+    if (indexVectorLength <= 0) return 0;
+    if (input.Type != VectorPartyInput) throw EngineError("HashLookup joins on a main-table column (VectorPartyInput)");
+    InputDesc d = makeInputDesc(input, /*allowWide=*/true);
+    if (d.mode != 0 && indexVector == nullptr) throw EngineError("indexVector must not be NULL for a column input");
+    if (hashIndex.numBuckets <= 0 || hashIndex.keyBytes <= 0 || hashIndex.keyBytes > 16 || hashIndex.numHashes < 0 || hashIndex.numHashes > 4)
+      throw EngineError("invalid CuckooHashIndex");
+    CuckooDesc H;
+    H.buckets = hashIndex.buckets;
+    for (int i = 0; i < 4; i++) H.seeds[i] = hashIndex.seeds[i];
+    H.keyBytes = hashIndex.keyBytes; H.numHashes = hashIndex.numHashes; H.numBuckets = hashIndex.numBuckets;
+    hashLookupKernel<<<gridFor(indexVectorLength, 256), 256, 0, (cudaStream_t)cudaStream>>>(
+        d, indexVector, baseCounts, startCount, indexVectorLength, H, reinterpret_cast<unsigned long long *>(output));
+    checkLastError("HashLookup");
+    return indexVectorLength;   // thrust::transform's end - begin (query/hash_lookup.cu:147-156)
+  });
 }
 CGoCallResHandle Expand(DimensionVector, DimensionVector, uint32_t *, uint32_t *, int, int, void *, int) {
   return unsupported("Expand", "non-aggregate queries are out of scope");

@@ -3,6 +3,7 @@
 #pragma once
 #include "column.cuh"
 #include "fused_device.cuh"
+#include "join.cuh"
 
 namespace aresb {
 
@@ -13,7 +14,15 @@ constexpr int kJitThreads = 1024;
 constexpr int kMaxGridCtas = 160;             // persistent grid: one CTA per SM (148 on B200)
 
 enum KeyMode : uint8_t { KEY_PACKED = 0, KEY_HASHED = 1 };
-enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3 };
+enum OperandKind : uint8_t { OPK_NONE = 0, OPK_COLUMN = 1, OPK_CONST = 2, OPK_STACK = 3, OPK_FOREIGN = 4 };
+
+// Joined dimension tables of a plan, in device memory for the duration of the batch's kernel (uploaded by executePlan).
+constexpr int kMaxForeignTables = ARES_MAX_FOREIGN_TABLES;
+constexpr int kMaxForeignCols = ARES_MAX_FOREIGN_COLUMNS;
+struct DevJoin {
+  CuckooDesc tables[kMaxForeignTables];
+  ForeignDesc cols[kMaxForeignCols];
+};
 
 struct DevColumn {
   InputDesc in;            // how to read it straight from global memory (any mode)
@@ -79,7 +88,12 @@ struct DevPlan {
   uint8_t denseFx;         // float sum accumulated as exact integers (three 32-bit pieces per slot), see jitAnalyzeDense
   int8_t fxMeasureInst;    // the measure instruction (a verbatim Float32 column with a zone map)
   int8_t fxShift;          // S: a row adds x * 2^S
-  uint8_t pad2[3];
+  uint8_t numForeignTables, numForeignCols;
+  uint8_t joinCol[kMaxForeignTables];       // main-table column matched with table t's primary key
+  uint8_t foreignTableOf[kMaxForeignCols];  // table of foreign column k (operand kind OPK_FOREIGN, acol / bcol = k)
+  uint8_t foreignClass[kMaxForeignCols];    // ValClass a read of foreign column k yields
+  uint8_t pad2[1];
+  const DevJoin *join;     // device copy of the tables' indexes and the foreign columns' batches
 };
 
 constexpr uint32_t kDenseMaxSlots = 8192;   // = slots of a CTA's accumulator slice in AggState::ctaAcc

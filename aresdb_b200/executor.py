@@ -91,6 +91,16 @@ class LegacyBatchExecutor:
                 action(A.Noop, [iv])
                 return None
             return iv
+        if isinstance(e, E.ForeignCol):
+            from . import joins as J
+            j = self.q.joins[e.table]
+            iv, keep = J.foreign_input(j.table, e.index, ctx["record_ids"][e.table].ptr,
+                                       j.timezone_ptr if e.timezone else None, j.timezone_size if e.timezone else 0)
+            ctx["frames"].append(keep)   # the host array of batch slices lives until the call returns
+            if action:
+                action(A.Noop, [iv])
+                return None
+            return iv
         if isinstance(e, E.Lit):
             iv = A.const_input(e.value, True, is_float=e.type == E.Type.Float)
             if action:
@@ -126,7 +136,7 @@ class LegacyBatchExecutor:
         bc = batch.base_counts.ptr if batch.base_counts else None
         size = batch.num_rows
         # preExec: prepareForFiltering + InitIndexVector (aql_batchexecutor.go:256)
-        ctx = {"size": size, "index": sp.zeros(4 * max(size, 1)), "frames": []}
+        ctx = {"size": size, "index": sp.zeros(4 * max(size, 1)), "frames": [], "record_ids": [], "rec_ptrs": None}
         predicate = sp.zeros(max(size, 1))
         self._call("InitIndexVector", ctx["index"].ptr, 0, size, stream, dev)
 
@@ -134,16 +144,31 @@ class LegacyBatchExecutor:
         def filter_action(fn, inputs):
             if ctx["size"] <= 0:
                 return
+            recs, nrec = ctx["rec_ptrs"], len(ctx["record_ids"])   # RecordID vectors are compacted with the index vector
             if len(inputs) == 1:
-                ctx["size"] = self._call("UnaryFilter", inputs[0], ctx["index"].ptr, predicate.ptr, ctx["size"], None, 0,
+                ctx["size"] = self._call("UnaryFilter", inputs[0], ctx["index"].ptr, predicate.ptr, ctx["size"], recs, nrec,
                                          bc, batch.start_count, fn, stream, dev)
             else:
                 ctx["size"] = self._call("BinaryFilter", inputs[0], inputs[1], ctx["index"].ptr, predicate.ptr,
-                                         ctx["size"], None, 0, bc, batch.start_count, fn, stream, dev)
+                                         ctx["size"], recs, nrec, bc, batch.start_count, fn, stream, dev)
 
-        for f in q.filters:
+        for f in q.filters[:q.num_main_filters]:
             self._eval(f, batch, ctx, filter_action)
             ctx["frames"].clear()
+        # join (aql_batchexecutor.go:115-147): one RecordID per surviving index position and joined table
+        if q.joins:
+            for j in q.joins:
+                rec = sp.zeros(8 * max(ctx["size"], 1))
+                ctx["record_ids"].append(rec)
+                if ctx["size"] > 0:
+                    self._call("HashLookup", A.vp_input(batch.columns[j.on.index]), rec.ptr, ctx["index"].ptr, ctx["size"], bc,
+                               batch.start_count, j.table.hash_index(), stream, dev)
+            ptrs = (C.c_void_p * len(q.joins))(*[r.ptr for r in ctx["record_ids"]])
+            ctx["rec_ptr_array"] = ptrs
+            ctx["rec_ptrs"] = C.cast(ptrs, C.c_void_p).value
+            for f in q.filters[q.num_main_filters:]:
+                self._eval(f, batch, ctx, filter_action)
+                ctx["frames"].clear()
         size = ctx["size"]
 
         # project: prepareForDimAndMeasureEval (aql_processor.go:743-776) — input buffers hold the
@@ -279,6 +304,22 @@ class FusedBatchExecutor:
         self.calls = 0
         self.skipped = 0   # batches whose zone map contradicts a filter (skipping.py): never launched
         self.expected_groups = expected_groups
+        # joined dimension tables: the lookup + foreign-column reads are a gather stage of the fused kernel
+        self._join_keep = []
+        if query.joins:
+            if len(query.joins) > A.ARES_MAX_FOREIGN_TABLES or len(query.foreign_columns) > A.ARES_MAX_FOREIGN_COLUMNS:
+                raise ValueError("too many joined tables / foreign columns for one plan")
+            self._plan.NumForeignTables = len(query.joins)
+            for t, j in enumerate(query.joins):
+                self._plan.ForeignTables[t].JoinColumn = j.on.index
+                self._plan.ForeignTables[t].Index = j.table.hash_index()
+            self._plan.NumForeignColumns = len(query.foreign_columns)
+            for k, (t, col, tz) in enumerate(query.foreign_columns):
+                j = query.joins[t]
+                f, keep = j.table.foreign_column(col, None, j.timezone_ptr if tz else None, j.timezone_size if tz else 0)
+                self._join_keep.append(keep)
+                self._plan.ForeignColumns[k].Table = t
+                self._plan.ForeignColumns[k].Column = f
 
     def process_batch(self, batch: Batch, stream=None):
         if should_skip_batch(self.q, batch.ranges):

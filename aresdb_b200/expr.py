@@ -43,6 +43,21 @@ class Col(Expr):
 
 
 @dataclass
+class ForeignCol(Expr):
+    """VarRef of column `index` of joined dimension table `table` (0-based position in AggQuery.joins; the reference's
+    VarRef.TableID - 1): read at the RecordID the join found for the row (ForeignColumnInput)."""
+    table: int
+    index: int
+    data_type: int
+    name: str = ""
+    timezone: bool = False   # enum column mapped through the query's timezone-offset table (makeForeignColumnInput)
+
+    @property
+    def type(self):
+        return DATA_TYPE_TO_EXPR_TYPE[self.data_type]
+
+
+@dataclass
 class Lit(Expr):
     """NumberLiteral; `type` Float makes it a ConstFloat, anything else a ConstInt
     (makeConstantInput, reference query/time_series_aggregate.go:239-270)."""
@@ -82,7 +97,7 @@ def _cast(e: Expr, t: Type) -> Expr:
 
 def resolve(e: Expr) -> Expr:
     """Bottom-up type resolution (returns a new tree)."""
-    if isinstance(e, (Col, Lit)):
+    if isinstance(e, (Col, Lit, ForeignCol)):
         return e
     if isinstance(e, Unary):
         c = resolve(e.expr)
@@ -134,7 +149,7 @@ def scratch_data_type(t: Type) -> int:
 
 def dimension_data_type(e: Expr) -> int:
     """GetDimensionDataType — reference query/common/dim_util.go:9-40."""
-    if isinstance(e, Col):
+    if isinstance(e, (Col, ForeignCol)):
         return e.data_type
     return {Type.Boolean: A.Bool, Type.Unsigned: A.Uint32, Type.Signed: A.Int32, Type.Float: A.Float32,
             Type.UUID: A.UUID}.get(e.type, A.Uint32)
@@ -154,3 +169,14 @@ def add(l, r): return Binary(A.Plus, l, r)
 def mul(l, r): return Binary(A.Multiply, l, r)
 def mod(l, r): return Binary(A.Mod, l, r)
 def div(l, r): return Binary(A.Divide, l, r)
+
+
+def uses_foreign(e: Expr) -> bool:
+    """Does the expression read a joined table's column?"""
+    if isinstance(e, ForeignCol):
+        return True
+    if isinstance(e, Unary):
+        return uses_foreign(e.expr)
+    if isinstance(e, Binary):
+        return uses_foreign(e.lhs) or uses_foreign(e.rhs)
+    return False

@@ -22,9 +22,24 @@ class Measure:
     expr: E.Expr | None = None
 
 
+@dataclass
+class Join:
+    """One joined dimension table: `table` (joins.DimensionTable, resident in the executor's memory space) matched on its
+    primary key by main-table column `on`; `timezone_table` optionally maps an enum column to a timezone offset."""
+    table: object
+    on: E.Col
+    timezone_ptr: int | None = None
+    timezone_size: int = 0
+
+
 class AggQuery:
-    def __init__(self, filters, dimensions, measure: Measure, reduce_mode: int = A.ARES_REDUCE_SORT):
-        self.filters = [E.resolve(f) for f in filters]
+    def __init__(self, filters, dimensions, measure: Measure, reduce_mode: int = A.ARES_REDUCE_SORT, joins=None):
+        self.joins = list(joins or [])
+        resolved = [E.resolve(f) for f in filters]
+        # main-table filters run before the join, filters that read a joined table after it
+        # (MainTableCommonFilters / ForeignTableCommonFilters, reference query/aql_batchexecutor.go:100-147)
+        self.filters = [f for f in resolved if not E.uses_foreign(f)] + [f for f in resolved if E.uses_foreign(f)]
+        self.num_main_filters = sum(1 for f in resolved if not E.uses_foreign(f))
         self.dimensions = [E.resolve(d) for d in dimensions]
         self.reduce_mode = reduce_mode
         # ---- dimensions: widest first, stable (reference query/aql_compiler.go:1341-1370) ----------
@@ -99,10 +114,16 @@ class AggQuery:
         """Post-order flattening of every expression: one PlanInst per non-leaf AST node (what
         processExpression turns into one cgo call, reference query/time_series_aggregate.go:493-593)."""
         insts: list[A.PlanInst] = []
+        self.foreign_columns = []   # distinct (table, column, timezone) leaves in first-use order = BatchPlan.ForeignColumns
 
         def operand(e: E.Expr) -> A.PlanOperand:
             o = A.PlanOperand()
-            if isinstance(e, E.Col):
+            if isinstance(e, E.ForeignCol):
+                key = (e.table, e.index, e.timezone)
+                if key not in self.foreign_columns:
+                    self.foreign_columns.append(key)
+                o.Kind, o.Column = A.PLAN_OPERAND_FOREIGN, self.foreign_columns.index(key)
+            elif isinstance(e, E.Col):
                 o.Kind, o.Column = A.PLAN_OPERAND_COLUMN, e.index
             elif isinstance(e, E.Lit):
                 o.Kind, o.ConstValid = A.PLAN_OPERAND_CONST, 1

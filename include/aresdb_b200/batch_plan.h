@@ -28,14 +28,18 @@
 enum {
   ARES_MAX_PLAN_COLUMNS = MAX_COLUMNS_OF_A_TABLE,
   ARES_MAX_PLAN_INSTS = 64,
-  ARES_PLAN_STACK_DEPTH = 4
+  ARES_PLAN_STACK_DEPTH = 4,
+  ARES_MAX_FOREIGN_TABLES = 4,
+  ARES_MAX_FOREIGN_COLUMNS = 8
 };
 
 enum PlanOperandKind {
   PLAN_OPERAND_NONE = 0,
   PLAN_OPERAND_COLUMN = 1, /* BatchPlan.Columns[Column]: what makeVectorPartySliceInput passes   */
   PLAN_OPERAND_CONST = 2,  /* what makeConstantInput passes (ConstInt / ConstFloat + IsValid)   */
-  PLAN_OPERAND_STACK = 3   /* result of an earlier PLAN_SINK_STACK instruction (LIFO)            */
+  PLAN_OPERAND_STACK = 3,  /* result of an earlier PLAN_SINK_STACK instruction (LIFO)            */
+  PLAN_OPERAND_FOREIGN = 4 /* BatchPlan.ForeignColumns[Column]: what makeForeignColumnInput passes — a column of a
+                            * joined dimension table, read at the RecordID the join finds for the row       */
 };
 
 typedef struct {
@@ -85,6 +89,22 @@ typedef struct {
   uint32_t Max;
 } ColumnRange;
 
+/* Dimension-table joins on the fused path (what BatchExecutorImpl.join() prepares per batch with HashLookup,
+ * query/aql_batchexecutor.go:115-147, and what makeForeignColumnInput passes per expression leaf).  The lookup is a gather
+ * stage INSIDE the fused kernel: the RecordID of a surviving row is found by probing the dimension table's cuckoo index
+ * with the row's join-column value when the first instruction that reads the table is reached, and the foreign column is
+ * read at it; no RecordID vector is materialised.  Join keys are 1- / 2- / 4-byte main-table columns. */
+typedef struct {
+  int32_t JoinColumn;    /* index into BatchPlan.Columns: the main-table column matched with the table's primary key */
+  CuckooHashIndex Index; /* the dimension table's primary-key index (device memory)                                  */
+} PlanForeignTable;
+
+typedef struct {
+  int32_t Table;              /* index into BatchPlan.ForeignTables                                                  */
+  ForeignColumnVector Column; /* as makeForeignColumnInput fills it; RecordIDs is ignored; Batches points to HOST memory
+                               * valid for the duration of the call (at most 8 batches); TimezoneLookup to device memory */
+} PlanForeignColumn;
+
 /* One batch of one table shard: column slices already resident on the device. */
 typedef struct {
   VectorPartySlice Columns[ARES_MAX_PLAN_COLUMNS];
@@ -99,6 +119,10 @@ typedef struct {
   uint32_t StartCount;
   uint32_t NumRows;
   ColumnRange Ranges[ARES_MAX_PLAN_COLUMNS]; /* zone map per entry of Columns (all zero: none) */
+  PlanForeignTable ForeignTables[ARES_MAX_FOREIGN_TABLES];
+  int32_t NumForeignTables;
+  PlanForeignColumn ForeignColumns[ARES_MAX_FOREIGN_COLUMNS];
+  int32_t NumForeignColumns;
 } BatchPlan;
 
 enum AresReduceMode {

@@ -240,6 +240,29 @@ static int read_input(const InputVector *in, uint32_t i, const uint32_t *index,
       *out = read_vp(&in->Vector.VP, index ? index[i] : i, baseCounts, startCount);
       return 0;
     }
+    case ForeignColumnInput: {
+      /* RecordIDJoinIterator::dereference — query/iterator.hpp:916-930: positional over the RecordID vector; the batch
+       * is batchID - BaseBatchID, bounds-checked against the last batch's record count; mode-0 batches yield the
+       * column default (prepareForeignTableIterators, query/binder.hpp:163-176); then the timezone table (:889-905). */
+      const ForeignColumnVector *f = &in->Vector.ForeignVP;
+      kind_t k = column_kind(f->DataType);
+      if ((int)k < 0) return -1;
+      RecordID rid = f->RecordIDs[i];
+      out->k = k;
+      out->valid = false;
+      if (rid.batchID && (rid.batchID - f->BaseBatchID < f->NumBatches - 1 || rid.index < (uint32_t)f->NumRecordsInLastBatch)) {
+        VectorPartySlice vp = f->Batches[rid.batchID - f->BaseBatchID];
+        vp.DataType = f->DataType;
+        if (vp.BasePtr == NULL) vp.DefaultValue = f->DefaultValue;
+        *out = read_vp(&vp, rid.index, NULL, 0);
+        if (f->TimezoneLookup && k != K_UUID && k != K_I64) {
+          int e = k == K_F32 ? (int)out->v.f : k == K_BOOL ? (int)out->v.b : (int)out->v.u;
+          int16_t off = e < f->TimezoneLookupSize ? f->TimezoneLookup[e] : 0;
+          if (k == K_F32) out->v.f = (float)off; else if (k == K_BOOL) out->v.b = off != 0; else out->v.u = (uint32_t)(int32_t)off;
+        }
+      }
+      return 0;
+    }
     default: return -1;
   }
 }
@@ -945,6 +968,47 @@ CGoCallResHandle HyperLogLog(DimensionVector prev, DimensionVector cur, uint32_t
     copy_dim_row(prev.DimValues, cur.DimValues, prev.NumDimsPerDimWidth, prev.VectorCapacity,
                  prev.VectorCapacity, cur.IndexVector[r], (uint32_t)r);
   return ok(resSize);
+}
+
+/* ------------------------------------------------------------------------------------------
+ * HashLookup — query/hash_lookup.cu:70-157, HashLookupFunctor query/functor.hpp:1173-1266
+ * ---------------------------------------------------------------------------------------- */
+CGoCallResHandle HashLookup(InputVector input, RecordID *output, uint32_t *indexVector, int n, uint32_t *baseCounts,
+                            uint32_t startCount, CuckooHashIndex h, void *s, int d) {
+  (void)s; (void)d;
+  const int cellBytes = 8 + h.keyBytes + 1;
+  const int bucketBytes = HASH_BUCKET_SIZE * cellBytes;
+  const int offSig = HASH_BUCKET_SIZE * 8, offKey = offSig + HASH_BUCKET_SIZE;
+  uint8_t *stash = h.buckets + (size_t)bucketBytes * h.numBuckets;
+  for (int i = 0; i < n; i++) {
+    cell_t c;
+    RecordID none = {0, 0};
+    output[i] = none;
+    if (read_input(&input, (uint32_t)i, indexVector, baseCounts, startCount, &c) < 0) return fail("HashLookup: unsupported input");
+    if (!c.valid) continue;
+    uint8_t key[16];
+    memset(key, 0, sizeof(key));
+    if (c.k == K_UUID) memcpy(key, &c.uuid, 16); else if (c.k == K_I64) memcpy(key, &c.v.l, 8);
+    else if (c.k == K_BOOL) key[0] = c.v.b; else memcpy(key, &c.v.u, 4);
+    bool found = false;
+    for (int t = 0; t < h.numHashes && !found; t++) {
+      uint32_t hv = oracle_murmur3_32(key, h.keyBytes, h.seeds[t]);
+      uint8_t *bucket = h.buckets + (size_t)(hv % (uint32_t)h.numBuckets) * bucketBytes;
+      uint8_t sig = (uint8_t)(hv >> 24);
+      if (sig < 1) sig = 1;
+      for (int j = 0; j < HASH_BUCKET_SIZE && !found; j++)
+        if (bucket[offSig + j] == sig && memcmp(bucket + offKey + j * h.keyBytes, key, h.keyBytes) == 0) {
+          memcpy(&output[i], bucket + 8 * j, 8);
+          found = true;
+        }
+    }
+    for (int j = 0; j < HASH_STASH_SIZE && !found; j++)
+      if (stash[offSig + j] != 0 && memcmp(stash + offKey + j * h.keyBytes, key, h.keyBytes) == 0) {
+        memcpy(&output[i], stash + 8 * j, 8);
+        found = true;
+      }
+  }
+  return ok(n);
 }
 
 CGoCallResHandle BootstrapDevice(void) { return ok(0); }

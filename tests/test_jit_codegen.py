@@ -30,6 +30,17 @@ def _dry_run(lib, q, rows=100000, start_bit=0, expected_groups=0, base_counts=No
         p.BaseCounts = base_counts
     for col, (lo, hi) in (ranges or {}).items():
         p.Ranges[col].Known, p.Ranges[col].Min, p.Ranges[col].Max = 1, lo, hi
+    keep = []
+    if getattr(q, "joins", None):   # joined dimension tables: fake device addresses, real host-side batch arrays
+        p.NumForeignTables = len(q.joins)
+        for t, j in enumerate(q.joins):
+            p.ForeignTables[t].JoinColumn = j.on.index
+            p.ForeignTables[t].Index = j.table.hash_index()
+        p.NumForeignColumns = len(q.foreign_columns)
+        for k, (t, col, tz) in enumerate(q.foreign_columns):
+            f, arr = q.joins[t].table.foreign_column(col, None, 0x7E0000000000 if tz else None, 12 if tz else 0)
+            keep.append(arr)
+            p.ForeignColumns[k].Table, p.ForeignColumns[k].Column = t, f
     src = C.c_char_p()
     h = fn(q.agg_spec(expected_groups), C.byref(p), C.byref(src))
     if h.pStrErr:
@@ -191,3 +202,16 @@ def test_zone_map_selects_direct_indexed_aggregation():
     for name, qq in list(T.queries().items()) + list(T.avg_queries().items()):
         size, s2 = _dry_run(lib, qq, ranges=DAY_RANGES)
         assert size > 0, name
+
+
+def test_join_queries_specialise():
+    """Plans that read joined dimension tables (cuckoo probe + foreign-column gather inside the fused kernel) compile."""
+    import harness as H
+    import test_joins as TJ
+    lib = A.load_engine()
+    orc = H.get_backend("oracle")            # host memory stands in for the device buffers: nothing is dereferenced
+    table, _ = TJ._dimension_table(orc)
+    for name, q in TJ.join_queries(table, 0x7E0000000000, 12).items():
+        size, src = _dry_run(lib, q)
+        assert size > 0, name
+        assert "cuckooLookup(P.join->tables[0]" in src and "foreignLoad(P.join->cols[" in src
