@@ -46,7 +46,7 @@ int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *mea
 // ---------------------------------------------------------------------------------------
 constexpr int R = 4;  // rows per quad
 // status word of the single-launch finalize / of an exchange part
-enum SmallFinalizeStatus : uint32_t { SF_OK = 0, SF_TOO_MANY = 1, SF_TABLE_OVERFLOW = 2, SF_OUTPUT_TOO_SMALL = 3, SF_PART_TRUNCATED = 4 };
+enum SmallFinalizeStatus : uint32_t { SF_OK = 0, SF_TOO_MANY = 1, SF_TABLE_OVERFLOW = 2, SF_OUTPUT_TOO_SMALL = 3, SF_PART_TRUNCATED = 4, SF_UNSETTLED = 5 };
 
 __device__ __forceinline__ void cvtVec(uint32_t (&v)[R], ValClass from, ValClass to) {
   if (from == to) return;
@@ -454,19 +454,36 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   __syncthreads();
 
   const uint32_t quadsPerTile = P.tileRows / R;
+  // Growth of the group table (see jit_kernel_tail.cuh): this kernel stops at CTA granularity — thread 0 looks at the
+  // STOP flag before every tile — and records the iterations it has folded; a resumed launch starts there.
+  __shared__ uint32_t sStop;
+  const uint32_t progIdx = blockIdx.x * kProgressWarps;
+  uint32_t foldedUntil = 0xFFFFFFFFu;
   // ---- staged full tiles: tile t handled by CTA (t mod gridDim), ring of kStages buffers ----
   if (P.staged && P.numFullTiles > 0) {
     const uint32_t first = blockIdx.x, step = gridDim.x;
-    if (threadIdx.x == 0) {
+    const uint32_t startIt = P.resume ? G.progress[progIdx] : 0u;
+    if (threadIdx.x == 0 && startIt != 0xFFFFFFFFu) {
       for (uint32_t s = 0; s < P.numStages; s++) {
-        uint32_t t = first + s * step;
+        uint32_t t = first + (startIt + s) * step;
         if (t < P.numFullTiles) issueTile(P, t, stages + (size_t)s * P.stageBytes, &bars[s]);
       }
     }
-    uint32_t it = 0;
-    for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
+    uint32_t it = 0, drainEnd = 0xFFFFFFFFu;
+    bool draining = false;
+    for (uint32_t t = first + startIt * step; startIt != 0xFFFFFFFFu && t < P.numFullTiles && it < drainEnd; t += step, it++) {
       const uint32_t s = it % P.numStages, parity = (it / P.numStages) & 1;
+      if (!draining) {
+        if (threadIdx.x == 0) sStop = *reinterpret_cast<volatile uint32_t *>(&G.counters[3]);
+        __syncthreads();
+        if (sStop != 0u && P.hll != 2) {   // stop folding; the tiles already in flight are still waited for
+          draining = true;
+          foldedUntil = startIt + it;
+          drainEnd = it + P.numStages;
+        }
+      }
       mbarWait(&bars[s], parity);
+      if (draining) continue;
       const uint8_t *stage = stages + (size_t)s * P.stageBytes;
       // shared-table admission is decided per tile (uniform in the CTA)
       const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (P.smemSlots / 4) * 3;
@@ -479,8 +496,17 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
       }
     }
   }
+  if (threadIdx.x == 0) G.progress[progIdx] = foldedUntil;
   // ---- rows not covered by staged tiles (tail, or the whole batch on the direct path) --------
-  {
+  // (every CTA folds its share of them once: progress[progIdx + 1] says so to a resumed launch; a launch that found the
+  // table at its threshold leaves its share to the next one.  The host makes room for direct-path batches up front.)
+  if (threadIdx.x == 0) {
+    if (!P.resume) G.progress[progIdx + 1] = 0u;
+    sStop = (P.hll != 2 && *reinterpret_cast<volatile uint32_t *>(&G.counters[3]) != 0u) || G.progress[progIdx + 1] != 0u;
+    if (!sStop) G.progress[progIdx + 1] = 1u;
+  }
+  __syncthreads();
+  if (!sStop) {
     const uint32_t begin = P.staged ? P.numFullTiles * P.tileRows : P.tailBegin;
     const uint32_t quads = (P.numRows - begin + R - 1) / R;
     const bool allowClaim = true;
@@ -790,6 +816,7 @@ __global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constan
   uint32_t status = SF_OK;
   if (G.counters[1]) status = SF_TABLE_OVERFLOW;
   else if (G.counters[2]) status = SF_PART_TRUNCATED;   // AggStateMergeParts met a part that did not hold all its rows
+  else if (G.counters[3] || G.counters[4]) status = SF_UNSETTLED;   // stopped at the growth threshold / rows parked: the host settles first
   else if (n > (uint32_t)kSmallFinalizeMax) status = SF_TOO_MANY;
   else if (!A.ordered && n > (uint32_t)A.outCapacity) status = SF_OUTPUT_TOO_SMALL;
   if (status != SF_OK || n == 0) {
@@ -914,6 +941,7 @@ struct AggState {
   void *mem;               // single allocation behind the table
   unsigned long long *ctaAcc;  // [kMaxGridCtas][8192] private accumulator slices of the fused kernel's CTAs
   unsigned long long *denseAcc = nullptr;  // [kGlobalDenseMaxSlots] shared accumulators of the global dense form (lazy)
+  uint64_t occUpper = 0;                   // host-side upper bound of the occupied slots (exact after a synchronise)
   uint8_t *smallScratch = nullptr;         // single-launch finalize: hash / index ping-pong arrays (in `mem`)
   uint32_t *resultDev = nullptr;           // [0] groups, [1] status, [2] claimed slots of the last single-launch finalize
   uint32_t *resultHost = nullptr;          // the same three words in mapped pinned host memory
@@ -953,7 +981,9 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   const size_t regBytes = st->hllDense ? cap * kHllRegisters * sizeof(uint32_t) : 0;
   const size_t claimedBytes = (cap * 4 + 255) / 256 * 256;
   const size_t smallBytes = (size_t)kSmallFinalizeMax * (8 + 8 + 4 + 4);
-  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes + regBytes + claimedBytes + smallBytes;
+  const size_t progressBytes = ((size_t)(kProgressTail + 1) * 4 + 255) / 256 * 256;
+  const size_t spillBytes = (size_t)kSpillCap * sizeof(SpillEntry);
+  size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes + regBytes + claimedBytes + smallBytes + progressBytes + spillBytes;
   void *mem = nullptr;
   CGoCallResHandle h = deviceMalloc(&mem, bytes);
   if (h.pStrErr) { std::string m(h.pStrErr); free((void *)h.pStrErr); throw EngineError(m); }
@@ -970,6 +1000,10 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   uint8_t *tail = p + 256 + cap * 16 + (rows ? cap * 32 : 0) + ctaAccBytes + regBytes;
   st->table.claimed = reinterpret_cast<uint32_t *>(tail);
   st->smallScratch = tail + claimedBytes;
+  st->table.progress = reinterpret_cast<uint32_t *>(tail + claimedBytes + smallBytes);
+  st->table.spill = reinterpret_cast<SpillEntry *>(tail + claimedBytes + smallBytes + progressBytes);
+  // half full = time to grow (the dense HLL directory does not grow: its register arrays are sized with it)
+  st->table.growAt = st->hllDense ? 0xFFFFFFFFu : (uint32_t)(cap / 2);
   st->resultDev = st->table.counters + 8;   // inside the 256-byte header
   if (!st->resultHost) {
     ARES_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&st->resultHost), 64, cudaHostAllocMapped));
@@ -1018,6 +1052,10 @@ static AggState *createState(const AggSpec &spec, cudaStream_t s, int device) {
     size_t want = (size_t)spec.ExpectedGroups * 2;
     size_t cap = (size_t)1 << 21;
     while (cap < want) cap <<= 1;
+    if (const char *e = getenv("ARESDB_B200_TABLE_SLOTS")) {   // tests: start small so that the table has to grow
+      const long v = atol(e);
+      if (v >= 1024 && (v & (v - 1)) == 0) cap = (size_t)v;
+    }
     if (st->hllDense) cap = kHllDenseSlots;
     allocTable(st, cap, s);
   } catch (...) {
@@ -1420,13 +1458,109 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   return 128 + (size_t)P.tableBytes + stageBytes * P.numStages;
 }
 
+// ---------------------------------------------------------------------------------------
+// growth of the group table
+// ---------------------------------------------------------------------------------------
+// The reference sizes its hash map at 2 x rows for every batch and so never runs out (query/hash_reduction.cu:211-292);
+// here the table starts L2-sized and doubles when it is half full.  Kernels notice on the device (DevTable::growAt
+// raises the STOP flag at claim time): tile kernels whose launch the host waits for drain and are resumed after the
+// growth; kernels the host does not wait for (direct-indexed ones) park new groups in the spill list; launches that
+// cannot be resumed (merges, folds, the direct path) get their room up front.
+__global__ void __launch_bounds__(256) rehashKernel(DevTable oldG, uint32_t n, DevTable newG) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const uint32_t slot = oldG.claimed[i];
+    const uint32_t to = globalFindOrClaim(newG, oldG.keys[slot], oldG.rows ? &oldG.rows[(size_t)slot * 4] : nullptr);
+    if (to != 0xFFFFFFFFu) newG.acc[to] = oldG.acc[slot];
+  }
+}
+
+__global__ void __launch_bounds__(256) mergeSpillKernel(DevTable G, uint32_t n, AggOp op) {
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const SpillEntry e = G.spill[i];
+    globalUpdate(G, op, e.key, G.rows ? e.row : nullptr, e.val);
+  }
+}
+
+struct TableCounters { uint32_t occupied, overflow, truncated, stop, spilled, spillOverflow; };
+static void checkOverflow(AggState *st, const uint32_t counters[2]);
+
+static TableCounters readCounters(AggState *st, cudaStream_t s) {
+  TableCounters c;
+  ARES_CUDA(cudaMemcpyAsync(&c, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  st->occUpper = c.occupied;
+  return c;
+}
+
+// New table of `newCap` slots holding the groups of the old one; STOP flag cleared.
+static void growTable(AggState *st, size_t newCap, cudaStream_t s) {
+  if (st->hllDense) throw EngineError("dense HLL state: more than " + std::to_string(st->capacity) + " dimension groups");
+  if (newCap > ((size_t)1 << 31)) throw EngineError("group table cannot grow beyond 2^31 slots");
+  void *oldMem = st->mem;
+  const DevTable oldG = st->table;
+  uint32_t header[64];
+  ARES_CUDA(cudaMemcpyAsync(header, oldG.counters, sizeof(header), cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  const uint32_t n = header[0];
+  allocTable(st, newCap, s);   // fresh table (keys empty, counters 0), new claim list / progress / spill areas
+  if (n) {
+    int blocks = divUp(n, 256);
+    if (blocks > smCount() * 8) blocks = smCount() * 8;
+    rehashKernel<<<blocks, 256, 0, s>>>(oldG, n, st->table);
+    checkLastError("rehash");
+  }
+  // progress of a stopped launch and parked rows survive the move
+  ARES_CUDA(cudaMemcpyAsync(st->table.progress, oldG.progress, (size_t)(kProgressTail + 1) * 4, cudaMemcpyDeviceToDevice, s));
+  const uint32_t spilled = header[4] < kSpillCap ? header[4] : kSpillCap;
+  if (spilled) ARES_CUDA(cudaMemcpyAsync(st->table.spill, oldG.spill, (size_t)spilled * sizeof(SpillEntry), cudaMemcpyDeviceToDevice, s));
+  uint32_t keep[2] = {header[4], header[5]};
+  ARES_CUDA(cudaMemcpyAsync(st->table.counters + 4, keep, sizeof(keep), cudaMemcpyHostToDevice, s));
+  ARES_CUDA(cudaMemcpyAsync(st->table.counters + 1, header + 1, 2 * sizeof(uint32_t), cudaMemcpyHostToDevice, s));   // overflow / truncated
+  ARES_CUDA(cudaStreamSynchronize(s));
+  deviceFree(oldMem);
+  st->occUpper = n;
+}
+
+// Folds parked rows (growing first when needed); loud when more rows were parked than the list holds.
+static void settleTable(AggState *st, cudaStream_t s) {
+  TableCounters c = readCounters(st, s);
+  if (c.spillOverflow)
+    throw EngineError("group table: more than " + std::to_string(kSpillCap) + " rows of new groups arrived from direct-indexed batches while the "
+                      "table was full (a zone map far off the data); recreate the AggState with a larger AggSpec.ExpectedGroups and replay");
+  if (c.overflow) checkOverflow(st, &c.occupied);
+  if (!c.stop && !c.spilled) return;
+  size_t cap = st->capacity;
+  while ((uint64_t)c.occupied + c.spilled > cap / 4) cap <<= 1;   // settle at a quarter full at most
+  if (cap != st->capacity || c.stop) growTable(st, cap == st->capacity ? cap << 1 : cap, s);
+  if (c.spilled) {
+    int blocks = divUp(c.spilled, 256);
+    mergeSpillKernel<<<blocks, 256, 0, s>>>(st->table, c.spilled, st->op);
+    checkLastError("mergeSpill");
+    ARES_CUDA(cudaMemsetAsync(st->table.counters + 4, 0, 8, s));
+    readCounters(st, s);
+  }
+}
+
+// Room for a launch that cannot be resumed and inserts at most `bound` new groups.
+static void ensureRoom(AggState *st, uint64_t bound, cudaStream_t s) {
+  if (st->hllDense) return;
+  if (st->occUpper + bound < st->table.growAt) { st->occUpper += bound; return; }
+  settleTable(st, s);   // exact occupancy (and nothing parked)
+  size_t cap = st->capacity;
+  while (st->occUpper + bound >= cap / 2) cap <<= 1;
+  if (cap != st->capacity) growTable(st, cap, s);
+  st->occUpper += bound;
+}
+
 static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   if (bp.NumRows == 0) return;
   if (bp.NumRows > 0x7FFFFFFFu) throw EngineError("a batch holds at most 2^31-1 rows");
   static thread_local DevPlan P;  // ~3 KB; passed by value as a __grid_constant__ parameter
   compilePlan(st, bp, P);
   P.tailBegin = 0;
-  P.ctaAcc = st->ctaAcc;
+  P.resume = 0;
   // archive batches: expand the RLE columns the plan reads (ARESDB_B200_EXPAND_RLE=0 keeps the positional path)
   std::vector<std::unique_ptr<Scratch>> expanded;
   static const bool expandRle = [] { const char *e = getenv("ARESDB_B200_EXPAND_RLE"); return !(e && e[0] == '0'); }();
@@ -1474,6 +1608,12 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
     P.join = joinMem->as<DevJoin>();
   }
   size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
+  // room in the group table (see "growth of the group table"): the direct path and the direct-indexed kernels are not
+  // waited for, so what they may insert is reserved up front (flush of the CTA slots / fold of the global slot array;
+  // out-of-range rows park); hash-table tile kernels are checked after the launch and resumed when they stopped.
+  const bool resumable = P.staged && P.denseNd == 0 && !st->hllDense;
+  if (!resumable && !st->hllDense) ensureRoom(st, P.staged ? (uint64_t)P.denseTotal : (uint64_t)P.numRows, s);
+  P.ctaAcc = st->ctaAcc;   // (after a possible growth: the slices live in the table's allocation)
   static bool attrSet[64] = {false};
   if (!attrSet[st->device & 63]) {
     ARES_CUDA(cudaFuncSetAttribute(fusedBatchKernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBudget));
@@ -1500,34 +1640,48 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   }
   // the specialised kernel covers the staged tiles AND the tail; the interpreter below is the
   // generic fallback (unaligned / RLE columns, NVRTC unavailable or disabled)
-  if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) {
-    if (P.denseGlobal) {
-      DenseFold F;
-      memset(&F, 0, sizeof(F));
-      uint32_t stride = 1;
-      for (int k = 0; k < P.denseNd; k++) {
-        const DevInst &I = P.insts[P.denseInst[k]];
-        F.lo[k] = P.denseLo[k]; F.cnt[k] = P.denseCnt[k]; F.step[k] = P.denseStep[k]; F.stride[k] = stride;
-        F.rowOff[k] = I.rowOff; F.width[k] = I.width; F.nullOff[k] = I.nullOff;
-        stride *= P.denseCnt[k] + 1;
+  for (;;) {
+    bool checkAfter = false;   // a hash-table tile kernel ran: wait for it and resume it if the table stopped it
+    if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) {
+      checkAfter = P.denseNd == 0 && !st->hllDense;
+      if (P.denseGlobal) {
+        DenseFold F;
+        memset(&F, 0, sizeof(F));
+        uint32_t stride = 1;
+        for (int k = 0; k < P.denseNd; k++) {
+          const DevInst &I = P.insts[P.denseInst[k]];
+          F.lo[k] = P.denseLo[k]; F.cnt[k] = P.denseCnt[k]; F.step[k] = P.denseStep[k]; F.stride[k] = stride;
+          F.rowOff[k] = I.rowOff; F.width[k] = I.width; F.nullOff[k] = I.nullOff;
+          stride *= P.denseCnt[k] + 1;
+        }
+        F.nd = P.denseNd; F.total = P.denseTotal;
+        F.keyMode = P.keyMode; F.hashBits = P.hashBits; F.rowBytes = P.rowBytes; F.op = P.aggOp;
+        F.neutral = P.accNeutral;
+        int blocks = divUp((int64_t)P.denseTotal, 256);
+        if (blocks > smCount() * 8) blocks = smCount() * 8;
+        denseFoldKernel<<<blocks, 256, 0, s>>>(st->denseAcc, F, st->table);
+        checkLastError("denseFold");
       }
-      F.nd = P.denseNd; F.total = P.denseTotal;
-      F.keyMode = P.keyMode; F.hashBits = P.hashBits; F.rowBytes = P.rowBytes; F.op = P.aggOp;
-      F.neutral = P.accNeutral;
-      int blocks = divUp((int64_t)P.denseTotal, 256);
-      if (blocks > smCount() * 8) blocks = smCount() * 8;
-      denseFoldKernel<<<blocks, 256, 0, s>>>(st->denseAcc, F, st->table);
-      checkLastError("denseFold");
+    } else {
+      if (P.denseNd != 0) {  // the interpreter needs the key-table layout
+        smemBytes = layoutStages(P, st->spec.ExpectedGroups, /*allowDense=*/false);
+        grid = gridFor();
+      }
+      checkAfter = P.staged && !st->hllDense;
+      if (st->keyMode == KEY_HASHED) fusedBatchKernel<true><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
+      else fusedBatchKernel<false><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
+      checkLastError("ExecuteBatchPlan");
     }
-    return;
+    if (!checkAfter) return;
+    const TableCounters c = readCounters(st, s);
+    if (c.overflow) checkOverflow(st, &c.occupied);
+    if (!c.stop) return;
+    size_t cap = st->capacity << 1;
+    while ((uint64_t)c.occupied >= cap / 4) cap <<= 1;   // resume at a quarter full at most
+    growTable(st, cap, s);
+    P.resume = 1;
+    P.ctaAcc = st->ctaAcc;
   }
-  if (P.denseNd != 0) {  // the interpreter needs the key-table layout
-    smemBytes = layoutStages(P, st->spec.ExpectedGroups, /*allowDense=*/false);
-    grid = gridFor();
-  }
-  if (st->keyMode == KEY_HASHED) fusedBatchKernel<true><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
-  else fusedBatchKernel<false><<<grid, kFusedThreads, smemBytes, s>>>(P, st->table);
-  checkLastError("ExecuteBatchPlan");
 }
 
 static void mergeRows(AggState *st, const DimensionVector &in, const uint8_t *values, int length, cudaStream_t s) {
@@ -1535,6 +1689,7 @@ static void mergeRows(AggState *st, const DimensionVector &in, const uint8_t *va
   for (int i = 0; i < NUM_DIM_WIDTH; i++)
     if (in.NumDimsPerDimWidth[i] != st->spec.NumDimsPerDimWidth[i]) throw EngineError("dimension layout differs from AggSpec");
   DimLayout L = makeDimLayout(in.NumDimsPerDimWidth, in.VectorCapacity);
+  ensureRoom(st, (uint64_t)length, s);
   int blocks = divUp(length, 256);
   if (blocks > smCount() * 8) blocks = smCount() * 8;
   mergeRowsKernel<<<blocks, 256, 0, s>>>(in.DimValues, L, values, st->measWidth, st->op, length, st->keyMode,
@@ -1552,11 +1707,13 @@ static void checkOverflow(AggState *st, const uint32_t counters[2]) {
 }
 
 static int64_t groupCount(AggState *st, cudaStream_t s) {
-  uint32_t c[2];
-  ARES_CUDA(cudaMemcpyAsync(c, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
-  ARES_CUDA(cudaStreamSynchronize(s));
-  checkOverflow(st, c);
-  return c[0];
+  TableCounters c = readCounters(st, s);
+  if (c.stop || c.spilled || c.spillOverflow) {
+    settleTable(st, s);
+    c = readCounters(st, s);
+  }
+  checkOverflow(st, &c.occupied);
+  return c.occupied;
 }
 
 // Dense HLL state -> carried rows.  Fills `block` (one dim row per group, capacity = groups, hash
@@ -1653,7 +1810,11 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
     finalizeSmallKernel<<<1, 1024, 0, s>>>(A);
     checkLastError("finalizeSmall");
     ARES_CUDA(cudaStreamSynchronize(s));
-    const uint32_t status = st->resultHost[1];
+    uint32_t status = st->resultHost[1];
+    if (status == SF_UNSETTLED) {   // grow / fold the parked rows, then once more (the table moved: new pointers)
+      settleTable(st, s);
+      return finalize(st, out, outValues, s, ordered);
+    }
     if (status == SF_OK) return st->resultHost[0];
     if (status == SF_TABLE_OVERFLOW) { const uint32_t c[2] = {st->resultHost[2], 1}; checkOverflow(st, c); }
     if (status == SF_OUTPUT_TOO_SMALL) throw EngineError("output DimensionVector capacity is smaller than the number of groups");
@@ -1864,6 +2025,7 @@ CGoCallResHandle AggStateMergeParts(void *state, const uint8_t *parts, int numPa
   return guarded("AggStateMergeParts", device, [&]() -> int64_t {
     AggState *st = asState(state);
     if (numParts <= 0) return 0;
+    ensureRoom(st, (uint64_t)numParts * (uint64_t)capRows, (cudaStream_t)cudaStream);
     DimLayout L = makeDimLayout(st->spec.NumDimsPerDimWidth, capRows);
     mergePartsKernel<<<smCount() * 2, 256, 0, (cudaStream_t)cudaStream>>>(parts, numParts, partStride, dimOffset, valuesOffset, L,
                                                                          st->measWidth, st->op, st->keyMode, (uint8_t)st->hashBits,
@@ -1890,6 +2052,7 @@ CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device) {
     resetClaimedKernel<<<smCount() * 4, 256, 0, s>>>(st->table, st->accNeutral);
     checkLastError("AggStateReset");
     ARES_CUDA(cudaMemsetAsync(st->table.counters, 0, 256, s));
+    st->occUpper = 0;
     return 0;
   });
 }

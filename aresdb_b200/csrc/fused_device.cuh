@@ -8,16 +8,31 @@
 namespace aresb {
 
 constexpr int kMaxStages = 4;
+constexpr int kProgressWarps = 32;         // progress slots per CTA (one per warp)
+constexpr int kProgressCtas = 160;         // = kMaxGridCtas
+constexpr int kProgressTail = kProgressCtas * kProgressWarps;   // index of the "tail rows done" flag
 constexpr uint32_t kSmemProbeLimit = 8;
 constexpr uint32_t kGlobalProbeLimit = 8192;
 constexpr unsigned long long kEmptyKey = ~0ull;
 constexpr uint64_t kMix = 0x9E3779B97F4A7C15ull;
 
+// A row (already reduced to key + measure) that arrived while the table was at its growth threshold, from a kernel
+// whose launches the host does not wait for (direct-indexed kernels: their flush and their out-of-range rows): folded
+// into the table after it has grown, at the state's next synchronising call.
+struct SpillEntry { unsigned long long key; uint64_t row[4]; uint64_t val; };
+constexpr uint32_t kSpillCap = 65536;
+constexpr uint32_t kSlotSpill = 0xFFFFFFFEu;
+
 struct DevTable {
   unsigned long long *keys;
   unsigned long long *acc;
   uint64_t *rows;        // [capacity][4] packed rows, wide (hashed) keys only
-  uint32_t *counters;    // [0] occupied slots, [1] overflow flag
+  uint32_t *counters;    // [0] occupied slots, [1] overflow flag, [2] truncated exchange part, [3] STOP: the table has
+                         // reached growAt — consumers finish their tile and drain; the host grows the table and resumes
+  uint32_t *progress;    // [kMaxGridCtas * 32 + 1] tile iterations each consumer warp has folded (resume point), tail flag
+  uint32_t growAt;       // claim ordinal at which the stop flag is raised (capacity / 2; 0xFFFFFFFF: never)
+  struct SpillEntry *spill;  // [kSpillCap] rows of kernels that cannot be resumed, parked while the table is full
+                         // (counters[4] = entries, counters[5] = spill overflow)
   uint32_t *claimed;     // [capacity] slot index of the i-th claimed group (claim order): finalize / reset / export
                          // walk this list instead of scanning the table
   uint32_t mask;
@@ -72,13 +87,16 @@ __device__ __forceinline__ uint32_t globalHome(const DevTable &G, unsigned long 
   return (mixKey(key) >> 3) & G.mask;
 }
 
-static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww) {
+// spillWhenStopped: a NEW key is not claimed once the stop flag is up (kSlotSpill: the caller parks the row).
+static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, unsigned long long key, const uint64_t *roww,
+                                                          bool spillWhenStopped = false) {
   uint32_t slot = globalHome(G, key);
 #pragma unroll 1
   for (uint32_t probe = 0; probe < kGlobalProbeLimit; probe++) {
     unsigned long long k = *reinterpret_cast<volatile unsigned long long *>(&G.keys[slot]);
     if (k == key) return slot;
     if (k == kEmptyKey) {
+      if (spillWhenStopped && *reinterpret_cast<volatile uint32_t *>(&G.counters[3]) != 0u) return kSlotSpill;
       unsigned long long old = atomicCAS(&G.keys[slot], kEmptyKey, key);
       if (old == kEmptyKey) {
         // claim ordinal: the lanes of the warp that claim in the same step share ONE add on the (single-address) counter
@@ -86,7 +104,9 @@ static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, uns
         uint32_t base = 0;
         if (lane == leader) base = atomicAdd(&G.counters[0], (uint32_t)__popc(peers));
         base = __shfl_sync(peers, base, leader);
-        G.claimed[base + __popc(peers & ((1u << lane) - 1u))] = slot;   // every slot is claimed once: the ordinal is < capacity
+        const uint32_t ord = base + __popc(peers & ((1u << lane) - 1u));
+        G.claimed[ord] = slot;   // every slot is claimed once: the ordinal is < capacity
+        if (ord >= G.growAt) *reinterpret_cast<volatile uint32_t *>(&G.counters[3]) = 1u;   // filling up: stop consuming tiles
         if (roww != nullptr && G.rows != nullptr) {
 #pragma unroll
           for (int i = 0; i < 4; i++) G.rows[(size_t)slot * 4 + i] = roww[i];
@@ -102,8 +122,21 @@ static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, uns
 }
 
 __device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsigned long long key, const uint64_t *roww,
-                                             uint64_t val) {
-  uint32_t slot = globalFindOrClaim(G, key, roww);
+                                             uint64_t val, bool spillWhenStopped = false) {
+  uint32_t slot = globalFindOrClaim(G, key, roww, spillWhenStopped);
+  if (slot == kSlotSpill) {
+    const uint32_t i = atomicAdd(&G.counters[4], 1u);
+    if (i < kSpillCap) {
+      SpillEntry e;
+      e.key = key; e.val = val;
+#pragma unroll
+      for (int w = 0; w < 4; w++) e.row[w] = roww ? roww[w] : 0;
+      G.spill[i] = e;
+    } else {
+      atomicExch(&G.counters[5], 1u);
+    }
+    return;
+  }
   if (slot != 0xFFFFFFFFu) aggAtomic(op, &G.acc[slot], val);
 }
 

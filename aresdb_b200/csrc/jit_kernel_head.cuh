@@ -42,6 +42,7 @@ struct JitParams {
   float fxScale;                          //                     2^S (a float sum's rows are added as integers x * 2^S)
   uint32_t fxPad;
   const DevJoin *join;                    // joined dimension tables (join.cuh), null without joins
+  uint32_t resume;                        // 1: second launch of the same batch after the table grew (progress[] says where)
 };
 
 

@@ -32,7 +32,7 @@ __device__ __forceinline__ unsigned long long jitKeyOf(const uint64_t (&key)[4][
 static __device__ __noinline__ void denseSlowRow(const JitParams &P, const uint32_t (&dvr)[JIT_ND], uint32_t vb, uint64_t meas) {
   uint64_t key[JIT_KW];
   densePack(dvr, vb, key);
-  globalUpdate(P.G, (AggOp)JIT_AGG_OP, jitKeyOfRow(key), JIT_KW == 1 ? nullptr : key, meas);
+  globalUpdate(P.G, (AggOp)JIT_AGG_OP, jitKeyOfRow(key), JIT_KW == 1 ? nullptr : key, meas, /*spillWhenStopped=*/true);
 }
 
 // Where the accumulators of the direct-indexed slots live (JIT_DENSE_ACC, chosen by the host):
@@ -291,6 +291,19 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   constexpr uint32_t kConsumerThreads = JIT_THREADS - 32;
   static_assert(JIT_TILE_ROWS == kConsumerThreads * 4, "one quad per consumer thread");
   const uint32_t first = blockIdx.x, step = gridDim.x;
+  // Growth of the group table (AggState: capacity doubles when half full).  The claim that crosses DevTable::growAt
+  // raises the STOP flag; a consumer warp that sees it before a tile stops folding rows ("drains": it keeps the ring
+  // protocol alive but touches nothing), and records how many tile iterations it has folded.  The host then grows the
+  // table and launches the kernel again with `resume`: every warp skips the iterations it already folded.  Nothing is
+  // lost and nothing is counted twice; the unit is one warp's 128 rows of one tile.
+  // (Direct-indexed kernels never drain — the host does not wait for them: their out-of-range rows and their flush park
+  // new groups in DevTable::spill while the table is at its threshold.)
+  constexpr bool kCanDrain = JIT_DENSE == 0;
+  const uint32_t progIdx = blockIdx.x * kProgressWarps + (threadIdx.x >> 5);
+  uint32_t myStart = 0;
+  if (kCanDrain && P.resume) myStart = P.G.progress[progIdx];
+  bool draining = false;
+  uint32_t foldedUntil = 0xFFFFFFFFu;   // iterations folded when the warp stopped (0xFFFFFFFF: all)
   if (threadIdx.x >= kConsumerThreads) {
     if (threadIdx.x == kConsumerThreads) {
       uint32_t it = 0;
@@ -304,7 +317,18 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     uint32_t it = 0;
     for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
       const uint32_t s = it % JIT_STAGES, parity = (it / JIT_STAGES) & 1;
+      // (read before the wait: the L2 round trip overlaps with it; a slightly older value only delays the stop by a tile)
+      const uint32_t stopFlag = kCanDrain ? *reinterpret_cast<volatile uint32_t *>(&P.G.counters[3]) : 0u;
       mbarWait(&bars[s], parity);
+      if (!draining && it >= myStart && stopFlag != 0u) {
+        draining = true;
+        foldedUntil = it;
+      }
+      if (draining || it < myStart) {   // nothing to fold: release the stage and move on
+        __syncwarp();
+        if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
+        continue;
+      }
       const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
       const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
       // the shared table is full and has turned away several times its size in rows: stop consulting it
@@ -329,10 +353,20 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
       if ((threadIdx.x & 31) == 0) mbarArrive(&empty[s]);
     }
   }
+  if (kCanDrain && threadIdx.x < kConsumerThreads && (threadIdx.x & 31) == 0) P.G.progress[progIdx] = foldedUntil;
   // ---- tail: the rows after the last full tile (< JIT_TILE_ROWS + 128) are copied into stage 0 by
   // the threads themselves, byte-exact (nothing beyond a column's last byte is touched), and go
-  // through the same rowEval.  One CTA does it; rows past the end are masked dead.
-  if (blockIdx.x == gridDim.x - 1) {
+  // through the same rowEval.  One CTA does it; rows past the end are masked dead.  (A stopped run leaves the tail to
+  // the resumed one: DevTable::progress[kProgressTail] records that it has been folded.)
+  __shared__ uint32_t sDoTail;
+  if (threadIdx.x == 0) {
+    if (kCanDrain && !P.resume && blockIdx.x == gridDim.x - 1) P.G.progress[kProgressTail] = 0u;   // a fresh batch
+    sDoTail = blockIdx.x == gridDim.x - 1 &&
+              (!kCanDrain || (*reinterpret_cast<volatile uint32_t *>(&P.G.counters[3]) == 0u && !(P.resume && P.G.progress[kProgressTail] != 0u)));
+  }
+  __syncthreads();
+  if (sDoTail) {
+    if (kCanDrain && threadIdx.x == 0) P.G.progress[kProgressTail] = 1u;
     uint32_t done = P.numFullTiles * JIT_TILE_ROWS;
     while (done < P.numRows) {
       __syncthreads();  // every warp has left the ring / the previous tail tile
@@ -400,8 +434,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     uint64_t key[JIT_KW];
     densePack(dvr, vb, key);
     const unsigned long long k = jitKeyOfRow(key);
-    if (JIT_DENSE_ACC != 1) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, accG);
-    if (JIT_DENSE_ACC != 0) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, accS);
+    // (the host does not wait for these kernels: when the table is at its growth threshold new groups are parked)
+    if (JIT_DENSE_ACC != 1) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, accG, true);
+    if (JIT_DENSE_ACC != 0) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, JIT_KW == 1 ? nullptr : key, accS, true);
   }
   return;
 #endif

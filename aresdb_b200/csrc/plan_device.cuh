@@ -94,6 +94,7 @@ struct DevPlan {
   uint8_t foreignClass[kMaxForeignCols];    // ValClass a read of foreign column k yields
   uint8_t pad2[1];
   const DevJoin *join;     // device copy of the tables' indexes and the foreign columns' batches
+  uint32_t resume;         // 1: relaunch of the same batch after the group table grew (DevTable::progress holds the resume points)
 };
 
 constexpr uint32_t kDenseMaxSlots = 8192;   // = slots of a CTA's accumulator slice in AggState::ctaAcc
