@@ -456,7 +456,7 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   const uint32_t quadsPerTile = P.tileRows / R;
   // Growth of the group table (see jit_kernel_tail.cuh): this kernel stops at CTA granularity — thread 0 looks at the
   // STOP flag before every tile — and records the iterations it has folded; a resumed launch starts there.
-  __shared__ uint32_t sStop;
+  volatile uint32_t &sStop = *reinterpret_cast<volatile uint32_t *>(smem + 72);   // header word (no static shared memory)
   const uint32_t progIdx = blockIdx.x * kProgressWarps;
   uint32_t foldedUntil = 0xFFFFFFFFu;
   // ---- staged full tiles: tile t handled by CTA (t mod gridDim), ring of kStages buffers ----

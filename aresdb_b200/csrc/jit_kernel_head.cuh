@@ -36,6 +36,8 @@ struct JitParams {
   // direct-indexed aggregation (JIT_DENSE): dimension k of a row has index (value or quotient) - dLo[k], valid when
   // below dCnt[k]; index dCnt[k] is the dimension's NULL; slot = sum_k index_k * dStride[k]; value = (dLo + index) * dStep
   uint32_t dLo[kJitMaxDenseDims], dCnt[kJitMaxDenseDims], dStride[kJitMaxDenseDims], dStep[kJitMaxDenseDims];
+  uint32_t dBase[kJitMaxDenseDims], dSpan[kJitMaxDenseDims], dMagic32[kJitMaxDenseDims];   // span division (see plan_device.cuh)
+  uint32_t dStrideB[kJitMaxDenseDims];   // dStride in the unit the fast path addresses slots in (bytes for the integer form: x 12)
   uint32_t dTotal, dReps, dRepStride;     // slots of one copy; lane-private copies (power of two), dRepStride slots apart
   unsigned long long *gAcc;               // JIT_DENSE == 2: the state's global accumulator array (dTotal slots in use)
   double fxInv;                           // JIT_DENSE_ACC == 4: 2^-S

@@ -27,12 +27,41 @@ __device__ __forceinline__ unsigned long long jitKeyOf(const uint64_t (&key)[4][
 
 #if JIT_DENSE
 // ---- direct-indexed aggregation (zone map known for every dimension, see jit.cu) --------------------
-// A row whose dimension values fall outside the announced ranges (or a NULL whose stored value is not the
-// canonical zero): the global hash table, keyed like every other path.
-static __device__ __noinline__ void denseSlowRow(const JitParams &P, const uint32_t (&dvr)[JIT_ND], uint32_t vb, uint64_t meas) {
-  uint64_t key[JIT_KW];
-  densePack(dvr, vb, key);
-  globalUpdate(P.G, (AggOp)JIT_AGG_OP, jitKeyOfRow(key), JIT_KW == 1 ? nullptr : key, meas, /*spillWhenStopped=*/true);
+// Quads the fast path could not finish — out of line, rare.  The fast path only says WHICH rows were inside the zone map
+// (inRange) and at which slots; everything else is recomputed here with full generality (rowEvalGeneric: alive mask,
+// packed key, converted measure), so that the fast path keeps no masks, keys or doubles alive:
+//   * alive rows outside the ranges (or a NULL whose stored value is not the canonical zero): the global hash table, keyed
+//     like every other path (new groups park in the spill list while the table is at its growth threshold);
+//   * rows inside whose value would leave a flag-less slot at its neutral element: the hash table as well;
+//   * integer form: rows inside whose value is off the 2^-S grid: added in double on the CTA's L2 slice at `slot`
+//     (-0.0, which would leave that half at its neutral element: the hash table).
+static __device__ __noinline__ void denseColdRows(const uint8_t *stage, uint32_t q, uint32_t row0, const JitParams &P, uint32_t nvalid,
+                                                  uint32_t inRange, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3,
+                                                  unsigned long long *tAcc) {
+  uint64_t key[4][JIT_KW], meas[4];
+  const uint32_t slot[4] = {s0, s1, s2, s3};
+  uint32_t alive = rowEvalGeneric(stage, q, row0, P, key, meas);
+  alive &= (1u << nvalid) - 1u;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    if (!((alive >> r) & 1u)) continue;
+    bool toHash = !((inRange >> r) & 1u);
+    if (!toHash) {
+      if (JIT_DENSE_ACC == 4 && JIT_DENSE != 2) {
+        const float x = (float)__longlong_as_double((long long)meas[r]);   // the measure is a float32 widened exactly
+        const float y = x * P.fxScale;
+        const bool onGrid = x > 0.0f && y < 4294967296.0f && __uint2float_rn(__float2uint_rz(y)) == y;
+        if (onGrid) continue;                                   // the fast path added its pieces
+        if (meas[r] != 0x8000000000000000ull) { aggAtomic((AggOp)JIT_AGG_OP, tAcc + slot[r], meas[r]); continue; }
+        toHash = true;                                          // -0.0
+      } else {
+        if (JIT_DENSE != 2 && JIT_DENSE_FLAGS) continue;        // flagged slots take every value
+        if (!JIT_DENSE_CHECK || meas[r] != P.accNeutral) continue;   // the fast path handled it
+        toHash = true;
+      }
+    }
+    if (toHash) globalUpdate(P.G, (AggOp)JIT_AGG_OP, jitKeyOfRow(key[r]), JIT_KW == 1 ? nullptr : key[r], meas[r], /*spillWhenStopped=*/true);
+  }
 }
 
 // Where the accumulators of the direct-indexed slots live (JIT_DENSE_ACC, chosen by the host):
@@ -40,7 +69,8 @@ static __device__ __noinline__ void denseSlowRow(const JitParams &P, const uint3
 //   1  shared memory (native ATOMS for 4-byte aggregates, a CAS loop for 8-byte ones);
 //   2  both: row positions 0-1 of a quad go to shared memory, 2-3 to the L2 slice, so that neither the SM's
 //      shared-memory atomic path nor its global-atomic path carries the whole stream; the flush adds the two halves;
-//   3  as 2 with three row positions in shared memory and one in the L2 slice.
+//   3  as 2 with three row positions in shared memory and one in the L2 slice;
+//   4  exact integer accumulation of a bounded float sum (three 32-bit counters per slot).
 constexpr uint32_t kDenseCap = JIT_SMEM_SLOTS;   // a multiple of 16; JIT_TABLE_BYTES >= 9 * kDenseCap
 // layout of the table region (dynamic shared memory + 128) in this mode: touched[kDenseCap] | acc[kDenseCap] (8 bytes each)
 __device__ __forceinline__ unsigned long long *denseSharedAcc() {
@@ -89,93 +119,74 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
   } else if (p) smemAtomic((AggOp)OP, generic, v);
 }
 
-__device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P,
-                                                  const bool (&fast)[4], const bool (&slow)[4], const uint32_t (&dslot)[4],
-                                                  const uint32_t (&dv)[4][JIT_ND], const uint32_t (&dvalid)[4], const uint64_t (&meas)[4],
+// `repOff`: this lane's copy of the slots (few slots are replicated per lane), in slots — loop invariant, computed once.
+__device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P, const uint8_t *stage,
+                                                  uint32_t q, uint32_t row0, uint32_t nvalid, uint32_t repOff, const bool (&fast)[4],
+                                                  bool cold, const uint32_t (&dslot)[4], const uint64_t (&meas)[4],
                                                   const uint32_t (&mraw)[4]) {
+  // slots: dslot + this lane's copy.  (Integer form: dslot arrives in BYTES — strides pre-multiplied by the 12-byte slot —
+  // and so does repOff; the slot index is only needed by the cold path.)
+  uint32_t s[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++) s[r] = dslot[r] + repOff;
   if (JIT_DENSE == 2) {
     // One accumulator array for the whole grid (more slots than a CTA holds).  No flags: a slot was reached iff it
     // differs from the aggregate's neutral element, so a row whose value would leave it there (-0.0 for float sums,
     // the extreme for min / max) goes down the hash path instead; the host only selects this form for aggregates
     // that cannot return to the neutral element otherwise.
-    bool later[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const bool f = fast[r] && (!JIT_DENSE_CHECK || meas[r] != P.accNeutral);
-      later[r] = slow[r] || (fast[r] && !f);
+      cold = cold || (fast[r] && !f);
       redGlobalPred<JIT_AGG_OP>(P.gAcc + dslot[r], meas[r], f);
     }
-    if (later[0] || later[1] || later[2] || later[3]) {
-#pragma unroll
-      for (int r = 0; r < 4; r++)
-        if (later[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
-    }
-    return;
-  }
-  const uint32_t rep = (threadIdx.x & (P.dReps - 1u)) * P.dRepStride;
-  uint32_t s[4];
-  bool go[4], later[4];
-#pragma unroll
-  for (int r = 0; r < 4; r++) {
-    s[r] = dslot[r] + rep;
-    // no flags: a row that would leave its slot at the neutral element goes down the hash path instead
-    go[r] = fast[r] && (JIT_DENSE_FLAGS || !JIT_DENSE_CHECK || meas[r] != P.accNeutral);
-    later[r] = slow[r] || (fast[r] && !go[r]);
-  }
-  if (JIT_DENSE_FLAGS) {
-#pragma unroll
-    for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], go[r]);
-  }
-  const uint32_t sAccAddr = touchedAddr + kDenseCap;
-  if (JIT_DENSE_ACC == 4) {
+  } else if (JIT_DENSE_ACC == 4) {
     // Exact integer accumulation of a float sum (jitAnalyzeDense): a slot is three 32-bit counters for the 11 / 11 / 10
     // bit pieces of x * 2^S, updated with fire-and-forget adds (nothing returns, nothing spins), and carries no flag —
-    // it was reached iff a counter is non-zero or its double half on the L2 slice left the neutral element.  Rows with
-    // x > 0 on the grid take that path.  The rest is rare and sits behind one branch: -0.0 (it would leave the double
-    // half at its neutral element) takes the hash path, everything else (zeros, NULL -> +0.0, negative, off the grid,
-    // beyond the announced maximum, NaN) is added in double.
-    const uint32_t fxAddr = touchedAddr;   // the table region holds only the counters in this mode
-    uint32_t ix[4];
-    bool onGrid[4];
-    bool rare = false;
+    // it was reached iff a counter is non-zero or its double half on the L2 slice left the neutral element.  A row is
+    // taken row by row — decide, then add — so that only one row's predicates are alive at a time: x > 0 on the grid
+    // (y = x * 2^S is an integer below 2^32: float -> u32 -> float gives y back) adds its three pieces.  Everything else
+    // in range (zeros, NULL -> +0.0, negative, off the grid, beyond the announced maximum, NaN, -0.0) is rare and is
+    // finished by denseColdRows.
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const float x = __uint_as_float(mraw[r]);
       const float y = x * P.fxScale;
-      ix[r] = __float2uint_rz(y);
-      onGrid[r] = fast[r] && x > 0.0f && y < 4294967296.0f && __uint2float_rn(ix[r]) == y;
-      rare = rare || slow[r] || (fast[r] && !onGrid[r]);
+      const uint32_t ix = __float2uint_rz(y);
+      const bool onGrid = fast[r] && x > 0.0f && y < 4294967296.0f && __uint2float_rn(ix) == y;
+      cold = cold || (fast[r] && !onGrid);
+      if (onGrid) {   // one branch around the three adds
+        const uint32_t a = touchedAddr + s[r];
+        asm volatile("red.shared.add.u32 [%0], %1;\n\tred.shared.add.u32 [%0+4], %2;\n\tred.shared.add.u32 [%0+8], %3;"
+                     ::"r"(a), "r"(ix & 0x7FFu), "r"((ix >> 11) & 0x7FFu), "r"(ix >> 22) : "memory");
+      }
     }
+  } else {
+    bool go[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      if (onGrid[r]) {   // one branch around the three adds
-        const uint32_t a = fxAddr + 12u * s[r];
-        asm volatile("red.shared.add.u32 [%0], %1;\n\tred.shared.add.u32 [%0+4], %2;\n\tred.shared.add.u32 [%0+8], %3;"
-                     ::"r"(a), "r"(ix[r] & 0x7FFu), "r"((ix[r] >> 11) & 0x7FFu), "r"(ix[r] >> 22) : "memory");
-      }
+      // no flags: a row that would leave its slot at the neutral element goes down the hash path instead
+      go[r] = fast[r] && (JIT_DENSE_FLAGS || !JIT_DENSE_CHECK || meas[r] != P.accNeutral);
+      cold = cold || (fast[r] && !go[r]);
     }
-    if (rare) {
+    if (JIT_DENSE_FLAGS) {
 #pragma unroll
-      for (int r = 0; r < 4; r++) {
-        if (slow[r] || (fast[r] && mraw[r] == 0x80000000u)) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
-        else if (fast[r] && !onGrid[r]) aggAtomic((AggOp)JIT_AGG_OP, tAcc + s[r], meas[r]);
-      }
+      for (int r = 0; r < 4; r++) stsFlag(touchedAddr + s[r], go[r]);
     }
-    return;
-  } else {
-  // (issuing the compare-and-swap loops of the shared-memory rows interleaved instead of one after the other was
-  // measured and changed nothing: 0.376 vs 0.372 ms on cfg3)
-  constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
+    const uint32_t sAccAddr = touchedAddr + kDenseCap;
+    // (issuing the compare-and-swap loops of the shared-memory rows interleaved instead of one after the other was
+    // measured and changed nothing: 0.376 vs 0.372 ms on cfg3)
+    constexpr int kToShared = JIT_DENSE_ACC == 1 ? 4 : JIT_DENSE_ACC == 2 ? 2 : JIT_DENSE_ACC == 3 ? 3 : 0;   // row positions 0 .. kToShared-1
 #pragma unroll
-  for (int r = 0; r < 4; r++) {
-    if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], go[r]);
-    else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], go[r]);
+    for (int r = 0; r < 4; r++) {
+      if (r < kToShared) redSharedPred<JIT_AGG_OP>(sAccAddr + 8u * s[r], denseSharedAcc() + s[r], meas[r], go[r]);
+      else redGlobalPred<JIT_AGG_OP>(tAcc + s[r], meas[r], go[r]);
+    }
   }
-  }
-  if (later[0] || later[1] || later[2] || later[3]) {
-#pragma unroll
-    for (int r = 0; r < 4; r++)
-      if (later[r]) denseSlowRow(P, dv[r], dvalid[r], meas[r]);
+  if (cold) {
+    const uint32_t inRange = (fast[0] ? 1u : 0u) | (fast[1] ? 2u : 0u) | (fast[2] ? 4u : 0u) | (fast[3] ? 8u : 0u);
+    constexpr uint32_t kUnit = JIT_DENSE_ACC == 4 && JIT_DENSE != 2 ? 12u : 1u;   // bytes -> slots
+    denseColdRows(stage, q, row0, P, nvalid, inRange, s[0] / kUnit, s[1] / kUnit, s[2] / kUnit, s[3] / kUnit, tAcc);
   }
 }
 #endif
@@ -258,6 +269,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   uint32_t touchedAddr = smemAddr(touched);
   asm volatile("" : "+r"(touchedAddr));   // keep it in a register: the compiler otherwise rebuilds the window address per store
   const uint32_t denseSlots = JIT_DENSE == 2 ? 0u : P.dRepStride * P.dReps;   // <= kDenseCap (host); 2: nothing CTA-private
+  const uint32_t repOff = JIT_DENSE == 2 ? 0u : (threadIdx.x & (P.dReps - 1u)) * P.dRepStride *
+                                                (JIT_DENSE_ACC == 4 ? 12u : 1u);   // this lane's copy of the slots (integer form: in bytes)
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
     if (JIT_DENSE_FLAGS) touched[i] = 0;
     if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
@@ -337,11 +350,11 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         const uint32_t q = threadIdx.x;
         uint64_t meas[4];
 #if JIT_DENSE
-        uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
-        bool fast[4], slow[4];
+        uint32_t dslot[4];
+        bool fast[4], anySlow;
         uint32_t mraw[4];
-        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, slow, dslot, dv, dvalid, meas, mraw))
-          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas, mraw);
+        if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, anySlow, dslot, meas, mraw))
+          jitAggregateDense(touchedAddr, tAcc, P, stage, q, t * JIT_TILE_ROWS + q * 4, 4u, repOff, fast, anySlow, dslot, meas, mraw);
         (void)allowClaim; (void)bypass;
 #else
         uint64_t key[4][JIT_KW];
@@ -358,7 +371,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   // the threads themselves, byte-exact (nothing beyond a column's last byte is touched), and go
   // through the same rowEval.  One CTA does it; rows past the end are masked dead.  (A stopped run leaves the tail to
   // the resumed one: DevTable::progress[kProgressTail] records that it has been folded.)
-  __shared__ uint32_t sDoTail;
+  volatile uint32_t &sDoTail = *reinterpret_cast<volatile uint32_t *>(smem + 72);   // header word (no static shared memory:
+                                                                                     // the dynamic part takes the CTA's whole budget)
   if (threadIdx.x == 0) {
     if (kCanDrain && !P.resume && blockIdx.x == gridDim.x - 1) P.G.progress[kProgressTail] = 0u;   // a fresh batch
     sDoTail = blockIdx.x == gridDim.x - 1 &&
@@ -388,11 +402,11 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         uint64_t meas[4];
         const uint32_t nvalid = rows - q * 4 < 4 ? rows - q * 4 : 4;
 #if JIT_DENSE
-        uint32_t dslot[4], dv[4][JIT_ND], dvalid[4];
-        bool fast[4], slow[4];
+        uint32_t dslot[4];
+        bool fast[4], anySlow;
         uint32_t mraw[4];
-        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, slow, dslot, dv, dvalid, meas, mraw))
-          jitAggregateDense(touchedAddr, tAcc, P, fast, slow, dslot, dv, dvalid, meas, mraw);
+        if (rowEval(stages, q, done + q * 4, P, nvalid, fast, anySlow, dslot, meas, mraw))
+          jitAggregateDense(touchedAddr, tAcc, P, stages, q, done + q * 4, nvalid, repOff, fast, anySlow, dslot, meas, mraw);
 #else
         uint64_t key[4][JIT_KW];
         uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);

@@ -78,6 +78,10 @@ struct DevPlan {
   uint8_t denseNd;
   uint8_t denseInst[8], denseViaQuot[8], denseNullCanon[8];
   uint32_t denseLo[8], denseCnt[8], denseStep[8];
+  // quotient dimensions whose dividend range is small (span * step <= 2^32): index = umulhi(x - denseBase, 2^32 / step + 1),
+  // in range iff x - denseBase < denseSpan (one subtraction, one multiply, one compare per row)
+  uint8_t denseSpan32[8];
+  uint32_t denseBase[8], denseSpan[8];
   uint32_t denseTotal;     // slots of one copy = prod (denseCnt[k] + 1)
   uint32_t tableBytes;     // shared memory between the header and the first stage (keys, or flags + accumulators)
   // more slots than a CTA holds: ONE array of accumulators in global memory (L2-resident) shared by all CTAs, folded
