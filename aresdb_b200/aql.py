@@ -431,7 +431,17 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
     # the time column by it (CONVERT_TZ is Plus, query/time_series_aggregate.go:87) before bucketizing
     tz_offset = 0
     if tz is not _dt.timezone.utc:
-        probe = [t for t in ((frm, to) if tf.get("column") else ()) if t is not None] or [int(now)]
+        ends = [t for t in ((frm, to) if tf.get("column") else ()) if t is not None]
+        if isinstance(tz, _dt.timezone):                     # numeric offset: constant by definition
+            probe = ends or [int(now)]
+        else:
+            if len(ends) < 2:
+                raise AQLError("a named time zone needs a time filter with both ends (its offset must be constant over the range)")
+            # every offset change strictly inside [from, to) matters — a range can cross TWO switches and end at the
+            # offset it started with (January to January): walk the range in steps no transition pair can hide in
+            # (zones switch at most a few times a year; 7 days is far below the shortest gap between two switches)
+            lo, hi = int(ends[0]), int(ends[1])
+            probe = list(range(lo, max(hi, lo + 1), 7 * 86400)) + [max(hi - 1, lo)]
         offsets = {int(_dt.datetime.fromtimestamp(t, tz).utcoffset().total_seconds()) for t in probe}
         if len(offsets) != 1:
             raise AQLError("a daylight-saving switch inside the time range is outside this front-end")

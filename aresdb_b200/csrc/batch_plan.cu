@@ -213,7 +213,7 @@ __device__ __forceinline__ void getOperand(const DevPlan &P, const DevInst &I, b
 #pragma unroll
       for (int r = 0; r < R; r++) v[r] = (uint32_t)c.in.constLo;
       valid = c.in.constValid ? 0xF : 0;
-    } else if (STAGED) {
+    } else if (STAGED && !c.rle) {
       fetchStaged(c, stage, q, v, valid);
     } else {
       fetchDirect(P, c, row0, nrows, v, valid);
@@ -522,8 +522,9 @@ fusedBatchKernel(const __grid_constant__ DevPlan P, const DevTable G) {
   const AggOp op = (AggOp)P.aggOp;
   for (uint32_t i = threadIdx.x; i < P.smemSlots; i += blockDim.x) {
     unsigned long long k = tKeys[i];
-    if (k != kEmptyKey) globalUpdate(G, op, k, nullptr, __ldcg(&tAcc[i]));
+    if (k != kEmptyKey) globalUpdate(G, op, k, nullptr, __ldcg(&tAcc[i]), /*spillWhenStopped=*/true);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *G.occPublish = *reinterpret_cast<volatile uint32_t *>(&G.counters[0]);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -753,7 +754,7 @@ __global__ void __launch_bounds__(256) copyPlusZeroKernel(const uint8_t *__restr
 struct DenseFold {
   uint32_t lo[8], cnt[8], step[8], stride[8];
   uint8_t rowOff[8], width[8], nullOff[8];
-  uint32_t nd, total;
+  uint32_t nd, total, reps;
   uint8_t keyMode, hashBits, rowBytes, op;
   unsigned long long neutral;
 };
@@ -762,9 +763,14 @@ __global__ void __launch_bounds__(256)
 denseFoldKernel(unsigned long long *__restrict__ acc, DenseFold F, DevTable G) {
   const uint32_t strideAll = gridDim.x * blockDim.x;
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < F.total; i += strideAll) {
-    const unsigned long long v = acc[i];
+    unsigned long long v = F.neutral;
+    for (uint32_t c = 0; c < F.reps; c++) {   // the copies the CTA groups accumulated into
+      const unsigned long long x = acc[(size_t)c * F.total + i];
+      if (x == F.neutral) continue;
+      acc[(size_t)c * F.total + i] = F.neutral;
+      v = v == F.neutral ? x : aggCombine((AggOp)F.op, v, x);
+    }
     if (v == F.neutral) continue;
-    acc[i] = F.neutral;
     uint64_t row[4] = {0, 0, 0, 0};
     uint8_t *rb = reinterpret_cast<uint8_t *>(row);
     uint32_t rem = i;
@@ -942,6 +948,8 @@ struct AggState {
   unsigned long long *ctaAcc;  // [kMaxGridCtas][8192] private accumulator slices of the fused kernel's CTAs
   unsigned long long *denseAcc = nullptr;  // [kGlobalDenseMaxSlots] shared accumulators of the global dense form (lazy)
   uint64_t occUpper = 0;                   // host-side upper bound of the occupied slots (exact after a synchronise)
+  uint32_t unchecked = 0;                  // hash-table batches launched since the last check of the STOP flag
+  bool everChecked = false;                // a batch of this query has been waited for (its occupancy is known)
   uint8_t *smallScratch = nullptr;         // single-launch finalize: hash / index ping-pong arrays (in `mem`)
   uint32_t *resultDev = nullptr;           // [0] groups, [1] status, [2] claimed slots of the last single-launch finalize
   uint32_t *resultHost = nullptr;          // the same three words in mapped pinned host memory
@@ -1010,6 +1018,7 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
     ARES_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&st->resultHostDev), st->resultHost, 0));
     memset(st->resultHost, 0, 64);
   }
+  st->table.occPublish = st->resultHostDev + 8;
   if (st->hllDense) ARES_CUDA(cudaMemsetAsync(st->table.regs, 0, regBytes, s));
   ARES_CUDA(cudaMemsetAsync(p, 0, 256, s));
   fillTableKernel<<<smCount() * 8, 256, 0, s>>>(st->table.keys, st->table.acc, cap, st->accNeutral);
@@ -1328,16 +1337,31 @@ expandRleKernel(InputDesc d, const uint32_t *__restrict__ baseCounts, uint32_t s
   }
 }
 
+// First-class RLE columns: run that holds the first index position of every tile (and of the batch's last position), so
+// that the kernel searches a window of a few runs per quad instead of the whole count vector per row.
+__global__ void __launch_bounds__(256)
+rleTileRunsKernel(const uint32_t *__restrict__ counts, uint32_t length, const uint32_t *__restrict__ baseCounts, uint32_t startCount,
+                  uint32_t numRows, uint32_t tileRows, uint32_t entries, uint32_t *__restrict__ out) {
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= entries) return;
+  uint64_t pos = (uint64_t)t * tileRows;
+  if (pos > numRows - 1) pos = numRows - 1;
+  const uint32_t row = baseCounts ? baseCounts[pos] : startCount + (uint32_t)pos;
+  out[t] = rlePosition(counts, length, row);
+}
+
 // Decides staged vs direct, the tile size, the stage layout, the TMA ring depth and the shared table
 // size.  The shared table gets what the workload needs first (a table that overflows sends rows to
 // contended L2 atomics, profiles/r01_agg_microbench.txt), the ring takes the rest.
 static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense = true) {
   bool canStage = P.numRows >= 1024;
+  bool anyRle = false;
   uint32_t rowBits = 0;
   for (int c = 0; c < P.ncols; c++) {
     DevColumn &col = P.cols[c];
     if (col.in.mode == 0 || !col.used) continue;
-    if (col.in.mode == 3) { canStage = false; break; }  // RLE: positional search, direct path
+    if (col.rle) { anyRle = true; continue; }            // RLE decoded in the kernel from its runs: nothing to stage
+    if (col.in.mode == 3) { canStage = false; break; }  // RLE without the specialised kernel: positional search, direct path
     if (col.width > 4) continue;                          // wide dims are read directly
     const uintptr_t v = reinterpret_cast<uintptr_t>(col.in.base + col.in.valuesOff);
     if (v & 15) canStage = false;
@@ -1364,12 +1388,12 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
     size_t stage = 0;
     for (int c = 0; c < P.ncols; c++) {
       const DevColumn &col = P.cols[c];
-      if (col.in.mode == 0 || !col.used || col.width > 4) continue;
+      if (col.in.mode == 0 || !col.used || col.width > 4 || col.rle) continue;
       stage += ((col.width ? (size_t)tr * col.width : tr / 8 + 16) + 15) / 16 * 16;
       if (col.in.mode == 2) stage += (tr / 8 + 16 + 15) / 16 * 16;
     }
-    // base counts of an RLE batch ride along when a SUM / AVG measure needs the run lengths
-    if (P.baseCounts != nullptr && !P.skipCount && (reinterpret_cast<uintptr_t>(P.baseCounts) & 15) == 0) stage += ((size_t)tr + 4) * 4;
+    // base counts of an RLE batch ride along when a SUM / AVG measure needs the run lengths, or an RLE column the row numbers
+    if (P.baseCounts != nullptr && (!P.skipCount || anyRle) && (reinterpret_cast<uintptr_t>(P.baseCounts) & 15) == 0) stage += ((size_t)tr + 4) * 4;
     return stage;
   };
   uint32_t tileRows = 0, stages = 0;
@@ -1397,7 +1421,16 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
         for (uint32_t tr : {3968u, 1920u, 896u}) {
           if (forceTile && tr != forceTile) continue;
           const uint32_t n = (uint32_t)(((size_t)kSmemBudget - 128 - 256) / stageBytesFor(tr));
-          if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; slots = 16; P.denseGlobal = 1; break; }
+          if (n >= 2) {
+            tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; slots = 16; P.denseGlobal = 1;
+            // L2 atomics saturate (~190 G/s) at >= ~1M distinct addresses and contend below (profiles/r01_agg_microbench.txt):
+            // replicate the slot array until it has about that many
+            uint32_t reps = 1;
+            while (reps < 8 && (uint64_t)P.denseTotal * reps * 2 <= kGlobalDenseMaxSlots && (uint64_t)P.denseTotal * reps < (1u << 20)) reps *= 2;
+            if (const char *e = getenv("ARESDB_B200_GLOBAL_REPS")) { const int v = atoi(e); if (v >= 1 && v <= 8 && (v & (v - 1)) == 0 && (uint64_t)P.denseTotal * v <= kGlobalDenseMaxSlots) reps = (uint32_t)v; }
+            P.denseGlobalReps = (uint8_t)reps;
+            break;
+          }
         }
       }
       if (!tileRows) P.denseNd = 0;   // no layout holds the slots: hash table
@@ -1421,7 +1454,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   if (tileRows) {
     for (int c = 0; c < P.ncols; c++) {
       DevColumn &col = P.cols[c];
-      if (col.in.mode == 0 || !col.used || col.width > 4) continue;
+      if (col.in.mode == 0 || !col.used || col.width > 4 || col.rle) continue;
       col.staged = 1;
       anyStaged = true;
       col.smemValues = (uint32_t)stageBytes;
@@ -1439,7 +1472,7 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   }
   P.smemBc = 0;
   P.tileBcBytes = 0;
-  if (anyStaged && P.baseCounts != nullptr && !P.skipCount && (reinterpret_cast<uintptr_t>(P.baseCounts) & 15) == 0) {
+  if (anyStaged && P.baseCounts != nullptr && (!P.skipCount || anyRle) && (reinterpret_cast<uintptr_t>(P.baseCounts) & 15) == 0) {
     P.smemBc = (uint32_t)stageBytes;
     P.tileBcBytes = (tileRows + 4) * 4;   // one count more than rows (run length = difference), padded to 16 bytes
     stageBytes += P.tileBcBytes;
@@ -1488,9 +1521,12 @@ static void checkOverflow(AggState *st, const uint32_t counters[2]);
 
 static TableCounters readCounters(AggState *st, cudaStream_t s) {
   TableCounters c;
-  ARES_CUDA(cudaMemcpyAsync(&c, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+  uint32_t *pinned = st->resultHost + 10;   // (pinned: a pageable target costs a staging copy and ~100 us)
+  ARES_CUDA(cudaMemcpyAsync(pinned, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
   ARES_CUDA(cudaStreamSynchronize(s));
+  memcpy(&c, pinned, sizeof(c));
   st->occUpper = c.occupied;
+  st->resultHost[8] = c.occupied;
   return c;
 }
 
@@ -1530,6 +1566,14 @@ static void settleTable(AggState *st, cudaStream_t s) {
     throw EngineError("group table: more than " + std::to_string(kSpillCap) + " rows of new groups arrived from direct-indexed batches while the "
                       "table was full (a zone map far off the data); recreate the AggState with a larger AggSpec.ExpectedGroups and replay");
   if (c.overflow) checkOverflow(st, &c.occupied);
+  if (c.stop && st->unchecked > 0) {
+    const uint32_t n = st->unchecked;
+    st->unchecked = 0;
+    throw EngineError("the group table reached its growth threshold (" + std::to_string(c.occupied) + " groups) during " + std::to_string(n) +
+                      " batch(es) whose launches were not waited for — the number of groups jumped from under an eighth of that threshold; "
+                      "rows were NOT folded: recreate the AggState with AggSpec.ExpectedGroups >= " + std::to_string((uint64_t)c.occupied * 4) +
+                      " (or set ARESDB_B200_CHECK_EVERY_BATCH=1) and replay the batches");
+  }
   if (!c.stop && !c.spilled) return;
   size_t cap = st->capacity;
   while ((uint64_t)c.occupied + c.spilled > cap / 4) cap <<= 1;   // settle at a quarter full at most
@@ -1561,19 +1605,36 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   compilePlan(st, bp, P);
   P.tailBegin = 0;
   P.resume = 0;
-  // archive batches: expand the RLE columns the plan reads (ARESDB_B200_EXPAND_RLE=0 keeps the positional path)
+  // Archive batches: run-length encoded (mode 3) columns.
+  //  * the column whose count vector IS the batch's base counts has one value per index position: it is read like an
+  //    uncompressed column (values / null bitmap of its runs), no copy;
+  //  * every other RLE column is a FIRST-CLASS input of the specialised kernel: decoded from its runs inside the tile loop
+  //    (jit_kernel_head.cuh ldrle) with a per-tile run hint computed below — HBM sees the runs, not the rows;
+  //  * without NVRTC (or with ARESDB_B200_EXPAND_RLE=1) the column is expanded once per batch for the interpreter.
   std::vector<std::unique_ptr<Scratch>> expanded;
-  static const bool expandRle = [] { const char *e = getenv("ARESDB_B200_EXPAND_RLE"); return !(e && e[0] == '0'); }();
-  if (expandRle && bp.NumRows >= 1024) {
+  static const bool forceExpand = [] { const char *e = getenv("ARESDB_B200_EXPAND_RLE"); return e && e[0] == '1'; }();
+  static const bool keepPositional = [] { const char *e = getenv("ARESDB_B200_EXPAND_RLE"); return e && e[0] == '0'; }();
+  if (bp.NumRows >= 1024 && !keepPositional) {
     const uint32_t n = bp.NumRows;
+    const bool firstClass = jitAvailable() && !forceExpand;
+    int nrle = 0;
     for (int c = 0; c < P.ncols; c++) {
       DevColumn &col = P.cols[c];
       if (!col.used || col.in.mode != 3 || col.width > 4) continue;
+      const bool direct = bp.BaseCounts != nullptr && reinterpret_cast<const uint32_t *>(col.in.base) == bp.BaseCounts;
+      if (direct && col.in.length >= n) {   // run number == index position
+        col.in.mode = 2;
+        continue;
+      }
+      if (firstClass && nrle < 4 && col.in.length > 0) {
+        col.rle = 1;
+        nrle++;
+        continue;
+      }
       const size_t nullBytes = ((size_t)(n + 31) / 32 * 4 + 16 + 63) / 64 * 64;
       const size_t valueBytes = (col.width ? (size_t)n * col.width : (size_t)(n + 31) / 32 * 4) + 64;
       expanded.emplace_back(new Scratch(nullBytes + valueBytes, s));
       uint8_t *buf = expanded.back()->as<uint8_t>();
-      const bool direct = bp.BaseCounts != nullptr && reinterpret_cast<const uint32_t *>(col.in.base) == bp.BaseCounts;
       int blocks = divUp((int64_t)(n + 31) / 32, 8);
       if (blocks > smCount() * 16) blocks = smCount() * 16;
       expandRleKernel<<<blocks, 256, 0, s>>>(col.in, bp.BaseCounts, bp.StartCount, n, col.width, direct, buf + nullBytes,
@@ -1608,6 +1669,18 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
     P.join = joinMem->as<DevJoin>();
   }
   size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
+  // per-tile run hints of the first-class RLE columns (the tile size is known now)
+  for (int c = 0; c < P.ncols; c++) {
+    DevColumn &col = P.cols[c];
+    if (!col.rle) continue;
+    if (!P.staged) { col.rle = 0; continue; }   // no tile loop (tiny batch): the generic positional read
+    const uint32_t entries = (P.numRows + P.tileRows - 1) / P.tileRows + 2;
+    expanded.emplace_back(new Scratch(sizeof(uint32_t) * entries, s));
+    rleTileRunsKernel<<<divUp(entries, 256), 256, 0, s>>>(reinterpret_cast<const uint32_t *>(col.in.base), col.in.length, bp.BaseCounts,
+                                                         bp.StartCount, P.numRows, P.tileRows, entries, expanded.back()->as<uint32_t>());
+    checkLastError("rleTileRuns");
+    col.tileRun = expanded.back()->as<uint32_t>();
+  }
   // room in the group table (see "growth of the group table"): the direct path and the direct-indexed kernels are not
   // waited for, so what they may insert is reserved up front (flush of the CTA slots / fold of the global slot array;
   // out-of-range rows park); hash-table tile kernels are checked after the launch and resumed when they stopped.
@@ -1654,7 +1727,7 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
           F.rowOff[k] = I.rowOff; F.width[k] = I.width; F.nullOff[k] = I.nullOff;
           stride *= P.denseCnt[k] + 1;
         }
-        F.nd = P.denseNd; F.total = P.denseTotal;
+        F.nd = P.denseNd; F.total = P.denseTotal; F.reps = P.denseGlobalReps ? P.denseGlobalReps : 1;
         F.keyMode = P.keyMode; F.hashBits = P.hashBits; F.rowBytes = P.rowBytes; F.op = P.aggOp;
         F.neutral = P.accNeutral;
         int blocks = divUp((int64_t)P.denseTotal, 256);
@@ -1673,12 +1746,25 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
       checkLastError("ExecuteBatchPlan");
     }
     if (!checkAfter) return;
+    // Waiting for every hash-table batch would cost a launch gap per batch (the host cannot prepare the next one while it
+    // waits).  The wait is therefore adaptive: always for the first batch of a query, and from then on whenever the
+    // occupancy last seen — read back then, or published by a finishing kernel into mapped pinned memory — is above an
+    // eighth of the threshold.  A table that fills from under an eighth of its threshold within unwatched batches is
+    // reported loudly at the next synchronising call (settleTable), never folded wrongly.
+    static const bool everyBatch = [] { const char *e = getenv("ARESDB_B200_CHECK_EVERY_BATCH"); return e && e[0] == '1'; }();
+    const uint64_t seen = st->resultHost[8] > st->occUpper ? st->resultHost[8] : st->occUpper;
+    if (P.resume == 0 && st->everChecked && !everyBatch && st->unchecked < 64 && seen * 8 < st->table.growAt) {
+      st->unchecked++;
+      return;
+    }
     const TableCounters c = readCounters(st, s);
+    st->everChecked = true;
     if (c.overflow) checkOverflow(st, &c.occupied);
-    if (!c.stop) return;
-    size_t cap = st->capacity << 1;
-    while ((uint64_t)c.occupied >= cap / 4) cap <<= 1;   // resume at a quarter full at most
-    growTable(st, cap, s);
+    if (!c.stop && !c.spilled) { st->unchecked = 0; return; }
+    if (c.stop && st->unchecked > 0) settleTable(st, s);   // raises: earlier unwatched batches stopped as well
+    const bool stopped = c.stop != 0;
+    settleTable(st, s);   // grows (a quarter full at most afterwards) and folds the parked groups
+    if (!stopped) return;
     P.resume = 1;
     P.ctaAcc = st->ctaAcc;
   }
@@ -2053,6 +2139,9 @@ CGoCallResHandle AggStateReset(void *state, void *cudaStream, int device) {
     checkLastError("AggStateReset");
     ARES_CUDA(cudaMemsetAsync(st->table.counters, 0, 256, s));
     st->occUpper = 0;
+    st->unchecked = 0;
+    st->everChecked = false;
+    st->resultHost[8] = 0;
     return 0;
   });
 }

@@ -20,7 +20,7 @@ constexpr uint64_t kMix = 0x9E3779B97F4A7C15ull;
 // whose launches the host does not wait for (direct-indexed kernels: their flush and their out-of-range rows): folded
 // into the table after it has grown, at the state's next synchronising call.
 struct SpillEntry { unsigned long long key; uint64_t row[4]; uint64_t val; };
-constexpr uint32_t kSpillCap = 65536;
+constexpr uint32_t kSpillCap = 1u << 20;   // 48 MB per state: covers the flush of every CTA's shared table (148 x 6144 keys)
 constexpr uint32_t kSlotSpill = 0xFFFFFFFEu;
 
 struct DevTable {
@@ -31,6 +31,8 @@ struct DevTable {
                          // reached growAt — consumers finish their tile and drain; the host grows the table and resumes
   uint32_t *progress;    // [kMaxGridCtas * 32 + 1] tile iterations each consumer warp has folded (resume point), tail flag
   uint32_t growAt;       // claim ordinal at which the stop flag is raised (capacity / 2; 0xFFFFFFFF: never)
+  volatile uint32_t *occPublish;  // mapped pinned host word: the occupancy a finishing kernel saw (read by the host without
+                         // synchronising: decides whether the next batch's launch has to be waited for)
   struct SpillEntry *spill;  // [kSpillCap] rows of kernels that cannot be resumed, parked while the table is full
                          // (counters[4] = entries, counters[5] = spill overflow)
   uint32_t *claimed;     // [capacity] slot index of the i-th claimed group (claim order): finalize / reset / export

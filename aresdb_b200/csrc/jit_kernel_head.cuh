@@ -12,6 +12,15 @@ constexpr int kJitMaxConsts = 64;
 constexpr int kJitMaxWide = 8;
 constexpr int kJitMaxMagic = 16;
 constexpr int kJitMaxDenseDims = 8;
+constexpr int kJitMaxRle = 4;
+// A mode-3 column read by the kernel straight from its runs: cumulative counts (length + 1 entries), null bitmap and
+// values of the RUNS, and the per-tile run hint computed by rleTileRunsKernel.
+struct RleColumn {
+  const uint32_t *counts;
+  const uint8_t *nulls, *values;
+  const uint32_t *tileRun;
+  uint32_t length, startBit;
+};
 
 // mirrors plan_device.cuh
 constexpr int kMaxForeignTables = 4;
@@ -44,7 +53,9 @@ struct JitParams {
   float fxScale;                          //                     2^S (a float sum's rows are added as integers x * 2^S)
   uint32_t fxPad;
   const DevJoin *join;                    // joined dimension tables (join.cuh), null without joins
-  uint32_t resume;                        // 1: second launch of the same batch after the table grew (progress[] says where)
+  uint32_t resume;
+  uint32_t startCount;                    // row number of index position 0 when the batch has no base counts
+  RleColumn rle[kJitMaxRle];              // run-length encoded columns decoded in place (see ldrle)                        // 1: second launch of the same batch after the table grew (progress[] says where)
 };
 
 
@@ -77,6 +88,31 @@ __device__ __forceinline__ uint32_t ldbits(const uint8_t *bits, uint32_t q) {
   const uint32_t bit = 4 * q + START_BIT;
   const uint32_t w = bits[bit >> 3] | ((uint32_t)bits[(bit >> 3) + 1] << 8);
   return w >> (bit & 7);  // callers test bits 0..3
+}
+
+// rows 4q .. 4q+3 of a run-length encoded column, decoded from its RUNS (the column is never expanded): the row numbers of
+// the quad's index positions are increasing, and the run of every position of tile `tile` lies in
+// [tileRun[tile], tileRun[tile + 1]] — usually one or two runs — so the quad's first row is found by a search over that
+// window and the next three by stepping forward.  Neighbouring threads read the same few counts / values (broadcast hits).
+template <int W, bool SIGNED>
+__device__ __forceinline__ void ldrle(const RleColumn &R, uint32_t tile, const uint32_t (&rows)[4], uint32_t (&v)[4], uint32_t &validNibble) {
+  uint32_t lo = R.tileRun[tile], hi = R.tileRun[tile + 1];
+  while (lo < hi) {   // last run in [lo, hi] that starts at or before rows[0]
+    const uint32_t mid = lo + ((hi - lo + 1) >> 1);
+    if (R.counts[mid] <= rows[0]) lo = mid; else hi = mid - 1;
+  }
+  uint32_t p = lo;
+  const uint32_t last = R.length - 1;
+  validNibble = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    while (p < last && R.counts[p + 1] <= rows[r]) p++;
+    if (W == 0) v[r] = (R.values[(p + R.startBit) >> 3] >> ((p + R.startBit) & 7)) & 1u;
+    else if (W == 1) v[r] = SIGNED ? (uint32_t)(int32_t)reinterpret_cast<const int8_t *>(R.values)[p] : R.values[p];
+    else if (W == 2) v[r] = SIGNED ? (uint32_t)(int32_t)reinterpret_cast<const int16_t *>(R.values)[p] : reinterpret_cast<const uint16_t *>(R.values)[p];
+    else v[r] = reinterpret_cast<const uint32_t *>(R.values)[p];
+    validNibble |= ((R.nulls[(p + R.startBit) >> 3] >> ((p + R.startBit) & 7)) & 1u) << r;
+  }
 }
 
 // x / d for a runtime-constant divisor as the high word of a 64x32-bit product (Lemire's fastdiv):

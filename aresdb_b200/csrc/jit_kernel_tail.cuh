@@ -138,7 +138,7 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     for (int r = 0; r < 4; r++) {
       const bool f = fast[r] && (!JIT_DENSE_CHECK || meas[r] != P.accNeutral);
       cold = cold || (fast[r] && !f);
-      redGlobalPred<JIT_AGG_OP>(P.gAcc + dslot[r], meas[r], f);
+      redGlobalPred<JIT_AGG_OP>(P.gAcc + s[r], meas[r], f);
     }
   } else if (JIT_DENSE_ACC == 4) {
     // Exact integer accumulation of a float sum (jitAnalyzeDense): a slot is three 32-bit counters for the 11 / 11 / 10
@@ -269,7 +269,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   uint32_t touchedAddr = smemAddr(touched);
   asm volatile("" : "+r"(touchedAddr));   // keep it in a register: the compiler otherwise rebuilds the window address per store
   const uint32_t denseSlots = JIT_DENSE == 2 ? 0u : P.dRepStride * P.dReps;   // <= kDenseCap (host); 2: nothing CTA-private
-  const uint32_t repOff = JIT_DENSE == 2 ? 0u : (threadIdx.x & (P.dReps - 1u)) * P.dRepStride *
+  const uint32_t repOff = JIT_DENSE == 2 ? (blockIdx.x & (P.dReps - 1u)) * P.dRepStride : (threadIdx.x & (P.dReps - 1u)) * P.dRepStride *
                                                 (JIT_DENSE_ACC == 4 ? 12u : 1u);   // this lane's copy of the slots (integer form: in bytes)
   for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
     if (JIT_DENSE_FLAGS) touched[i] = 0;
@@ -454,10 +454,12 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   }
   return;
 #endif
+  // (the CTA's table is folded whatever the state of the global one: groups it cannot take right now are parked)
   for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
-    if (k != kEmptyKey) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, nullptr, __ldcg(&tAcc[i]));
+    if (k != kEmptyKey) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, nullptr, __ldcg(&tAcc[i]), /*spillWhenStopped=*/true);
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) *P.G.occPublish = *reinterpret_cast<volatile uint32_t *>(&P.G.counters[0]);
 }
 
 }  // namespace aresb

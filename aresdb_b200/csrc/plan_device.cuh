@@ -36,7 +36,9 @@ struct DevColumn {
   uint8_t used;            // some instruction reads the column (unreferenced columns of the batch cost nothing)
   uint32_t rangeLo, rangeHi;  // zone map of the batch (BatchPlan.Ranges): valid values lie in [rangeLo, rangeHi]
   uint8_t rangeKnown;
-  uint8_t pad[3];
+  uint8_t rle;             // run-length encoded (mode 3) column decoded in the kernel from its runs — never expanded, never staged
+  uint8_t pad[2];
+  const uint32_t *tileRun; // rle: run that holds the first index position of every tile (+ one entry for the last position)
 };
 
 struct DevInst {
@@ -88,6 +90,7 @@ struct DevPlan {
   // into the group table by denseFoldKernel after the batch; a slot was reached iff it differs from accNeutral
   unsigned long long *denseAcc;
   uint8_t denseGlobal;
+  uint8_t denseGlobalReps;   // copies of the global slot array (power of two; CTA b uses copy b mod reps): spreads the L2 atomics
   uint8_t neutralSafe;     // no sequence of row values can bring a reached accumulator back to accNeutral (set by compilePlan)
   uint8_t denseFx;         // float sum accumulated as exact integers (three 32-bit pieces per slot), see jitAnalyzeDense
   int8_t fxMeasureInst;    // the measure instruction (a verbatim Float32 column with a zone map)

@@ -31,6 +31,12 @@ def filter_excludes_range(f: E.Expr, ranges: dict) -> bool:
         return False
     lo, hi = ranges[col.index]
     num = int(lit.value)
+    # The kernel (and the reference) compares in the promoted class: an integer literal is a ConstInt (int32), so the
+    # comparison runs in int32 whatever the column is (query/utils.hpp:83-94) and a uint32 value >= 2^31 compares as a
+    # negative number.  Only skip when the literal and the whole range are representable in int32 without wrapping, so
+    # that the unbounded comparison below says what the kernel would.
+    if not (-(2 ** 31) <= num < 2 ** 31 and 0 <= lo <= hi < 2 ** 31):
+        return False
     if op == A.GreaterThanOrEqual:
         return hi < num
     if op == A.GreaterThan:

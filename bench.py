@@ -519,6 +519,9 @@ def gpu_run(args):
         fused kernels by a copier thread, produces the batch's zone map on the device, and reads the result back."""
         from aresdb_b200.executor import compute_zone_map
         copy_stream = lib.CreateCudaStream(local)
+
+        class CopySpace:   # what compute_zone_map needs of a memory space: the stream and device to run on
+            stream, device = copy_stream, local
         staging = [[torch.empty_like(b) for b in table.bufs[0]] for _ in range(2)]
         nb = len(batches)
         rows_b = batches[0].num_rows
@@ -528,6 +531,7 @@ def gpu_run(args):
             ex.reset()
             main = torch.cuda.current_stream()
             ready = [threading.Event() for _ in range(nb)]
+            zms = [None] * nb
             freed = [None] * nb
             freed_set = [threading.Event() for _ in range(nb)]
             h2d = [0]
@@ -544,7 +548,14 @@ def gpu_run(args):
                         for dst, src in zip(staging[slot], table.host[i]):
                             lib.AsyncCopyHostToDevice(dst.data_ptr(), src.data_ptr(), src.numel(), copy_stream, local)
                             h2d[0] += src.numel()
-                        lib.WaitForCudaStream(copy_stream, local)
+                        if batches[i].ranges is not None:
+                            # the zone map of the freshly resident batch, on the COPY stream (it overlaps the fused kernel of
+                            # the previous batch on the main stream); ComputeColumnRanges synchronises that stream
+                            cols = [columns.slice_of(t.data_ptr(), dt, rows_b, 0, table.values_off, 2)
+                                    for t, dt in zip(staging[slot], synth.COLUMN_TYPES)]
+                            zms[i] = compute_zone_map(lib, CopySpace, cols)
+                        else:
+                            lib.WaitForCudaStream(copy_stream, local)
                         ready[i].set()
                 except Exception as e:   # noqa: BLE001
                     err.append(e)
@@ -561,8 +572,7 @@ def gpu_run(args):
                     raise err[0]
                 slot = i & 1
                 cols = [columns.slice_of(t.data_ptr(), dt, rows_b, 0, table.values_off, 2) for t, dt in zip(staging[slot], synth.COLUMN_TYPES)]
-                zm = compute_zone_map(lib, space, cols) if batches[i].ranges is not None else None
-                ex.process_batch(Batch(cols, rows_b, ranges=zm))
+                ex.process_batch(Batch(cols, rows_b, ranges=zms[i]))
                 ev = torch.cuda.Event()
                 ev.record(main)
                 freed[i] = ev

@@ -7,7 +7,12 @@
 import sys
 from pathlib import Path
 
+import os
+
 import pytest
+
+# a specialised kernel that fails to compile must fail the test, not fall back to the interpreter kernel silently
+os.environ.setdefault("ARESDB_B200_JIT_STRICT", "1")
 
 ROOT = Path(__file__).resolve().parent.parent
 sys.path.insert(0, str(ROOT))

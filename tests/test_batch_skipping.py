@@ -72,3 +72,16 @@ def test_fused_executor_skips_batches():
     ex.close()
     assert ex.skipped == 1 and ex.calls == 2
     T.assert_same_result(got, T.run_legacy(orc, q, hbs), ctx="fused + skipping")
+
+
+def test_values_that_wrap_in_int32_are_never_skipped_on():
+    """A uint32 value >= 2^31 compares as a negative int32 against an integer literal (the reference's promotion); the
+    zone map's unbounded integers would say otherwise, so such ranges / literals never skip."""
+    from aresdb_b200 import cabi as A, expr as E
+    from aresdb_b200.skipping import filter_excludes_range
+    col = E.Col(0, A.Uint32)
+    big = {0: (2 ** 31 + 5, 2 ** 31 + 9)}
+    assert not filter_excludes_range(E.resolve(E.lt(col, E.Lit(100))), big)     # int32: negative < 100 is TRUE for every row
+    assert not filter_excludes_range(E.resolve(E.gt(col, E.Lit(2 ** 31 + 20))), {0: (1, 2)})
+    assert filter_excludes_range(E.resolve(E.lt(col, E.Lit(100))), {0: (200, 300)})
+    assert filter_excludes_range(E.resolve(E.ge(col, E.Lit(-5))), {0: (200, 300)}) is False

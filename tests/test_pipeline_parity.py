@@ -343,11 +343,13 @@ def _archive_batch(be, seed, runs=6000):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("runs", [6000, 150000])
 @pytest.mark.parametrize("name", ["cfg2", "cfg3_count", "int_sum", "min_city"])
-def test_fused_plan_on_archive_style_batches(name):
-    """Mode-3 columns and base counts go through ExecuteBatchPlan too — the RLE columns are expanded once per
-    batch, the base counts are staged with the columns — and agree with the reference sequence, including
-    the x run-length of SUM / COUNT."""
+def test_fused_plan_on_archive_style_batches(name, runs):
+    """Mode-3 columns and base counts go through ExecuteBatchPlan too — the RLE columns are FIRST-CLASS inputs of the
+    specialised kernel (decoded from their runs inside the tile loop, never expanded), the base counts are staged with
+    the columns — and agree with the reference sequence, including the x run-length of SUM / COUNT.  150000 index
+    positions: dozens of tiles, runs of the finer column crossing tile borders."""
     import ctypes as C
     eng, orc = H.get_backend("b200"), H.get_backend("oracle")
     q = queries()[name]
@@ -360,13 +362,13 @@ def test_fused_plan_on_archive_style_batches(name):
     exp_ex, got_ex = LegacyBatchExecutor(orc.lib, orc.space, q), FusedBatchExecutor(eng.lib, eng.space, q)
     before = jit_launches()
     for seed in (1, 2):
-        exp_ex.process_batch(_archive_batch(orc, seed))
-        got_ex.process_batch(_archive_batch(eng, seed))
+        exp_ex.process_batch(_archive_batch(orc, seed, runs))
+        got_ex.process_batch(_archive_batch(eng, seed, runs))
     exp, got = exp_ex.result(), got_ex.result()
     got_ex.close()
     assert exp.groups > 0
     assert_same_result(got, exp, ctx=f"archive/{name}")
-    # the RLE columns were expanded and the batches ran on the specialised (staged) kernel
+    # the batches ran on the specialised (staged) kernel
     assert jit_launches() - before == 2
 
 
