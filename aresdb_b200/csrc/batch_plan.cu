@@ -1436,10 +1436,17 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
       if (!tileRows) P.denseNd = 0;   // no layout holds the slots: hash table
     }
     if (!tileRows) {
+      // compacted-index form (survivors of the filters gathered per tile before the expensive part): HLL plans, whose
+      // per-row work after the filters (murmur of the value, register lookup, update) dwarfs the filters themselves
+      P.compact = 0;
+      if (allowDense && P.denseNd == 0 && jitAvailable() && planCompactable(P)) {
+        const char *e = getenv("ARESDB_B200_COMPACT");
+        P.compact = e ? (e[0] == '1') : (P.hll != 0);
+      }
       for (uint32_t sl : {slots, slots / 2, slots / 4}) {
         for (uint32_t tr : {3968u, 1920u, 896u}) {  // 128 rows x (31 | 15 | 7) consumer warps
           if (forceTile && tr != forceTile) continue;
-          size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8;
+          size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8 - (P.compact ? kCompactListBytes : 0u);
           uint32_t n = (uint32_t)(avail / stageBytesFor(tr));
           if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; break; }
         }
@@ -1488,7 +1495,8 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   P.stageBytes = (uint32_t)stageBytes;
   P.smemSlots = slots;
   P.tableBytes = P.denseNd != 0 ? (slots * (P.denseFx ? 12 : 9) + 127) / 128 * 128 : slots * 8;
-  return 128 + (size_t)P.tableBytes + stageBytes * P.numStages;
+  if (P.denseNd != 0 || !P.staged) P.compact = 0;
+  return 128 + (size_t)P.tableBytes + (P.compact ? kCompactListBytes : 0u) + stageBytes * P.numStages;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1616,7 +1624,15 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   static const bool keepPositional = [] { const char *e = getenv("ARESDB_B200_EXPAND_RLE"); return e && e[0] == '0'; }();
   if (bp.NumRows >= 1024 && !keepPositional) {
     const uint32_t n = bp.NumRows;
-    const bool firstClass = jitAvailable() && !forceExpand;
+    // (the tile loop is driven by the TMA ring: at least one plain column must be staged for the RLE columns to ride along)
+    int stageable = 0;
+    for (int c = 0; c < P.ncols; c++) {
+      const DevColumn &col = P.cols[c];
+      if (col.used && col.width <= 4 && (col.in.mode == 1 || col.in.mode == 2)) stageable++;
+      if (col.used && col.in.mode == 3 && col.width <= 4 && bp.BaseCounts != nullptr &&
+          reinterpret_cast<const uint32_t *>(col.in.base) == bp.BaseCounts && col.in.length >= n) stageable++;
+    }
+    const bool firstClass = jitAvailable() && !forceExpand && stageable > 0;
     int nrle = 0;
     for (int c = 0; c < P.ncols; c++) {
       DevColumn &col = P.cols[c];

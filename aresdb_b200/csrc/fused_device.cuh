@@ -123,22 +123,24 @@ static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, uns
   return 0xFFFFFFFFu;
 }
 
+// parks one row (out of line: it is rare, and globalUpdate is inlined at every aggregation site)
+static __device__ __noinline__ void globalPark(const DevTable &G, unsigned long long key, const uint64_t *roww, uint64_t val) {
+  const uint32_t i = atomicAdd(&G.counters[4], 1u);
+  if (i < kSpillCap) {
+    SpillEntry e;
+    e.key = key; e.val = val;
+#pragma unroll
+    for (int w = 0; w < 4; w++) e.row[w] = roww ? roww[w] : 0;
+    G.spill[i] = e;
+  } else {
+    atomicExch(&G.counters[5], 1u);
+  }
+}
+
 __device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsigned long long key, const uint64_t *roww,
                                              uint64_t val, bool spillWhenStopped = false) {
   uint32_t slot = globalFindOrClaim(G, key, roww, spillWhenStopped);
-  if (slot == kSlotSpill) {
-    const uint32_t i = atomicAdd(&G.counters[4], 1u);
-    if (i < kSpillCap) {
-      SpillEntry e;
-      e.key = key; e.val = val;
-#pragma unroll
-      for (int w = 0; w < 4; w++) e.row[w] = roww ? roww[w] : 0;
-      G.spill[i] = e;
-    } else {
-      atomicExch(&G.counters[5], 1u);
-    }
-    return;
-  }
+  if (slot == kSlotSpill) { globalPark(G, key, roww, val); return; }
   if (slot != 0xFFFFFFFFu) aggAtomic(op, &G.acc[slot], val);
 }
 

@@ -290,6 +290,10 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   if (threadIdx.x == 0) {
     *claims = 0;
     *misses = 0;
+    reinterpret_cast<uint32_t *>(smem + 76)[0] = 0;   // compaction cursors / stop words (JIT_COMPACT)
+    reinterpret_cast<uint32_t *>(smem + 76)[1] = 0;
+    reinterpret_cast<uint32_t *>(smem + 76)[2] = 0;
+    reinterpret_cast<uint32_t *>(smem + 76)[3] = 0;
     for (int s = 0; s < JIT_STAGES; s++) {
       mbarInit(&bars[s], 1);
       mbarInit(&empty[s], JIT_THREADS / 32 - 1);
@@ -331,9 +335,9 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     for (uint32_t t = first; t < P.numFullTiles; t += step, it++) {
       const uint32_t s = it % JIT_STAGES, parity = (it / JIT_STAGES) & 1;
       // (read before the wait: the L2 round trip overlaps with it; a slightly older value only delays the stop by a tile)
-      const uint32_t stopFlag = kCanDrain ? *reinterpret_cast<volatile uint32_t *>(&P.G.counters[3]) : 0u;
+      const uint32_t stopFlag = kCanDrain ? __ldcg(&P.G.counters[3]) : 0u;   // (L2, not system scope)
       mbarWait(&bars[s], parity);
-      if (!draining && it >= myStart && stopFlag != 0u) {
+      if (!JIT_COMPACT && !draining && it >= myStart && stopFlag != 0u) {   // (compacted form: decided CTA-wide below)
         draining = true;
         foldedUntil = it;
       }
@@ -356,6 +360,52 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         if (rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, 4u, fast, anySlow, dslot, meas, mraw))
           jitAggregateDense(touchedAddr, tAcc, P, stage, q, t * JIT_TILE_ROWS + q * 4, 4u, repOff, fast, anySlow, dslot, meas, mraw);
         (void)allowClaim; (void)bypass;
+#elif JIT_COMPACT
+        // Compacted index vector (warp ballot + prefix sum): pass 1 evaluates ONLY the filters of the thread's quad and
+        // appends the surviving rows' tile positions to a CTA-wide list — a warp reserves its span with one add on the
+        // shared cursor, lanes place their rows by an in-warp prefix sum; pass 2 hands the list out four rows per thread
+        // and evaluates dimensions / measure / aggregation on those only, so the expensive part runs on dense quads
+        // (roughly `selectivity` of the warps do it, the rest skip).  One named barrier per tile among the consumers:
+        // list and cursor are double-buffered by tile parity.  The growth stop is decided CTA-wide here (every warp
+        // must reach the barrier): thread 0's view of the flag, published before the barrier.
+        (void)meas;
+        const uint32_t par = it & 1u;
+        uint16_t *list = reinterpret_cast<uint16_t *>(smem + 128 + JIT_SMEM_SLOTS * 8) + par * 4096u;
+        uint32_t *cursor = reinterpret_cast<uint32_t *>(smem + 76) + par;       // smem + 76, + 80
+        uint32_t *stopWord = reinterpret_cast<uint32_t *>(smem + 84) + par;     // smem + 84, + 88
+        const uint32_t alive = rowAlive(stage, q, t * JIT_TILE_ROWS + q * 4, P);
+        const uint32_t lane = threadIdx.x & 31u;
+        uint32_t incl = __popc(alive);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+          const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+          if ((int)lane >= o) incl += up;
+        }
+        uint32_t base = 0;
+        if (lane == 31) base = atomicAdd(cursor, incl);
+        base = __shfl_sync(0xFFFFFFFFu, base, 31) + incl - __popc(alive);
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+          if ((alive >> r) & 1u) list[base++] = (uint16_t)(q * 4 + r);
+        if (threadIdx.x == 0) {
+          *stopWord = kCanDrain ? stopFlag : 0u;
+          reinterpret_cast<uint32_t *>(smem + 76)[par ^ 1u] = 0;   // the other tile's cursor: nobody touches it until after the next barrier
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        if (*reinterpret_cast<volatile uint32_t *>(stopWord) != 0u) {
+          draining = true;
+          foldedUntil = it;
+        } else {
+          const uint32_t nAlive = *reinterpret_cast<volatile uint32_t *>(cursor);
+          for (uint32_t j = threadIdx.x; j * 4 < nAlive; j += kConsumerThreads) {
+            uint32_t rows4[4];
+#pragma unroll
+            for (int r = 0; r < 4; r++) rows4[r] = j * 4 + r < nAlive ? (uint32_t)list[j * 4 + r] : 0xFFFFu;
+            uint64_t key[4][JIT_KW], m2[4];
+            const uint32_t a2 = rowEvalGather(stage, rows4, t * JIT_TILE_ROWS, P, key, m2);
+            jitAggregate(T, P, a2, key, m2, allowClaim, bypass, misses);
+          }
+        }
 #else
         uint64_t key[4][JIT_KW];
         const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);

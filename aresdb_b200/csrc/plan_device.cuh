@@ -101,6 +101,8 @@ struct DevPlan {
   uint8_t foreignClass[kMaxForeignCols];    // ValClass a read of foreign column k yields
   uint8_t pad2[1];
   const DevJoin *join;     // device copy of the tables' indexes and the foreign columns' batches
+  uint8_t compact;         // survivors of the filters are compacted per tile (warp ballot + prefix sum into a CTA-wide index
+                           // list) before dimensions / measure are evaluated — chosen when that work dominates (HLL)
   uint32_t resume;         // 1: relaunch of the same batch after the group table grew (DevTable::progress holds the resume points)
 };
 
@@ -112,6 +114,8 @@ constexpr uint32_t kGlobalDenseMaxSlots = 1u << 21;   // 16 MB of accumulators p
 // when NVRTC is unavailable or disabled (ARESDB_B200_JIT=0) so that the caller falls back to the
 // interpreter kernel; throws EngineError when code generation / compilation fails.
 bool jitAvailable();
+bool planCompactable(const DevPlan &P);   // filters first, no RLE / base counts / joins: the compacted-index form applies
+constexpr uint32_t kCompactListBytes = 16384;  // two lists (double-buffered per tile) of the survivors' tile row numbers (u16)
 void jitAnalyzeDense(DevPlan &P, bool bypass);
 size_t jitCompileOnly(const DevPlan &P, std::string *sourceOut);
 bool jitLaunchStaged(const DevPlan &P, const DevTable &G, size_t smemBytes, int grid, cudaStream_t s);
