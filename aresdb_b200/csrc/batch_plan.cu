@@ -1409,14 +1409,15 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
         for (uint32_t n = kMaxStages; n >= 2 && !tileRows; n--) {
           const size_t need = 128 + n * stageBytesFor(tr);
           if (need >= (size_t)kSmemBudget) continue;
-          const size_t slotBytes = P.denseFx ? 12 : 9;   // three 32-bit piece counters, or flag + 8-byte accumulator
+          // three 32-bit piece counters, or flag + 8-byte accumulator; HLL: one 32-bit map entry (slot -> group's registers)
+          const size_t slotBytes = P.hll ? 4 : P.denseFx ? 12 : 9;
           uint32_t cap = (uint32_t)(((size_t)kSmemBudget - need) / slotBytes / 16 * 16);
           if (cap > kDenseMaxSlots) cap = kDenseMaxSlots;
           if (cap >= P.denseTotal) { tileRows = tr; stages = n; slots = cap; }
         }
         if (tileRows) break;
       }
-      if (!tileRows && P.neutralSafe && P.denseTotal <= kGlobalDenseMaxSlots) {
+      if (!tileRows && !P.hll && P.neutralSafe && P.denseTotal <= kGlobalDenseMaxSlots) {
         // more slots than a CTA holds: one accumulator array in global memory for the whole grid; shared memory is all ring
         for (uint32_t tr : {3968u, 1920u, 896u}) {
           if (forceTile && tr != forceTile) continue;
@@ -1436,17 +1437,21 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
       if (!tileRows) P.denseNd = 0;   // no layout holds the slots: hash table
     }
     if (!tileRows) {
-      // compacted-index form (survivors of the filters gathered per tile before the expensive part): HLL plans, whose
-      // per-row work after the filters (murmur of the value, register lookup, update) dwarfs the filters themselves
+      // compacted-index form (survivors of the filters gathered per tile before the expensive part)
       P.compact = 0;
       if (allowDense && P.denseNd == 0 && jitAvailable() && planCompactable(P)) {
+        // (measured on cfg4 HLL without zone maps: 1.40 ms against 1.25 ms for the plain form — the kernel is bound by the
+        // latency of its directory / register accesses, and the barrier of the compaction costs more than the instructions
+        // it saves, profiles/r02_fused_hll_v2_compact_rejected.summary.txt: opt-in only)
         const char *e = getenv("ARESDB_B200_COMPACT");
-        P.compact = e ? (e[0] == '1') : (P.hll != 0);
+        P.compact = e ? (e[0] == '1') : 0;
       }
+      if (P.partition) P.compact = 0;
       for (uint32_t sl : {slots, slots / 2, slots / 4}) {
+        if (P.partition && sl != 8192) break;      // the tile buffer of the partitioned form IS the 64 KB table region
         for (uint32_t tr : {3968u, 1920u, 896u}) {  // 128 rows x (31 | 15 | 7) consumer warps
           if (forceTile && tr != forceTile) continue;
-          size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8 - (P.compact ? kCompactListBytes : 0u);
+          size_t avail = (size_t)kSmemBudget - 128 - (size_t)sl * 8 - (P.compact ? kCompactListBytes : 0u) - (P.partition ? kPartitionExtraBytes : 0u);
           uint32_t n = (uint32_t)(avail / stageBytesFor(tr));
           if (n >= 2) { tileRows = tr; stages = n > (uint32_t)kMaxStages ? kMaxStages : n; break; }
         }
@@ -1494,9 +1499,10 @@ static size_t layoutStages(DevPlan &P, uint32_t expectedGroups, bool allowDense 
   if (P.denseNd == 0) P.denseGlobal = 0;
   P.stageBytes = (uint32_t)stageBytes;
   P.smemSlots = slots;
-  P.tableBytes = P.denseNd != 0 ? (slots * (P.denseFx ? 12 : 9) + 127) / 128 * 128 : slots * 8;
-  if (P.denseNd != 0 || !P.staged) P.compact = 0;
-  return 128 + (size_t)P.tableBytes + (P.compact ? kCompactListBytes : 0u) + stageBytes * P.numStages;
+  P.tableBytes = P.denseNd != 0 ? (slots * (P.hll ? 4 : P.denseFx ? 12 : 9) + 127) / 128 * 128 : slots * 8;
+  if (P.denseNd != 0 || !P.staged) { P.compact = 0; P.partition = 0; }
+  if (P.partition && (slots != 8192 || P.tileRows > 4096)) P.partition = 0;
+  return 128 + (size_t)P.tableBytes + (P.compact ? kCompactListBytes : 0u) + (P.partition ? kPartitionExtraBytes : 0u) + stageBytes * P.numStages;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1521,6 +1527,26 @@ __global__ void __launch_bounds__(256) mergeSpillKernel(DevTable G, uint32_t n, 
   for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const SpillEntry e = G.spill[i];
     globalUpdate(G, op, e.key, G.rows ? e.row : nullptr, e.val);
+  }
+}
+
+// Radix-partitioned aggregation, pass 2: the entries the fused kernel appended tile by tile (each tile's span sorted by
+// partition, its directory line giving the 64 segment offsets) are folded PARTITION-MAJOR: warp w takes pair
+// (partition, tile) number w, w + W, ... in that order, so that at any moment the whole grid updates the same
+// partition = one contiguous 1/64 of the table's slots, which stays in L2 while it is being worked on.
+__global__ void __launch_bounds__(256)
+partitionAggregateKernel(const uint4 *__restrict__ entries, const uint32_t *__restrict__ dir, uint32_t numTiles, AggOp op, DevTable G) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint64_t warps = (uint64_t)gridDim.x * (blockDim.x >> 5), pairs = (uint64_t)kPartitions * numTiles;
+  for (uint64_t idx = (uint64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); idx < pairs; idx += warps) {
+    const uint32_t p = (uint32_t)(idx / numTiles), tile = (uint32_t)(idx % numTiles);
+    const uint32_t *line = dir + (size_t)tile * kPartDirWords;
+    const uint32_t begin = line[kPartitions + 1] + line[p], end = line[kPartitions + 1] + line[p + 1];
+    for (uint32_t i = begin + lane; i < end; i += 32) {
+      const uint4 e = entries[i];
+      globalUpdate(G, op, (unsigned long long)e.x | ((unsigned long long)e.y << 32), nullptr,
+                   (uint64_t)e.z | ((uint64_t)e.w << 32), /*spillWhenStopped=*/true);
+    }
   }
 }
 
@@ -1684,7 +1710,27 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
     ARES_CUDA(cudaStreamSynchronize(s));   // J is reused by the next call of this thread
     P.join = joinMem->as<DevJoin>();
   }
+  // radix-partitioned aggregation when the table is far beyond L2 (or ARESDB_B200_PARTITION=1): packed keys, plain sums /
+  // min / max, specialised kernel only
+  {
+    const char *e = getenv("ARESDB_B200_PARTITION");
+    const bool want = e ? e[0] == '1' : st->capacity >= kPartitionMinSlots;
+    P.partition = want && jitAvailable() && st->keyMode == KEY_PACKED && !st->hll && P.numForeignCols == 0 && st->capacity >= 4096;
+    int lg = 0;
+    while (((size_t)1 << lg) < st->capacity) lg++;
+    P.partShift = (uint8_t)(lg > 6 ? lg - 6 : 0);
+  }
   size_t smemBytes = layoutStages(P, st->spec.ExpectedGroups);
+  std::unique_ptr<Scratch> partMem;
+  if (P.partition) {
+    const size_t dirBytes = ((size_t)P.numFullTiles * kPartDirWords * 4 + 255) / 256 * 256;
+    partMem.reset(new Scratch(256 + dirBytes + (size_t)P.numRows * sizeof(uint4), s));
+    uint8_t *pm = partMem->as<uint8_t>();
+    P.partCursor = reinterpret_cast<uint32_t *>(pm);
+    P.partDir = reinterpret_cast<uint32_t *>(pm + 256);
+    P.partBuf = reinterpret_cast<uint4 *>(pm + 256 + dirBytes);
+    ARES_CUDA(cudaMemsetAsync(pm, 0, 256, s));
+  }
   // per-tile run hints of the first-class RLE columns (the tile size is known now)
   for (int c = 0; c < P.ncols; c++) {
     DevColumn &col = P.cols[c];
@@ -1700,7 +1746,7 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
   // room in the group table (see "growth of the group table"): the direct path and the direct-indexed kernels are not
   // waited for, so what they may insert is reserved up front (flush of the CTA slots / fold of the global slot array;
   // out-of-range rows park); hash-table tile kernels are checked after the launch and resumed when they stopped.
-  const bool resumable = P.staged && P.denseNd == 0 && !st->hllDense;
+  const bool resumable = P.staged && P.denseNd == 0 && !st->hllDense && !P.partition;
   if (!resumable && !st->hllDense) ensureRoom(st, P.staged ? (uint64_t)P.denseTotal : (uint64_t)P.numRows, s);
   P.ctaAcc = st->ctaAcc;   // (after a possible growth: the slices live in the table's allocation)
   static bool attrSet[64] = {false};
@@ -1733,6 +1779,15 @@ static void executePlan(AggState *st, const BatchPlan &bp, cudaStream_t s) {
     bool checkAfter = false;   // a hash-table tile kernel ran: wait for it and resume it if the table stopped it
     if (P.staged && jitLaunchStaged(P, st->table, smemBytes, grid, s)) {
       checkAfter = P.denseNd == 0 && !st->hllDense;
+      if (P.partition) {   // pass 2: fold the entries partition by partition; the table is checked (and grown) after every batch
+        partitionAggregateKernel<<<smCount() * 8, 256, 0, s>>>(P.partBuf, P.partDir, P.numFullTiles, (AggOp)P.aggOp, st->table);
+        checkLastError("partitionAggregate");
+        const TableCounters c = readCounters(st, s);
+        st->everChecked = true;
+        if (c.overflow) checkOverflow(st, &c.occupied);
+        if (c.stop || c.spilled) settleTable(st, s);
+        return;
+      }
       if (P.denseGlobal) {
         DenseFold F;
         memset(&F, 0, sizeof(F));
@@ -2175,6 +2230,10 @@ CGoCallResHandle AresJitDryRun(AggSpec spec, const BatchPlan *plan, char **sourc
     static thread_local DevPlan P;
     compilePlan(&st, *plan, P);
     P.tailBegin = 0;
+    if (const char *e = getenv("ARESDB_B200_PARTITION")) {   // the partitioned form of the kernel (normally chosen by table size)
+      P.partition = e[0] == '1' && st.keyMode == KEY_PACKED && !st.hll && P.numForeignCols == 0;
+      P.partShift = 15;
+    }
     layoutStages(P, spec.ExpectedGroups);
     std::string src;
     size_t n = P.staged ? jitCompileOnly(P, &src) : 0;

@@ -6,6 +6,8 @@
 // rowEval() precede this text.
 namespace aresb {
 
+constexpr uint32_t kPartitionsJ = 64;   // = kPartitions (plan_device.cuh)
+
 __device__ __forceinline__ void jitIssueTile(const JitParams &P, uint32_t tile, uint8_t *stage, uint64_t *bar) {
   mbarExpectTx(bar, JIT_STAGE_TX_BYTES);
 #pragma unroll
@@ -119,6 +121,34 @@ __device__ __forceinline__ void redSharedPred(uint32_t addr, unsigned long long 
   } else if (p) smemAtomic((AggOp)OP, generic, v);
 }
 
+__device__ __forceinline__ uint8_t *denseSmemBase() {
+  extern __shared__ __align__(128) uint8_t denseSmem0[];
+  return denseSmem0 + 128;
+}
+
+// Dense-register HLL, rows the map could not serve (`unknown`: inside the zone map, slot not resolved yet) or that lie
+// outside the zone map: the group's directory slot is found the general way; resolved slots are entered into the map.
+static __device__ __noinline__ void denseColdRowsHll(const uint8_t *stage, uint32_t q, uint32_t row0, const JitParams &P, uint32_t nvalid,
+                                                     uint32_t inRange, uint32_t unknown, uint32_t s0, uint32_t s1, uint32_t s2, uint32_t s3) {
+#if JIT_HLL == 2
+  uint64_t key[4][JIT_KW], meas[4];
+  const uint32_t slot[4] = {s0, s1, s2, s3};
+  uint32_t alive = rowEvalGeneric(stage, q, row0, P, key, meas);
+  alive &= (1u << nvalid) - 1u;
+  volatile uint32_t *map = reinterpret_cast<volatile uint32_t *>(denseSmemBase());
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    if (!((alive >> r) & 1u)) continue;
+    const bool in = (inRange >> r) & 1u;
+    if (in && !((unknown >> r) & 1u)) continue;            // folded on the fast path
+    const uint32_t ds = hllDenseLocate(P.G, nullptr, jitKeyOf(key, meas, r), JIT_KW == 1 ? nullptr : key[r]);
+    if (ds == 0xFFFFFFFFu) continue;
+    if (in) map[slot[r]] = ds;
+    atomicMax(&P.G.regs[(size_t)ds * kHllRegisters + ((uint32_t)meas[r] & (kHllRegisters - 1))], (uint32_t)meas[r] + 1u);
+  }
+#endif
+}
+
 // `repOff`: this lane's copy of the slots (few slots are replicated per lane), in slots — loop invariant, computed once.
 __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned long long *tAcc, const JitParams &P, const uint8_t *stage,
                                                   uint32_t q, uint32_t row0, uint32_t nvalid, uint32_t repOff, const bool (&fast)[4],
@@ -129,6 +159,27 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
   uint32_t s[4];
 #pragma unroll
   for (int r = 0; r < 4; r++) s[r] = dslot[r] + repOff;
+  if (JIT_HLL == 2) {
+    // Dense-register HLL addressed by the zone map: the table region is a map slot -> directory slot of the group (whose
+    // 16384 registers live at regs + 16384 * that).  A known slot costs one shared-memory load and one fire-and-forget
+    // RED.MAX; an unknown one (first row of the group in this CTA) goes through denseColdRows, which fills the map.
+    volatile uint32_t *map = reinterpret_cast<volatile uint32_t *>(denseSmemBase());
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t ds = fast[r] ? map[s[r]] : 0u;
+      const bool known = fast[r] && ds != 0xFFFFFFFFu;
+      cold = cold || (fast[r] && !known);
+      if (known) atomicMax(&P.G.regs[(size_t)ds * kHllRegisters + ((uint32_t)meas[r] & (kHllRegisters - 1))], (uint32_t)meas[r] + 1u);
+    }
+    if (cold) {
+      const uint32_t unknown = (fast[0] && map[s[0]] == 0xFFFFFFFFu ? 1u : 0u) | (fast[1] && map[s[1]] == 0xFFFFFFFFu ? 2u : 0u) |
+                               (fast[2] && map[s[2]] == 0xFFFFFFFFu ? 4u : 0u) | (fast[3] && map[s[3]] == 0xFFFFFFFFu ? 8u : 0u);
+      const uint32_t inRange = (fast[0] ? 1u : 0u) | (fast[1] ? 2u : 0u) | (fast[2] ? 4u : 0u) | (fast[3] ? 8u : 0u);
+      // rows already folded through the map must not be folded again: hand over only unknown-slot and out-of-range rows
+      denseColdRowsHll(stage, q, row0, P, nvalid, inRange, unknown, s[0], s[1], s[2], s[3]);
+    }
+    return;
+  }
   if (JIT_DENSE == 2) {
     // One accumulator array for the whole grid (more slots than a CTA holds).  No flags: a slot was reached iff it
     // differs from the aggregate's neutral element, so a row whose value would leave it there (-0.0 for float sums,
@@ -271,7 +322,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   const uint32_t denseSlots = JIT_DENSE == 2 ? 0u : P.dRepStride * P.dReps;   // <= kDenseCap (host); 2: nothing CTA-private
   const uint32_t repOff = JIT_DENSE == 2 ? (blockIdx.x & (P.dReps - 1u)) * P.dRepStride : (threadIdx.x & (P.dReps - 1u)) * P.dRepStride *
                                                 (JIT_DENSE_ACC == 4 ? 12u : 1u);   // this lane's copy of the slots (integer form: in bytes)
-  for (uint32_t i = threadIdx.x; i < denseSlots; i += JIT_THREADS) {
+  for (uint32_t i = threadIdx.x; JIT_HLL == 2 && i < denseSlots; i += JIT_THREADS) reinterpret_cast<uint32_t *>(tKeys)[i] = 0xFFFFFFFFu;
+  for (uint32_t i = threadIdx.x; JIT_HLL != 2 && i < denseSlots; i += JIT_THREADS) {
     if (JIT_DENSE_FLAGS) touched[i] = 0;
     if (JIT_DENSE_ACC != 1) tAcc[i] = P.accNeutral;
     if (JIT_DENSE_ACC == 4) {
@@ -294,6 +346,10 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
     reinterpret_cast<uint32_t *>(smem + 76)[1] = 0;
     reinterpret_cast<uint32_t *>(smem + 76)[2] = 0;
     reinterpret_cast<uint32_t *>(smem + 76)[3] = 0;
+    if (JIT_PARTITION) {   // partition histogram / fill cursors
+      uint32_t *h = reinterpret_cast<uint32_t *>(smem + 128 + JIT_SMEM_SLOTS * 8);
+      for (int i = 0; i < 3 * (int)kPartitionsJ + 2; i++) h[i] = 0;
+    }
     for (int s = 0; s < JIT_STAGES; s++) {
       mbarInit(&bars[s], 1);
       mbarInit(&empty[s], JIT_THREADS / 32 - 1);
@@ -315,7 +371,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   // lost and nothing is counted twice; the unit is one warp's 128 rows of one tile.
   // (Direct-indexed kernels never drain — the host does not wait for them: their out-of-range rows and their flush park
   // new groups in DevTable::spill while the table is at its threshold.)
-  constexpr bool kCanDrain = JIT_DENSE == 0;
+  constexpr bool kCanDrain = JIT_DENSE == 0 && JIT_PARTITION == 0;   // (the partitioned form inserts nothing in this kernel)
   const uint32_t progIdx = blockIdx.x * kProgressWarps + (threadIdx.x >> 5);
   uint32_t myStart = 0;
   if (kCanDrain && P.resume) myStart = P.G.progress[progIdx];
@@ -406,6 +462,61 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
             jitAggregate(T, P, a2, key, m2, allowClaim, bypass, misses);
           }
         }
+#elif JIT_PARTITION
+        // Radix-partitioned aggregation, pass 1 (the group table is far beyond L2: a random atomic per row would miss it
+        // every time).  The tile's surviving rows become (key, measure) entries, counting-sorted in shared memory by the
+        // PARTITION of the table their home slot lies in (64 partitions = 64 contiguous slot ranges), and are appended
+        // to the batch's entry buffer in HBM as one contiguous, partition-ordered span (coalesced 16-byte writes) with a
+        // directory line saying where each partition's segment of this tile starts.  Pass 2 (partitionAggregateKernel)
+        // then folds partition after partition, so that the slot range being updated stays L2-resident.
+        static_assert(JIT_KW == 1 && JIT_HLL == 0, "partitioned form: packed keys");
+        uint4 *buf = reinterpret_cast<uint4 *>(tKeys);                                   // 3968 entries x 16 B <= 64 KB
+        uint32_t *hist = reinterpret_cast<uint32_t *>(smem + 128 + JIT_SMEM_SLOTS * 8);  // [64]
+        uint32_t *off = hist + kPartitionsJ;                                              // [65]
+        uint32_t *fill = off + kPartitionsJ + 1;                                          // [64]
+        uint32_t *span = fill + kPartitionsJ;                                             // [1]
+        uint64_t key[4][JIT_KW];
+        const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
+        uint32_t part[4];
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          part[r] = globalHome(P.G, key[r][0]) >> P.partShift;
+          if ((alive >> r) & 1u) atomicAdd(&hist[part[r]], 1u);
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        if (threadIdx.x < 32) {   // one warp: exclusive scan of the 64 counts, the tile's span in the entry buffer, its directory line
+          const uint32_t c0 = hist[2 * threadIdx.x], c1 = hist[2 * threadIdx.x + 1];
+          uint32_t incl = c0 + c1;
+#pragma unroll
+          for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t up = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+            if ((int)threadIdx.x >= o) incl += up;
+          }
+          const uint32_t ex = incl - c0 - c1, total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+          uint32_t base = 0;
+          if (threadIdx.x == 0) base = atomicAdd(P.partCursor, total);
+          base = __shfl_sync(0xFFFFFFFFu, base, 0);
+          off[2 * threadIdx.x] = ex; off[2 * threadIdx.x + 1] = ex + c0;
+          hist[2 * threadIdx.x] = 0; hist[2 * threadIdx.x + 1] = 0;
+          fill[2 * threadIdx.x] = 0; fill[2 * threadIdx.x + 1] = 0;
+          uint32_t *line = P.partDir + (size_t)t * (kPartitionsJ + 2);
+          line[2 * threadIdx.x] = ex; line[2 * threadIdx.x + 1] = ex + c0;
+          if (threadIdx.x == 0) { off[kPartitionsJ] = total; *span = base; line[kPartitionsJ] = total; line[kPartitionsJ + 1] = base; }
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+#pragma unroll
+        for (int r = 0; r < 4; r++) {
+          if (!((alive >> r) & 1u)) continue;
+          const uint32_t pos = off[part[r]] + atomicAdd(&fill[part[r]], 1u);
+          buf[pos] = make_uint4((uint32_t)key[r][0], (uint32_t)(key[r][0] >> 32), (uint32_t)meas[r], (uint32_t)(meas[r] >> 32));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        {
+          const uint32_t total = off[kPartitionsJ], base = *span;
+          for (uint32_t i = threadIdx.x; i < total; i += kConsumerThreads) P.partBuf[base + i] = buf[i];
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kConsumerThreads) : "memory");
+        (void)allowClaim; (void)bypass;
 #else
         uint64_t key[4][JIT_KW];
         const uint32_t alive = rowEval(stage, q, t * JIT_TILE_ROWS + q * 4, P, key, meas);
@@ -461,7 +572,12 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         uint64_t key[4][JIT_KW];
         uint32_t alive = rowEval(stages, q, done + q * 4, P, key, meas);
         alive &= (1u << nvalid) - 1u;
+#if JIT_PARTITION
+        for (int r = 0; r < 4; r++)   // (the shared table region is the tile buffer in this form: straight to the global table)
+          if ((alive >> r) & 1u) globalUpdate(P.G, (AggOp)JIT_AGG_OP, jitKeyOf(key, meas, r), nullptr, meas[r], /*spillWhenStopped=*/true);
+#else
         jitAggregate(T, P, alive, key, meas, true, false, misses);
+#endif
 #endif
       }
       done += rows;
@@ -505,7 +621,7 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
   return;
 #endif
   // (the CTA's table is folded whatever the state of the global one: groups it cannot take right now are parked)
-  for (uint32_t i = threadIdx.x; i < JIT_SMEM_SLOTS; i += JIT_THREADS) {
+  for (uint32_t i = threadIdx.x; i < (JIT_PARTITION ? 0u : (uint32_t)JIT_SMEM_SLOTS); i += JIT_THREADS) {
     unsigned long long k = tKeys[i];
     if (k != kEmptyKey) globalUpdate(P.G, (AggOp)JIT_AGG_OP, k, nullptr, __ldcg(&tAcc[i]), /*spillWhenStopped=*/true);
   }

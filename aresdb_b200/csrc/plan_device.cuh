@@ -103,6 +103,12 @@ struct DevPlan {
   const DevJoin *join;     // device copy of the tables' indexes and the foreign columns' batches
   uint8_t compact;         // survivors of the filters are compacted per tile (warp ballot + prefix sum into a CTA-wide index
                            // list) before dimensions / measure are evaluated — chosen when that work dominates (HLL)
+  uint8_t partition;       // radix-partitioned aggregation (tables beyond L2): the kernel emits (key, measure) entries sorted by
+                           // table partition, a second kernel folds them partition by partition
+  uint8_t partShift;       // partition of a key = its home slot >> partShift (64 partitions)
+  uint4 *partBuf;          // [numRows] entries of this batch
+  uint32_t *partDir;       // [numFullTiles][kPartDirWords]: per tile, offsets of the 64 partition segments + span base
+  uint32_t *partCursor;    // entries appended so far
   uint32_t resume;         // 1: relaunch of the same batch after the group table grew (DevTable::progress holds the resume points)
 };
 
@@ -115,6 +121,10 @@ constexpr uint32_t kGlobalDenseMaxSlots = 1u << 21;   // 16 MB of accumulators p
 // interpreter kernel; throws EngineError when code generation / compilation fails.
 bool jitAvailable();
 bool planCompactable(const DevPlan &P);   // filters first, no RLE / base counts / joins: the compacted-index form applies
+constexpr uint32_t kPartitions = 64;
+constexpr uint32_t kPartDirWords = kPartitions + 2;   // off[0..64] (off[64] = entries of the tile), span base
+constexpr uint32_t kPartitionExtraBytes = 2048;   // histogram / offsets / fill cursors behind the 64 KB tile buffer
+constexpr size_t kPartitionMinSlots = (size_t)1 << 23;   // tables from 8M slots (>= 128 MB of keys + accumulators: beyond L2)
 constexpr uint32_t kCompactListBytes = 16384;  // two lists (double-buffered per tile) of the survivors' tile row numbers (u16)
 void jitAnalyzeDense(DevPlan &P, bool bypass);
 size_t jitCompileOnly(const DevPlan &P, std::string *sourceOut);

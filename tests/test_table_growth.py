@@ -54,6 +54,18 @@ elif case == "spill":     # direct-indexed kernels with the zone map of ANOTHER 
     got = T.run_fused(eng, q, small, zone_maps=zms)
     assert T.dense_launches(eng) - before == 2 and exp.groups > 4096
     T.assert_same_result(got, exp, ctx=case)
+elif case == "partition":   # radix-partitioned aggregation forced on (ARESDB_B200_PARTITION=1): entries sorted by table partition per
+    # tile, folded partition by partition — same results as the direct form, for sums / counts / min, few and many groups
+    big = [synth.generate_batch(d, 700000, num_cities=120, null_rate=0.02) for d in range(2)]
+    qs = {"unique": AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE)),
+          "cfg3": AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0))], [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE)),
+          "count": AggQuery([], [CITY, STATUS], Measure("count")),
+          "min": AggQuery([E.eq(STATUS, E.Lit(2))], [E.floor(TS, E.Lit(60))], Measure("min", CITY))}
+    import ctypes as C
+    for name, q in qs.items():
+        exp = T.run_legacy(orc, q, big)
+        got = T.run_fused(eng, q, big)
+        assert (got.packed_rows() == exp.packed_rows()).all() and got.measures.tobytes() == exp.measures.tobytes(), name
 elif case == "merge":     # AggStateMerge of more rows than the table holds
     from aresdb_b200.executor import FusedBatchExecutor
     q = AggQuery([], [TS, CITY], Measure("count"))
@@ -76,12 +88,15 @@ print("ok")
 
 
 @pytest.mark.parametrize("jit", ["1", "0"])
-@pytest.mark.parametrize("case,slots", [("hash", 1 << 17), ("hash_big", 0), ("hash32", 1 << 17), ("spill", 1 << 12), ("merge", 1 << 12)])
+@pytest.mark.parametrize("case,slots", [("hash", 1 << 17), ("hash_big", 0), ("hash32", 1 << 17), ("spill", 1 << 12), ("merge", 1 << 12),
+                                        ("partition", 0), ("partition", 1 << 18)])
 def test_table_grows(case, slots, jit):
-    if jit == "0" and case == "spill":
-        pytest.skip("the interpreter has no direct-indexed form")
+    if jit == "0" and case in ("spill", "partition"):
+        pytest.skip("the interpreter has no direct-indexed / partitioned form")
     code = CHILD.format(tests=str(ROOT / "tests"), root=str(ROOT), case=case)
     env = dict(os.environ, ARESDB_B200_JIT=jit)
+    if case == "partition":
+        env["ARESDB_B200_PARTITION"] = "1"
     if slots:
         env["ARESDB_B200_TABLE_SLOTS"] = str(slots)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=900)
