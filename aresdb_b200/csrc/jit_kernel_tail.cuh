@@ -163,17 +163,22 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     // Dense-register HLL addressed by the zone map: the table region is a map slot -> directory slot of the group (whose
     // 16384 registers live at regs + 16384 * that).  A known slot costs one shared-memory load and one fire-and-forget
     // RED.MAX; an unknown one (first row of the group in this CTA) goes through denseColdRows, which fills the map.
-    volatile uint32_t *map = reinterpret_cast<volatile uint32_t *>(denseSmemBase());
+    // (the four map entries are read back to back — plain loads: a stale "unknown" only sends the row to the cold path,
+    // which resolves the slot again — and only then the four updates are issued)
+    const uint32_t *map = reinterpret_cast<const uint32_t *>(denseSmemBase());
+    asm volatile("" ::: "memory");
+    uint32_t ds[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) ds[r] = map[fast[r] ? s[r] : 0u];
 #pragma unroll
     for (int r = 0; r < 4; r++) {
-      const uint32_t ds = fast[r] ? map[s[r]] : 0u;
-      const bool known = fast[r] && ds != 0xFFFFFFFFu;
+      const bool known = fast[r] && ds[r] != 0xFFFFFFFFu;
       cold = cold || (fast[r] && !known);
-      if (known) atomicMax(&P.G.regs[(size_t)ds * kHllRegisters + ((uint32_t)meas[r] & (kHllRegisters - 1))], (uint32_t)meas[r] + 1u);
+      if (known) atomicMax(&P.G.regs[(size_t)ds[r] * kHllRegisters + ((uint32_t)meas[r] & (kHllRegisters - 1))], (uint32_t)meas[r] + 1u);
     }
     if (cold) {
-      const uint32_t unknown = (fast[0] && map[s[0]] == 0xFFFFFFFFu ? 1u : 0u) | (fast[1] && map[s[1]] == 0xFFFFFFFFu ? 2u : 0u) |
-                               (fast[2] && map[s[2]] == 0xFFFFFFFFu ? 4u : 0u) | (fast[3] && map[s[3]] == 0xFFFFFFFFu ? 8u : 0u);
+      const uint32_t unknown = (fast[0] && ds[0] == 0xFFFFFFFFu ? 1u : 0u) | (fast[1] && ds[1] == 0xFFFFFFFFu ? 2u : 0u) |
+                               (fast[2] && ds[2] == 0xFFFFFFFFu ? 4u : 0u) | (fast[3] && ds[3] == 0xFFFFFFFFu ? 8u : 0u);
       const uint32_t inRange = (fast[0] ? 1u : 0u) | (fast[1] ? 2u : 0u) | (fast[2] ? 4u : 0u) | (fast[3] ? 8u : 0u);
       // rows already folded through the map must not be folded again: hand over only unknown-slot and out-of-range rows
       denseColdRowsHll(stage, q, row0, P, nvalid, inRange, unknown, s[0], s[1], s[2], s[3]);

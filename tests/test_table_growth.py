@@ -57,11 +57,10 @@ elif case == "spill":     # direct-indexed kernels with the zone map of ANOTHER 
 elif case == "partition":   # radix-partitioned aggregation forced on (ARESDB_B200_PARTITION=1): entries sorted by table partition per
     # tile, folded partition by partition — same results as the direct form, for sums / counts / min, few and many groups
     big = [synth.generate_batch(d, 700000, num_cities=120, null_rate=0.02) for d in range(2)]
-    qs = {"unique": AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE)),
-          "cfg3": AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0))], [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE)),
-          "count": AggQuery([], [CITY, STATUS], Measure("count")),
-          "min": AggQuery([E.eq(STATUS, E.Lit(2))], [E.floor(TS, E.Lit(60))], Measure("min", CITY))}
-    import ctypes as C
+    qs = dict(unique=AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE)),
+              cfg3=AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0))], [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE)),
+              count=AggQuery([], [CITY, STATUS], Measure("count")),
+              minc=AggQuery([E.eq(STATUS, E.Lit(2))], [E.floor(TS, E.Lit(60))], Measure("min", CITY)))
     for name, q in qs.items():
         exp = T.run_legacy(orc, q, big)
         got = T.run_fused(eng, q, big)
