@@ -170,11 +170,18 @@ __device__ __forceinline__ void jitAggregateDense(uint32_t touchedAddr, unsigned
     uint32_t ds[4];
 #pragma unroll
     for (int r = 0; r < 4; r++) ds[r] = map[fast[r] ? s[r] : 0u];
+    // (register index in 32 bits — the dense directory has at most 2^18 groups —, the update a PREDICATED red: no branch
+    // around it, and the four addresses are ready before the first one is issued)
+    uint32_t *reg[4];
+#pragma unroll
+    for (int r = 0; r < 4; r++) reg[r] = P.G.regs + ((ds[r] << 14) | ((uint32_t)meas[r] & (kHllRegisters - 1)));
+    static_assert(kHllRegisters == 1u << 14, "register index packing");
 #pragma unroll
     for (int r = 0; r < 4; r++) {
       const bool known = fast[r] && ds[r] != 0xFFFFFFFFu;
       cold = cold || (fast[r] && !known);
-      if (known) atomicMax(&P.G.regs[(size_t)ds[r] * kHllRegisters + ((uint32_t)meas[r] & (kHllRegisters - 1))], (uint32_t)meas[r] + 1u);
+      asm volatile("{ .reg .pred p; setp.ne.u32 p, %0, 0; @p red.global.max.u32 [%1], %2; }"
+                   ::"r"((uint32_t)known), "l"(reg[r]), "r"((uint32_t)meas[r] + 1u) : "memory");
     }
     if (cold) {
       const uint32_t unknown = (fast[0] && ds[0] == 0xFFFFFFFFu ? 1u : 0u) | (fast[1] && ds[1] == 0xFFFFFFFFu ? 2u : 0u) |
@@ -408,7 +415,8 @@ extern "C" __global__ void __launch_bounds__(JIT_THREADS, 1) aresFusedJit(const 
         continue;
       }
       const uint8_t *stage = stages + (size_t)s * JIT_STAGE_BYTES;
-      const bool allowClaim = *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
+      // (direct-indexed forms have no shared key table: no volatile read of its fill per tile)
+      const bool allowClaim = JIT_DENSE != 0 || *reinterpret_cast<volatile uint32_t *>(claims) < (JIT_SMEM_SLOTS / 4) * 3;
       // the shared table is full and has turned away several times its size in rows: stop consulting it
       const bool bypass = JIT_BYPASS && !allowClaim && *reinterpret_cast<volatile uint32_t *>(misses) > 4u * JIT_SMEM_SLOTS;
       {

@@ -44,7 +44,14 @@ elif case == "hash32":    # hash-reduce mode with the bypass kernel
     exp = T.run_legacy(orc, q, hbs)
     got = T.run_fused(eng, q, hbs, expected_groups=100000)
     assert exp.groups > 100000
-    T.assert_same_result(got, exp, ordered=False, ctx=case)
+    # group identity in this mode is the 32-bit hash: ~5 pairs of different rows collide at this size and merge; which
+    # member names the merged group is unspecified on the reference's device path too (concurrent insert), so the
+    # comparison is by hash, and every row named must be a row of the data
+    import hashes as HS
+    by_hash = lambda r: dict(zip(HS.murmur3_32(r.packed_rows()).tolist(), r.measures.tolist()))
+    assert got.groups == exp.groups and by_hash(got) == by_hash(exp), "hash32: groups by hash differ"
+    every = T.run_legacy(orc, AggQuery([], [CITY, E.floor(TS, E.Lit(2))], Measure("count")), hbs)
+    assert every.groups > exp.groups and set(got.rows) <= set(every.rows)
 elif case == "spill":     # direct-indexed kernels with the zone map of ANOTHER batch: every row is out of range
     q = AggQuery([E.eq(STATUS, E.Lit(1))], [E.floor(TS, E.Lit(60)), CITY], Measure("sum", FARE))
     small = [synth.generate_batch(d, 30000, num_cities=50) for d in range(2)]
