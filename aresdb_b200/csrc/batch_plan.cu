@@ -16,6 +16,7 @@
 // each group's packed dimension row with the reference's murmur3, sorts the g groups by hash,
 // merges equal hashes and writes the reference's output layout — the observable result of the
 // reference's Sort+Reduce (ARES_REDUCE_SORT) or HashReduce (ARES_REDUCE_HASH) over all batches.
+#include <cooperative_groups.h>
 #include <memory>
 #include <vector>
 
@@ -27,6 +28,8 @@
 #include "radix_sort.cuh"
 #include "scan.cuh"
 #include "small_sort.cuh"
+
+namespace cg = cooperative_groups;
 
 namespace aresb {
 
@@ -792,12 +795,20 @@ denseFoldKernel(unsigned long long *__restrict__ acc, DenseFold F, DevTable G) {
 // ---------------------------------------------------------------------------------------
 // single-launch finalize for results of up to kSmallFinalizeMax groups
 // ---------------------------------------------------------------------------------------
-// One CTA walks the claim list (no table scan, no compaction), hashes each group's packed row with the reference's
-// murmur3, sorts the (hash, claim ordinal) pairs (smallSortBody), merges runs of equal hashes with the aggregate's
-// rule — the member claimed first names the run — and writes the reference's DimensionVector block + measure vector.
-// The group count goes to a mapped pinned host word, so the host's only interaction is one stream synchronise.
-// `ordered == 0` is the exchange form (AggStateExport): the claimed slots as they are, no sort, no merge.
+// One thread-block cluster of kFinCtas CTAs walks the claim list (no table scan, no compaction), hashes each group's
+// packed row with the reference's murmur3, sorts the (hash, claim ordinal) pairs — one bucketing pass over the top 12 hash
+// bits (histogram in L2, every CTA scans it into its own shared memory), then every element ranks itself inside its
+// bucket —, merges runs of equal hashes with the aggregate's rule — the member claimed first names the run — and writes
+// the reference's DimensionVector block + measure vector.  The phases are chains of two or three dependent loads per
+// element: 8192 threads give every thread at most four elements, so a phase costs a few memory latencies, and the
+// phases are separated by the hardware cluster barrier (one CTA of 1024 threads took 225 us for 19,200 groups, all of
+// it serialised latency: profiles/r02_launches_cfg3.csv).  The group count goes to a mapped pinned host word, so the
+// host's only interaction is one stream synchronise.  `ordered == 0` is the exchange form (AggStateExport /
+// AggStateExportPart): the claimed slots as they are, no sort, no merge.
 constexpr int kSmallFinalizeMax = kSmallSortMax;
+constexpr int kFinCtas = 8;                          // portable cluster maximum
+constexpr uint32_t kFinThreads = kFinCtas * 1024u;
+constexpr size_t kFinHistWords = 2 * kSmallBuckets + 64;   // bucket counts | scatter cursors | per-CTA run-head totals
 
 struct SmallFinalizeArgs {
   DevTable G;
@@ -805,6 +816,7 @@ struct SmallFinalizeArgs {
   uint64_t hashMask;
   uint64_t *hashA, *tmpK;   // scratch: kSmallFinalizeMax entries each
   uint32_t *idxA, *tmpI;
+  uint32_t *hist;           // scratch: kFinHistWords
   uint8_t *outBlock, *outValues;
   uint64_t *outHash;
   uint32_t *outIndex;
@@ -814,9 +826,11 @@ struct SmallFinalizeArgs {
   uint8_t keyMode, hashBits, op, plusZero, ordered;
 };
 
-__global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constant__ SmallFinalizeArgs A) {
-  __shared__ uint32_t cnt[kSmallBuckets], off[kSmallBuckets + 1];
+__global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(1024) finalizeSmallKernel(const __grid_constant__ SmallFinalizeArgs A) {
+  __shared__ uint32_t off[kSmallBuckets + 1];
   __shared__ uint32_t sWarp[1024 / 32 + 1];
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t ctaRank = cluster.block_rank(), gtid = ctaRank * 1024u + threadIdx.x;
   const DevTable &G = A.G;
   const uint32_t n = G.counters[0];
   uint32_t status = SF_OK;
@@ -825,11 +839,12 @@ __global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constan
   else if (G.counters[3] || G.counters[4]) status = SF_UNSETTLED;   // stopped at the growth threshold / rows parked: the host settles first
   else if (n > (uint32_t)kSmallFinalizeMax) status = SF_TOO_MANY;
   else if (!A.ordered && n > (uint32_t)A.outCapacity) status = SF_OUTPUT_TOO_SMALL;
-  if (status != SF_OK || n == 0) {
-    if (threadIdx.x == 0) {
-      A.resultDev[0] = 0; A.resultDev[1] = status; A.resultDev[2] = n;
-      A.resultHost[0] = 0; A.resultHost[1] = status; A.resultHost[2] = n;
-    }
+  auto publish = [&](uint32_t groups, uint32_t st, uint32_t claimedSlots) {
+    A.resultDev[0] = groups; A.resultDev[1] = st; A.resultDev[2] = claimedSlots;
+    A.resultHost[0] = groups; A.resultHost[1] = st; A.resultHost[2] = claimedSlots;
+  };
+  if (status != SF_OK || n == 0) {   // (uniform over the cluster: nobody waits at a barrier below)
+    if (gtid == 0) publish(0, status, n);
     return;
   }
   auto rowOf = [&](uint32_t slot, uint64_t (&w)[4]) {
@@ -840,7 +855,7 @@ __global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constan
     }
   };
   if (!A.ordered) {
-    for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+    for (uint32_t i = gtid; i < n; i += kFinThreads) {
       const uint32_t slot = G.claimed[i];
       uint64_t w[4];
       rowOf(slot, w);
@@ -848,14 +863,15 @@ __global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constan
       storeMeasure(A.outValues, i, A.width, G.acc[slot]);
       if (A.outIndex) A.outIndex[i] = i;
     }
-    if (threadIdx.x == 0) {
-      A.resultDev[0] = n; A.resultDev[1] = SF_OK; A.resultDev[2] = n;
-      A.resultHost[0] = n; A.resultHost[1] = SF_OK; A.resultHost[2] = n;
-    }
+    if (gtid == 0) publish(n, SF_OK, n);
     return;
   }
-  // 1. (reference hash of the group's row, claim ordinal)
-  for (uint32_t i = threadIdx.x; i < n; i += 1024) {
+  uint32_t *cnt = A.hist, *cur = A.hist + kSmallBuckets, *ctaHeads = A.hist + 2 * kSmallBuckets;
+  const int shift = A.hashBits - kSmallBits;
+  for (uint32_t b = gtid; b < (uint32_t)kSmallBuckets; b += kFinThreads) { cnt[b] = 0; cur[b] = 0; }
+  cluster.sync();
+  // 1. reference hash of every group's row; histogram of the top hash bits
+  for (uint32_t i = gtid; i < n; i += kFinThreads) {
     const unsigned long long key = G.keys[G.claimed[i]];
     uint64_t h;
     if (A.keyMode == KEY_PACKED) {
@@ -865,26 +881,67 @@ __global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constan
       h = A.hashBits == 64 ? key & A.hashMask : key;
     }
     A.hashA[i] = h;
-    A.idxA[i] = i;
+    atomicAdd(&cnt[(uint32_t)(h >> shift) & (kSmallBuckets - 1)], 1u);
+  }
+  cluster.sync();
+  // 2. bucket offsets: every CTA scans the histogram for itself (no barrier, and the offsets are in shared memory)
+  {
+    constexpr int kPer = kSmallBuckets / 1024;
+    uint32_t c[kPer], sum = 0, total;
+#pragma unroll
+    for (int j = 0; j < kPer; j++) { c[j] = cnt[threadIdx.x * kPer + j]; sum += c[j]; }
+    uint32_t excl = blockExclusiveScan<1024>(sum, sWarp, &total);
+#pragma unroll
+    for (int j = 0; j < kPer; j++) { off[threadIdx.x * kPer + j] = excl; excl += c[j]; }
+    if (threadIdx.x == 0) off[kSmallBuckets] = total;
   }
   __syncthreads();
-  // 2. sort by (hash, ordinal)
-  smallSortBody(A.hashA, A.idxA, A.tmpK, A.tmpI, (int)n, A.hashBits - kSmallBits, cnt, off, sWarp);
-  // 3. runs of equal hashes: every thread owns a contiguous chunk, counts the run heads in it ...
-  const uint32_t per = (n + 1023) / 1024;
-  const uint32_t begin = threadIdx.x * per < n ? threadIdx.x * per : n, end = begin + per < n ? begin + per : n;
+  // 3. unordered scatter into the buckets
+  for (uint32_t i = gtid; i < n; i += kFinThreads) {
+    const uint64_t h = A.hashA[i];
+    const uint32_t d = (uint32_t)(h >> shift) & (kSmallBuckets - 1);
+    const uint32_t p = off[d] + atomicAdd(&cur[d], 1u);
+    A.tmpK[p] = h;
+    A.tmpI[p] = i;
+  }
+  cluster.sync();
+  // 4. every element finds its rank among its bucket's members by (hash, claim ordinal): 4.7 members on average for
+  // 19,200 groups; a degenerate bucket only costs time
+  for (uint32_t i = gtid; i < n; i += kFinThreads) {
+    const uint64_t k = A.tmpK[i];
+    const uint32_t v = A.tmpI[i];
+    const uint32_t d = (uint32_t)(k >> shift) & (kSmallBuckets - 1);
+    const uint32_t lo = off[d], hi = off[d + 1];
+    uint32_t rank = 0;
+    for (uint32_t j = lo; j < hi; j++) {
+      const uint64_t kj = A.tmpK[j];
+      rank += (kj < k) || (kj == k && A.tmpI[j] < v);
+    }
+    A.hashA[lo + rank] = k;
+    A.idxA[lo + rank] = v;
+  }
+  cluster.sync();
+  // 5. runs of equal hashes: every thread owns a contiguous chunk, counts the run heads in it ...
+  const uint32_t per = (n + kFinThreads - 1) / kFinThreads;
+  const uint32_t begin = gtid * per < n ? gtid * per : n, end = begin + per < n ? begin + per : n;
   uint32_t heads = 0;
   for (uint32_t j = begin; j < end; j++) heads += j == 0 || A.hashA[j] != A.hashA[j - 1];
-  uint32_t g;
-  uint32_t pos = blockExclusiveScan<1024>(heads, sWarp, &g);
+  uint32_t ctaTotal;
+  uint32_t pos = blockExclusiveScan<1024>(heads, sWarp, &ctaTotal);
+  if (threadIdx.x == 0) ctaHeads[ctaRank] = ctaTotal;
+  cluster.sync();
+  uint32_t g = 0;
+#pragma unroll
+  for (int r = 0; r < kFinCtas; r++) {
+    const uint32_t t = ctaHeads[r];
+    if ((uint32_t)r < ctaRank) pos += t;
+    g += t;
+  }
   if (g > (uint32_t)A.outCapacity) {
-    if (threadIdx.x == 0) {
-      A.resultDev[0] = 0; A.resultDev[1] = SF_OUTPUT_TOO_SMALL; A.resultDev[2] = g;
-      A.resultHost[0] = 0; A.resultHost[1] = SF_OUTPUT_TOO_SMALL; A.resultHost[2] = g;
-    }
+    if (gtid == 0) publish(0, SF_OUTPUT_TOO_SMALL, g);
     return;
   }
-  // ... 4. and folds + emits the runs that start in its chunk (a run may extend into the next chunks)
+  // ... 6. and folds + emits the runs that start in its chunk (a run may extend into the next chunks)
   for (uint32_t j = begin; j < end; j++) {
     const uint64_t h = A.hashA[j];
     if (!(j == 0 || h != A.hashA[j - 1])) continue;
@@ -903,10 +960,7 @@ __global__ void __launch_bounds__(1024) finalizeSmallKernel(const __grid_constan
     if (A.outIndex) A.outIndex[pos] = pos;
     pos++;
   }
-  if (threadIdx.x == 0) {
-    A.resultDev[0] = g; A.resultDev[1] = SF_OK; A.resultDev[2] = n;
-    A.resultHost[0] = g; A.resultHost[1] = SF_OK; A.resultHost[2] = n;
-  }
+  if (gtid == 0) publish(g, SF_OK, n);
 }
 
 // AggStateReset: only the claimed slots are emptied (and, for dense HLL states, only their register arrays).
@@ -988,7 +1042,7 @@ static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   const size_t ctaAccBytes = (size_t)kMaxGridCtas * 8192 * sizeof(unsigned long long);
   const size_t regBytes = st->hllDense ? cap * kHllRegisters * sizeof(uint32_t) : 0;
   const size_t claimedBytes = (cap * 4 + 255) / 256 * 256;
-  const size_t smallBytes = (size_t)kSmallFinalizeMax * (8 + 8 + 4 + 4);
+  const size_t smallBytes = (size_t)kSmallFinalizeMax * (8 + 8 + 4 + 4) + kFinHistWords * 4;
   const size_t progressBytes = ((size_t)(kProgressTail + 1) * 4 + 255) / 256 * 256;
   const size_t spillBytes = (size_t)kSpillCap * sizeof(SpillEntry);
   size_t bytes = cap * 16 + (rows ? cap * 32 : 0) + 256 + ctaAccBytes + regBytes + claimedBytes + smallBytes + progressBytes + spillBytes;
@@ -1959,12 +2013,13 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
     A.tmpK = A.hashA + kSmallFinalizeMax;
     A.idxA = reinterpret_cast<uint32_t *>(A.tmpK + kSmallFinalizeMax);
     A.tmpI = A.idxA + kSmallFinalizeMax;
+    A.hist = A.tmpI + kSmallFinalizeMax;
     A.outBlock = out.DimValues; A.outValues = outValues;
     A.outHash = ordered ? out.HashValues : nullptr; A.outIndex = out.IndexVector;
     A.resultDev = st->resultDev; A.resultHost = st->resultHostDev;
     A.rowBytes = st->rowLayout.rowBytes; A.width = width; A.outCapacity = out.VectorCapacity;
     A.keyMode = st->keyMode; A.hashBits = (uint8_t)st->hashBits; A.op = st->op; A.plusZero = plusZero; A.ordered = ordered;
-    finalizeSmallKernel<<<1, 1024, 0, s>>>(A);
+    finalizeSmallKernel<<<kFinCtas, 1024, 0, s>>>(A);
     checkLastError("finalizeSmall");
     ARES_CUDA(cudaStreamSynchronize(s));
     uint32_t status = st->resultHost[1];
@@ -2169,7 +2224,7 @@ CGoCallResHandle AggStateExportPart(void *state, uint8_t *part, int capRows, siz
     A.resultDev = reinterpret_cast<uint32_t *>(part); A.resultHost = st->resultHostDev + 4;   // host copy unused
     A.rowBytes = st->rowLayout.rowBytes; A.width = st->measWidth; A.outCapacity = capRows;
     A.keyMode = st->keyMode; A.hashBits = (uint8_t)st->hashBits; A.op = st->op; A.plusZero = 0; A.ordered = 0;
-    finalizeSmallKernel<<<1, 1024, 0, (cudaStream_t)cudaStream>>>(A);
+    finalizeSmallKernel<<<kFinCtas, 1024, 0, (cudaStream_t)cudaStream>>>(A);
     checkLastError("AggStateExportPart");
     return 0;
   });

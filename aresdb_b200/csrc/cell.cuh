@@ -164,8 +164,10 @@ ARES_HD uint32_t hllValueOfHash(uint64_t hashed, bool hostShift = false) {
   if (!hostShift) {
     // CUDA semantics of the reference's int shift, closed form of the loop below: the lowest set bit among bits 14..31
     // decides; none set: the loop runs to bit 64 (rho = 50)
+    // (branch-free: clz(brev(x)) is 32 for x == 0, and 32 + 18 = 50)
     const uint32_t x = (uint32_t)(hashed >> 14) & 0x3FFFFu;
-    const uint32_t r = x ? (uint32_t)__ffs((int)x) - 1u : 50u;
+    const uint32_t c = (uint32_t)__clz((int)__brev(x));
+    const uint32_t r = c + (c >> 5) * 18u;
     return (r << 16) | group;
   }
 #endif
