@@ -583,10 +583,10 @@ mergePartsKernel(const uint8_t *__restrict__ parts, int numParts, size_t partStr
 // ---------------------------------------------------------------------------------------
 // one CTA per group (d-th in hash order): number of registers that were hit
 __global__ void __launch_bounds__(256)
-hllDenseCountKernel(const uint32_t *__restrict__ regs, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ order,
+hllDenseCountKernel(const uint32_t *__restrict__ regs, const unsigned long long *__restrict__ acc, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ order,
                     uint32_t *__restrict__ counts) {
   __shared__ uint32_t sWarp[256 / 32 + 1];
-  const uint32_t *r = regs + (size_t)slotOf[order[blockIdx.x]] * kHllRegisters;
+  const uint32_t *r = regs + (size_t)((uint32_t)acc[slotOf[order[blockIdx.x]]] - 1u) * kHllRegisters;   // (claim ordinal: hllRegArray)
   uint32_t c = 0;
   for (uint32_t i = threadIdx.x; i < kHllRegisters; i += 256) c += r[i] != 0;
   uint32_t total;
@@ -615,12 +615,12 @@ __global__ void __launch_bounds__(1024) hllDenseOffsetsKernel(const uint32_t *__
 
 // one CTA per group: its hit registers in ascending register order -> (key, value, group ordinal)
 __global__ void __launch_bounds__(256)
-hllDenseEmitKernel(const uint32_t *__restrict__ regs, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ order,
+hllDenseEmitKernel(const uint32_t *__restrict__ regs, const unsigned long long *__restrict__ acc, const uint32_t *__restrict__ slotOf, const uint32_t *__restrict__ order,
                    const uint64_t *__restrict__ sortedHash, const uint32_t *__restrict__ offsets,
                    uint64_t *__restrict__ outHash, uint32_t *__restrict__ outVals, uint32_t *__restrict__ outIndex) {
   __shared__ uint32_t sWarp[256 / 32 + 1];
   const uint32_t d = blockIdx.x;
-  const uint32_t *r = regs + (size_t)slotOf[order[d]] * kHllRegisters;
+  const uint32_t *r = regs + (size_t)((uint32_t)acc[slotOf[order[d]]] - 1u) * kHllRegisters;
   const uint64_t hi = sortedHash[d] & 0xFFFFFFFFFFFF0000ull;
   uint32_t pos = offsets[d];
   for (uint32_t base = 0; base < kHllRegisters; base += 256) {
@@ -969,7 +969,8 @@ resetClaimedKernel(DevTable G, unsigned long long neutral) {
   const uint32_t n = G.counters[0];
   if (G.regs != nullptr) {   // one CTA per claimed group at a time: 16384 registers
     for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
-      uint4 *r = reinterpret_cast<uint4 *>(G.regs + (size_t)G.claimed[i] * kHllRegisters);
+      if (i >= kHllDenseMaxGroups) break;   // (claims past the register arrays were turned away)
+      uint4 *r = reinterpret_cast<uint4 *>(G.regs + (size_t)i * kHllRegisters);   // register arrays go by claim ordinal
       for (uint32_t k = threadIdx.x; k < kHllRegisters / 4; k += blockDim.x) r[k] = make_uint4(0, 0, 0, 0);
     }
   }
@@ -1010,7 +1011,6 @@ struct AggState {
   uint32_t *resultHostDev = nullptr;       // device alias of resultHost
 };
 
-constexpr uint32_t kHllDenseMaxGroups = 4096;   // dense HLL: directory of 8192 slots, 64 KB of registers per slot
 constexpr size_t kHllDenseSlots = 8192;
 
 static uint64_t neutralOf(AggOp op) {
@@ -1040,7 +1040,7 @@ static ValClass measureClassOf(int dt) {
 static void allocTable(AggState *st, size_t cap, cudaStream_t s) {
   const bool rows = st->keyMode == KEY_HASHED;
   const size_t ctaAccBytes = (size_t)kMaxGridCtas * 8192 * sizeof(unsigned long long);
-  const size_t regBytes = st->hllDense ? cap * kHllRegisters * sizeof(uint32_t) : 0;
+  const size_t regBytes = st->hllDense ? (size_t)kHllDenseMaxGroups * kHllRegisters * sizeof(uint32_t) : 0;   // by claim ordinal
   const size_t claimedBytes = (cap * 4 + 255) / 256 * 256;
   const size_t smallBytes = (size_t)kSmallFinalizeMax * (8 + 8 + 4 + 4) + kFinHistWords * 4;
   const size_t progressBytes = ((size_t)(kProgressTail + 1) * 4 + 255) / 256 * 256;
@@ -1910,7 +1910,7 @@ static void mergeRows(AggState *st, const DimensionVector &in, const uint8_t *va
 
 static void checkOverflow(AggState *st, const uint32_t counters[2]) {
   if (counters[1] && st->hllDense)
-    throw EngineError("dense HLL state: more than " + std::to_string(st->capacity) +
+    throw EngineError("dense HLL state: more than " + std::to_string(kHllDenseMaxGroups) +
                       " dimension groups; recreate the AggState with AggSpec.ExpectedGroups > 4096 (entry mode) and replay the batches");
   if (counters[1])
     throw EngineError("group table overflow: more than " + std::to_string(st->capacity) +
@@ -1958,7 +1958,7 @@ static void denseCarried(AggState *st, cudaStream_t s, DenseCarried &out, bool c
   iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);
   sortKeyIndexPairs(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 64, s);
   Scratch counts(sizeof(uint32_t) * (size_t)n, s), offsets(sizeof(uint32_t) * ((size_t)n + 1), s);
-  hllDenseCountKernel<<<n, 256, 0, s>>>(st->table.regs, slotOf.as<uint32_t>(), order.as<uint32_t>(), counts.as<uint32_t>());
+  hllDenseCountKernel<<<n, 256, 0, s>>>(st->table.regs, st->table.acc, slotOf.as<uint32_t>(), order.as<uint32_t>(), counts.as<uint32_t>());
   checkLastError("hllDenseCount");
   hllDenseOffsetsKernel<<<1, 1024, 0, s>>>(counts.as<uint32_t>(), n, offsets.as<uint32_t>());
   checkLastError("hllDenseOffsets");
@@ -1975,7 +1975,7 @@ static void denseCarried(AggState *st, cudaStream_t s, DenseCarried &out, bool c
   emitGroupsKernel<<<divUp(n, 256), 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), order.as<uint32_t>(), (uint32_t)n,
                                                  out.block.as<uint8_t>(), L, nullptr);
   checkLastError("emitGroups");
-  hllDenseEmitKernel<<<n, 256, 0, s>>>(st->table.regs, slotOf.as<uint32_t>(), order.as<uint32_t>(), hash.as<uint64_t>(),
+  hllDenseEmitKernel<<<n, 256, 0, s>>>(st->table.regs, st->table.acc, slotOf.as<uint32_t>(), order.as<uint32_t>(), hash.as<uint64_t>(),
                                        offsets.as<uint32_t>(), out.hash.as<uint64_t>(), out.values.as<uint32_t>(),
                                        out.index.as<uint32_t>());
   checkLastError("hllDenseEmit");

@@ -42,6 +42,7 @@ struct DevTable {
 };
 
 constexpr uint32_t kHllRegisters = 1u << 14;   // p = 14
+constexpr uint32_t kHllDenseMaxGroups = 4096;  // dense HLL: directory of 8192 slots, register arrays for 4096 groups
 
 // ---------------------------------------------------------------------------------------
 // device helpers: TMA bulk copy + mbarrier (sm_90+ PTX; SASS: UBLKCP / SYNCS)
@@ -108,6 +109,9 @@ static __device__ __noinline__ uint32_t globalFindOrClaim(const DevTable &G, uns
         base = __shfl_sync(peers, base, leader);
         const uint32_t ord = base + __popc(peers & ((1u << lane) - 1u));
         G.claimed[ord] = slot;   // every slot is claimed once: the ordinal is < capacity
+        // dense HLL directory: the group's register array is addressed by its claim ordinal (see hllRegArray), published
+        // in the slot's otherwise unused accumulator word as ordinal + 1
+        if (G.regs != nullptr) *reinterpret_cast<volatile unsigned long long *>(&G.acc[slot]) = (unsigned long long)ord + 1ull;
         if (ord >= G.growAt) *reinterpret_cast<volatile uint32_t *>(&G.counters[3]) = 1u;   // filling up: stop consuming tiles
         if (roww != nullptr && G.rows != nullptr) {
 #pragma unroll
@@ -149,7 +153,21 @@ __device__ __forceinline__ void globalUpdate(const DevTable &G, AggOp op, unsign
 // registers in G.regs.  `mirror` (optional) is a shared-memory copy of G.keys with the same
 // geometry, filled on demand, so that steady-state lookups never leave the SM.
 // ---------------------------------------------------------------------------------------
-// Directory slot of `key` (claimed on first sight), 0xFFFFFFFF when the directory is full.
+// Register arrays are addressed by the group's CLAIM ORDINAL, not by its directory slot: the arrays of the groups a batch
+// touches are then contiguous (101 groups: 6.6 MB), where slot-addressed arrays are 64 KB chunks scattered over the whole
+// 512 MB allocation — and random accesses over that many pages ran at a THIRD of the rate (reductions and plain loads
+// alike, 56 against 173-218 G/s: profiles/r02_red_lanes.txt; the translation caches, not L2).  The claiming thread
+// publishes ordinal + 1 in the slot's accumulator word right after its claim; a thread that finds the key an instant
+// earlier waits for it.
+__device__ __forceinline__ uint32_t hllRegArray(const DevTable &G, uint32_t slot) {
+  unsigned long long o;
+  do {
+    o = *reinterpret_cast<volatile unsigned long long *>(&G.acc[slot]);
+  } while (o == 0ull);
+  return (uint32_t)o - 1u;
+}
+
+// Register array (claim ordinal) of `key`'s group, claimed on first sight; 0xFFFFFFFF when the directory is full.
 __device__ __forceinline__ uint32_t hllDenseLocate(const DevTable &G, unsigned long long *mirror, unsigned long long key,
                                                    const uint64_t *roww) {
   uint32_t slot = globalHome(G, key);
@@ -176,7 +194,12 @@ __device__ __forceinline__ uint32_t hllDenseLocate(const DevTable &G, unsigned l
       }
     }
   }
-  return slot;
+  const uint32_t arr = hllRegArray(G, slot);
+  if (arr >= kHllDenseMaxGroups) {   // more groups than register arrays: reported like a full directory
+    atomicExch(&G.counters[1], 1u);
+    return 0xFFFFFFFFu;
+  }
+  return arr;
 }
 
 // Register update: registers only grow, so a (possibly stale) plain read that already shows a value >= ours makes the
@@ -188,9 +211,9 @@ __device__ __forceinline__ void hllRegisterMax(uint32_t *reg, uint32_t want) {
 
 __device__ __forceinline__ void hllDenseUpdate(const DevTable &G, unsigned long long *mirror, unsigned long long key,
                                                const uint64_t *roww, uint32_t value) {
-  const uint32_t slot = hllDenseLocate(G, mirror, key, roww);
-  if (slot == 0xFFFFFFFFu) return;
-  hllRegisterMax(&G.regs[(size_t)slot * kHllRegisters + (value & (kHllRegisters - 1))], value + 1u);
+  const uint32_t arr = hllDenseLocate(G, mirror, key, roww);
+  if (arr == 0xFFFFFFFFu) return;
+  hllRegisterMax(&G.regs[(size_t)arr * kHllRegisters + (value & (kHllRegisters - 1))], value + 1u);
 }
 
 // ---------------------------------------------------------------------------------------
