@@ -277,7 +277,7 @@ class ClockSampler:
 class DeviceTable:
     """The synthetic fact table of one rank: its day-batches resident in HBM (+ pinned host mirrors for e2e)."""
 
-    def __init__(self, lib, space, dev, days, rows_per_batch, city_dist, mirror_host):
+    def __init__(self, lib, space, dev, days, rows_per_batch, city_dist, mirror_host, shard=0):
         import torch
         from aresdb_b200 import columns, synth
         from aresdb_b200.executor import compute_zone_map
@@ -286,7 +286,7 @@ class DeviceTable:
         self.values_off = None
         zm_ms = []
         for d in days:
-            bufs, self.values_off = synth.generate_batch_cuda(d, rows_per_batch, dev, city_dist=city_dist)
+            bufs, self.values_off = synth.generate_batch_cuda(d, rows_per_batch, dev, city_dist=city_dist, seed=20260922 + shard)
             cols = [columns.slice_of(b.data_ptr(), dt, rows_per_batch, 0, self.values_off, 2) for b, dt in zip(bufs, synth.COLUMN_TYPES)]
             self.bufs.append(bufs)
             self.cols.append(cols)
@@ -414,7 +414,7 @@ def gpu_run(args):
     table = DeviceTable(lib, space, dev, my_days, rows_per_batch, WL.get("city_dist", "uniform"), mirror_host=not args.no_e2e)
     zone_map_ms = table.zone_map_ms
 
-    def run_workload(name, steps, warmup, zone_maps, table, with_kernel=True, with_e2e=False, verify=True):
+    def run_workload(name, steps, warmup, zone_maps, table, with_kernel=True, with_e2e=False, verify=True, rows_scale=1):
         """Times one workload on `table`; returns the sub-result dict (device-resident value, kernel-alone roofline,
         optional e2e, verification)."""
         wl = WORKLOADS[name]
@@ -423,7 +423,7 @@ def gpu_run(args):
         rows_b = (args.rows or wl["rows"]) // nb
         count = len(table.days) if nb > 1 else 1
         batches = table.batches(zone_maps, rows_b, count)
-        rows_all = (args.rows or wl["rows"])
+        rows_all = (args.rows or wl["rows"]) * rows_scale
         ex = ShardedFusedQuery(lib, space, q, expected_groups=wl["expected_groups"])
 
         def finish():
@@ -614,6 +614,21 @@ def gpu_run(args):
             subs["cfg3_zipf"] = run_workload("cfg3_zipf", sub_steps, sub_warm, True, ztable)
             del ztable
 
+    # N > 1: the headline keeps the table at 1e9 rows (strong scaling, as the metric is worded); the same query over a
+    # table that grows with the ranks — every rank holds a 1e9-row SHARD of all the days (AresDB shards a table by key, so
+    # every shard sees every group), 1e9 x N rows in all — is reported beside it
+    weak = None
+    if world > 1 and not args.no_weak and not args.rows:
+        del table
+        torch.cuda.empty_cache()
+        wtable = DeviceTable(lib, space, dev, list(range(num_batches)), rows_per_batch, WL.get("city_dist", "uniform"),
+                             mirror_host=False, shard=rank)
+        w = run_workload(args.workload, args.steps, args.warmup, not args.no_zone_maps, wtable, with_kernel=False, rows_scale=world)
+        weak = {"scaling": "weak", "rows": rows_total * world, "rows_per_gpu": rows_total, "value": w["value"], "unit": "rows/s",
+                "ms_per_step": w["ms_per_step"], "p50_query_ms": w["p50_query_ms"], "verified": w.get("verified"),
+                "groups": w.get("groups"), "gpu_launches": w["gpu_launches"]}
+        del wtable
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -650,6 +665,7 @@ def gpu_run(args):
         "gpu_launches": main["gpu_launches"],
         "roofline": roof, "roofline_nozm": (subs.get("cfg3_nozm") or {}).get("roofline"),
         "e2e": main.get("e2e"), "cpu_baseline": cpu, "clocks": clocks, "workloads": subs or None,
+        "weak_scaling": weak,
     }
     os.write(real_stdout, (json.dumps(out) + "\n").encode())
     if world > 1:
@@ -703,6 +719,7 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-sub", action="store_true", help="N = 1: skip the sub-results of the other BASELINE configs")
+    ap.add_argument("--no-weak", action="store_true", help="N > 1: skip the weak-scaling leg (1e9 rows per GPU)")
     ap.add_argument("--no-zipf", action="store_true", help="skip the Zipf-city sub-result (a second 11.5 GB table)")
     args = ap.parse_args()
     select_workload(args.workload)
