@@ -446,12 +446,16 @@ def gpu_run(args):
             torch.cuda.synchronize()
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
             launches0 = lib.kernel_launch_count()
+            import gc
+            gc.collect()
+            gc.disable()   # (a collection inside a 0.5 ms step would be the whole step)
             evs[0].record()
             last = None
             for i in range(steps):
                 last = fn()
                 evs[i + 1].record()
             torch.cuda.synchronize()
+            gc.enable()
             if world > 1:
                 dist.barrier()
             per = [evs[i].elapsed_time(evs[i + 1]) for i in range(steps)]
@@ -470,6 +474,7 @@ def gpu_run(args):
             torch.cuda.synchronize()
             torch.cuda.profiler.stop()
         out = {"value": rows_all / (ms / 1e3), "unit": "rows/s", "ms_per_step": ms, "p50_query_ms": float(np.median(per)),
+               "step_ms": [round(x, 4) for x in per],
                "steps": steps, "gpu_launches": int(launches), "zone_maps": bool(zone_maps)}
 
         # dominant kernel timed alone (one launch per batch, back to back), L2 cold because a batch >> L2
@@ -653,7 +658,7 @@ def gpu_run(args):
     out = {
         "metric": WL["metric"], "value": main["value"], "unit": "rows/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
-        "p50_query_ms": main["p50_query_ms"],
+        "p50_query_ms": main["p50_query_ms"], "step_ms": main["step_ms"],
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": WL["dtype"],
         "data": "synthetic", "groups": main["groups"], "verified": main.get("verified"), "check": main.get("check"),
         "config": {"workload": WL["desc"], "rows": rows_total, "batches": num_batches, "rows_per_batch": rows_total // num_batches,
