@@ -353,6 +353,9 @@ _PLAN_SIGS = {
     "AggStateDestroy": [_VP, C.c_int],
     "AggStateExportPart": [_VP, _VP, C.c_int, C.c_size_t, C.c_size_t, _VP, C.c_int],
     "AggStateMergeParts": [_VP, _VP, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, _VP, C.c_int],
+    "AggStateExportPartToPeers": [_VP, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_size_t, C.c_int, C.c_size_t,
+                                  C.c_size_t, C.c_uint32, _VP, C.c_int],
+    "AggStateMergePartsWhenFlagged": [_VP, _VP, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, _VP, C.c_uint32, _VP, C.c_int],
     "ComputeColumnRanges": [C.POINTER(VectorPartySlice), C.c_int, C.POINTER(ColumnRange), _VP, C.c_int],
 }
 _MEM_SIGS = {

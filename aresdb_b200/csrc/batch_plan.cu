@@ -49,7 +49,7 @@ int reduceByHash(const uint64_t *hash, const uint32_t *index, const uint8_t *mea
 // ---------------------------------------------------------------------------------------
 constexpr int R = 4;  // rows per quad
 // status word of the single-launch finalize / of an exchange part
-enum SmallFinalizeStatus : uint32_t { SF_OK = 0, SF_TOO_MANY = 1, SF_TABLE_OVERFLOW = 2, SF_OUTPUT_TOO_SMALL = 3, SF_PART_TRUNCATED = 4, SF_UNSETTLED = 5 };
+enum SmallFinalizeStatus : uint32_t { SF_OK = 0, SF_TOO_MANY = 1, SF_TABLE_OVERFLOW = 2, SF_OUTPUT_TOO_SMALL = 3, SF_PART_TRUNCATED = 4, SF_UNSETTLED = 5, SF_PEER_LATE = 6 };
 
 __device__ __forceinline__ void cvtVec(uint32_t (&v)[R], ValClass from, ValClass to) {
   if (from == to) return;
@@ -552,10 +552,34 @@ mergeRowsKernel(const uint8_t *__restrict__ block, DimLayout L, const uint8_t *_
 // Exchange step of a sharded query, receiving side: all N gathered parts ([groups, status, rows | dimension block of
 // `L.capacity` rows | measures]) are folded by ONE launch; the row counts are read from the parts' headers on the
 // device, so the host never waits for them.  A part whose sender could not fit its rows raises counters[2].
+// `flags` != nullptr (exchange over peer memory, AggStateMergePartsWhenFlagged): the parts are written into this GPU's
+// memory by the PEERS' export kernels, each of which then stores `epoch` into flags[its rank] with release semantics at
+// system scope; every CTA waits for all numParts flags (acquire, system scope) before it reads a part.  The wait is
+// bounded (a peer that never arrives: counters[2], reported by finalize), so the kernel cannot hang the GPU.
 __global__ void __launch_bounds__(256)
-mergePartsKernel(const uint8_t *__restrict__ parts, int numParts, size_t partStride, size_t dimOff, size_t valOff, DimLayout L,
-                 int width, AggOp op, uint8_t keyMode, uint8_t hashBits, int hll, DevTable G) {
+mergePartsKernel(const uint8_t *parts, int numParts, size_t partStride, size_t dimOff, size_t valOff, DimLayout L,
+                 int width, AggOp op, uint8_t keyMode, uint8_t hashBits, int hll, DevTable G, const uint32_t *flags, uint32_t epoch) {
   const uint32_t stride = gridDim.x * blockDim.x;
+  if (flags != nullptr) {
+    __shared__ uint32_t sLate;
+    if (threadIdx.x == 0) {
+      uint32_t late = 0;
+      const long long t0 = clock64();
+      for (int p = 0; p < numParts && !late; p++) {
+        for (;;) {
+          uint32_t seen;
+          asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(seen) : "l"(flags + p) : "memory");
+          if ((int32_t)(seen - epoch) >= 0) break;
+          if (clock64() - t0 > 4000000000ll) { late = 1; break; }   // ~2 s at 2 GHz
+          __nanosleep(100);
+        }
+      }
+      sLate = late;
+      if (late) atomicExch(&G.counters[2], 2u);
+    }
+    __syncthreads();
+    if (sLate) return;
+  }
   for (int p = 0; p < numParts; p++) {
     const uint8_t *part = parts + (size_t)p * partStride;
     const uint32_t *hdr = reinterpret_cast<const uint32_t *>(part);
@@ -635,6 +659,69 @@ hllDenseEmitKernel(const uint32_t *__restrict__ regs, const unsigned long long *
     }
     pos += total;
     __syncthreads();
+  }
+}
+
+// Dense registers -> the reference's register vectors directly (AggStateFinalizeHLL; query/hll.cu:262-290 semantics without
+// the detour through (key, value) entries: 13M entries = 212 MB for 808 groups).  Layout pass, one CTA: per group d in hash
+// order with counts[d] hit registers — its output ordinal among the groups that have any, the byte offset of its vector
+// (4 bytes per hit register below HLL_DENSE_THRESHOLD, else HLL_DENSE_SIZE), totals[0] = dims, totals[1] = bytes.
+__global__ void __launch_bounds__(1024)
+hllVectorLayoutKernel(const uint32_t *__restrict__ counts, int n, uint32_t *__restrict__ outIdx, uint32_t *__restrict__ byteOff,
+                      uint32_t *__restrict__ rowsOf, unsigned long long *__restrict__ totals) {
+  __shared__ uint32_t sWarp[1024 / 32 + 1];
+  __shared__ uint32_t sCarryP, sCarryB;
+  if (threadIdx.x == 0) { sCarryP = 0; sCarryB = 0; }
+  __syncthreads();
+  for (int base = 0; base < n; base += 1024) {
+    const int i = base + threadIdx.x;
+    const uint32_t c = i < n ? counts[i] : 0;
+    const uint32_t p = c != 0, sz = c == 0 ? 0u : (c < (uint32_t)HLL_DENSE_THRESHOLD ? c * 4u : (uint32_t)HLL_DENSE_SIZE);
+    uint32_t totP, totB;
+    const uint32_t exP = blockExclusiveScan<1024>(p, sWarp, &totP);
+    __syncthreads();
+    const uint32_t exB = blockExclusiveScan<1024>(sz, sWarp, &totB);
+    if (i < n) {
+      outIdx[i] = sCarryP + exP;
+      byteOff[i] = sCarryB + exB;
+      if (p) rowsOf[sCarryP + exP] = (uint32_t)i;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { sCarryP += totP; sCarryB += totB; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) { totals[0] = sCarryP; totals[1] = sCarryB; }
+}
+
+// one CTA per group: its vector (sparse: (rho << 16 | register) entries in ascending register order; dense: one rho byte
+// per register) and its register count
+__global__ void __launch_bounds__(256)
+hllVectorEmitKernel(const uint32_t *__restrict__ regs, const unsigned long long *__restrict__ acc, const uint32_t *__restrict__ slotOf,
+                    const uint32_t *__restrict__ order, const uint32_t *__restrict__ counts, const uint32_t *__restrict__ outIdx,
+                    const uint32_t *__restrict__ byteOff, uint8_t *__restrict__ vec, uint16_t *__restrict__ regCount) {
+  __shared__ uint32_t sWarp[256 / 32 + 1];
+  const uint32_t d = blockIdx.x, c = counts[d];
+  if (c == 0) return;
+  if (threadIdx.x == 0) regCount[outIdx[d]] = (uint16_t)c;
+  const uint32_t *r = regs + (size_t)((uint32_t)acc[slotOf[order[d]]] - 1u) * kHllRegisters;
+  uint8_t *dst = vec + byteOff[d];
+  // a register holds value + 1, value = rho << 16 | register (0: never hit); the vectors carry rho + 1
+  if (c < (uint32_t)HLL_DENSE_THRESHOLD) {
+    uint32_t pos = 0;
+    for (uint32_t base = 0; base < kHllRegisters; base += 256) {
+      const uint32_t reg = base + threadIdx.x, v = r[reg];
+      uint32_t total;
+      const uint32_t excl = blockExclusiveScan<256>(v != 0, sWarp, &total);
+      if (v != 0) reinterpret_cast<uint32_t *>(dst)[pos + excl] = (((((v - 1u) >> 16) & 0xFFu) + 1u) << 16) | reg;
+      pos += total;
+      __syncthreads();
+    }
+  } else {
+    for (uint32_t q = threadIdx.x; q < kHllRegisters / 4; q += 256) {
+      const uint4 v = reinterpret_cast<const uint4 *>(r)[q];
+      auto rho = [](uint32_t x) { return x ? ((((x - 1u) >> 16) & 0xFFu) + 1u) : 0u; };
+      reinterpret_cast<uint32_t *>(dst)[q] = rho(v.x) | (rho(v.y) << 8) | (rho(v.z) << 16) | (rho(v.w) << 24);
+    }
   }
 }
 
@@ -835,6 +922,7 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(1024) finaliz
   const uint32_t n = G.counters[0];
   uint32_t status = SF_OK;
   if (G.counters[1]) status = SF_TABLE_OVERFLOW;
+  else if (G.counters[2] == 2u) status = SF_PEER_LATE;   // AggStateMergePartsWhenFlagged gave up waiting for a peer's part
   else if (G.counters[2]) status = SF_PART_TRUNCATED;   // AggStateMergeParts met a part that did not hold all its rows
   else if (G.counters[3] || G.counters[4]) status = SF_UNSETTLED;   // stopped at the growth threshold / rows parked: the host settles first
   else if (n > (uint32_t)kSmallFinalizeMax) status = SF_TOO_MANY;
@@ -961,6 +1049,58 @@ __global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(1024) finaliz
     pos++;
   }
   if (gtid == 0) publish(g, SF_OK, n);
+}
+
+// Exchange over peer memory, sending side: ONE kernel (a cluster of kFinCtas CTAs) writes this rank's rows as a part
+// ([rows, status, claimed | dimension block | measures], the layout of AggStateExportPart) into its own receive buffer,
+// copies the part into the same slot of every peer's receive buffer with 16-byte stores over NVLink, and then stores
+// `epoch` into flags[myRank] on every peer (release, system scope) — export, all-gather and the "it has arrived" signal
+// in one launch, no collective library and no host in between.
+struct PeerExportArgs {
+  SmallFinalizeArgs F;            // the export itself (ordered = 0); F.outBlock / F.outValues / F.resultDev lie in the local slot
+  uint8_t *peerSlot[16];          // this rank's slot in every peer's receive buffer (peerSlot[myRank]: the local one)
+  uint32_t *peerFlag[16];         // &flags[myRank] on every peer
+  size_t partBytes;               // multiple of 16
+  uint32_t numPeers, myRank, epoch;
+};
+
+__global__ void __cluster_dims__(kFinCtas, 1, 1) __launch_bounds__(1024) exportToPeersKernel(const __grid_constant__ PeerExportArgs E) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const uint32_t gtid = cluster.block_rank() * 1024u + threadIdx.x;
+  const SmallFinalizeArgs &A = E.F;
+  const DevTable &G = A.G;
+  const uint32_t n = G.counters[0];
+  uint32_t status = SF_OK;
+  if (G.counters[1]) status = SF_TABLE_OVERFLOW;
+  else if (G.counters[3] || G.counters[4]) status = SF_UNSETTLED;
+  else if (n > (uint32_t)A.outCapacity) status = SF_OUTPUT_TOO_SMALL;
+  if (status == SF_OK) {
+    for (uint32_t i = gtid; i < n; i += kFinThreads) {
+      const uint32_t slot = G.claimed[i];
+      uint64_t w[4];
+      if (A.keyMode == KEY_PACKED) { w[0] = G.keys[slot]; w[1] = w[2] = w[3] = 0; }
+      else {
+#pragma unroll
+        for (int k = 0; k < 4; k++) w[k] = G.rows[(size_t)slot * 4 + k];
+      }
+      unpackRow(A.outBlock, A.L, i, w);
+      storeMeasure(A.outValues, i, A.width, G.acc[slot]);
+    }
+  }
+  if (gtid == 0) { A.resultDev[0] = status == SF_OK ? n : 0u; A.resultDev[1] = status; A.resultDev[2] = n; }
+  cluster.sync();   // the local part is complete (and visible to the cluster)
+  // the part travels as it lies: header, the used prefix of every section would save bytes, but a part is 0.5 MB and the
+  // copy is a few microseconds of NVLink time
+  const uint4 *src = reinterpret_cast<const uint4 *>(E.peerSlot[E.myRank]);
+  const uint32_t words = (uint32_t)(E.partBytes / 16);
+  for (uint32_t p = 0; p < E.numPeers; p++) {
+    if (p == E.myRank) continue;
+    uint4 *dst = reinterpret_cast<uint4 *>(E.peerSlot[p]);
+    for (uint32_t i = gtid; i < words; i += kFinThreads) dst[i] = src[i];
+  }
+  __threadfence_system();
+  cluster.sync();   // every thread's stores are ordered before the flags
+  if (gtid < E.numPeers) asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(E.peerFlag[gtid]), "r"(E.epoch) : "memory");
 }
 
 // AggStateReset: only the claimed slots are emptied (and, for dense HLL states, only their register arrays).
@@ -1982,6 +2122,73 @@ static void denseCarried(AggState *st, cudaStream_t s, DenseCarried &out, bool c
   ARES_CUDA(cudaStreamSynchronize(s));  // the locals above are released in stream order; keep it simple
 }
 
+// Dense HLL state -> the final outputs of AggStateFinalizeHLL, straight from the register arrays.
+static int64_t denseVectors(AggState *st, cudaStream_t s, uint8_t **dimValuesPtr, uint8_t **hllVectorPtr, size_t *hllVectorSizePtr,
+                            uint16_t **hllDimRegIDCountPtr) {
+  uint32_t c[2];
+  ARES_CUDA(cudaMemcpyAsync(c, st->table.counters, sizeof(c), cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  checkOverflow(st, c);
+  const int n = (int)c[0];
+  if (n == 0) return 0;
+  // groups in the order of the reference hash of their dim row
+  const int tiles = divUp((int64_t)st->capacity, kCmpTile);
+  Scratch state(scanStateBytes(tiles) + sizeof(uint32_t), s);
+  ARES_CUDA(cudaMemsetAsync(state.ptr, 0, state.bytes, s));
+  ScanTileState sst = makeScanState(state.ptr, tiles);
+  uint32_t *dCount = reinterpret_cast<uint32_t *>(static_cast<uint8_t *>(state.ptr) + scanStateBytes(tiles));
+  Scratch slotOf(sizeof(uint32_t) * (size_t)n, s), hash(sizeof(uint64_t) * (size_t)n, s), vals(sizeof(uint32_t) * (size_t)n, s);
+  compactGroupsKernel<<<tiles, kCmpThreads, 0, s>>>(st->table, st->capacity, st->keyMode, 64, ~0ull, st->rowLayout.rowBytes, 4, sst,
+                                                   slotOf.as<uint32_t>(), hash.as<uint64_t>(), vals.as<uint8_t>(), dCount);
+  checkLastError("compactGroups");
+  Scratch order(sizeof(uint32_t) * (size_t)n, s), tmpK(sizeof(uint64_t) * (size_t)n, s), tmpV(sizeof(uint32_t) * (size_t)n, s);
+  iotaKernel<<<divUp(n, 256), 256, 0, s>>>(order.as<uint32_t>(), n);
+  sortKeyIndexPairs(hash.as<uint64_t>(), order.as<uint32_t>(), tmpK.as<uint64_t>(), tmpV.as<uint32_t>(), n, 64, s);
+  Scratch counts(sizeof(uint32_t) * (size_t)n, s), outIdx(sizeof(uint32_t) * (size_t)n, s), byteOff(sizeof(uint32_t) * (size_t)n, s);
+  Scratch rowsOf(sizeof(uint32_t) * (size_t)n, s), totalsDev(sizeof(unsigned long long) * 2, s);
+  hllDenseCountKernel<<<n, 256, 0, s>>>(st->table.regs, st->table.acc, slotOf.as<uint32_t>(), order.as<uint32_t>(), counts.as<uint32_t>());
+  checkLastError("hllDenseCount");
+  hllVectorLayoutKernel<<<1, 1024, 0, s>>>(counts.as<uint32_t>(), n, outIdx.as<uint32_t>(), byteOff.as<uint32_t>(), rowsOf.as<uint32_t>(),
+                                          totalsDev.as<unsigned long long>());
+  checkLastError("hllVectorLayout");
+  // the groups' dim rows in hash order (the groups with registers are picked out of it below)
+  Scratch blockAll((size_t)st->rowLayout.rowBytes * n, s);
+  DimLayout Lin = makeDimLayout(st->spec.NumDimsPerDimWidth, n);
+  emitGroupsKernel<<<divUp(n, 256), 256, 0, s>>>(st->table, st->keyMode, slotOf.as<uint32_t>(), order.as<uint32_t>(), (uint32_t)n,
+                                                 blockAll.as<uint8_t>(), Lin, nullptr);
+  checkLastError("emitGroups");
+  unsigned long long totals[2] = {0, 0};
+  ARES_CUDA(cudaMemcpyAsync(totals, totalsDev.ptr, sizeof(totals), cudaMemcpyDeviceToHost, s));
+  ARES_CUDA(cudaStreamSynchronize(s));
+  const int dims = (int)totals[0];
+  if (dims == 0) return 0;
+  void *vec = nullptr, *cnt = nullptr, *out = nullptr;
+  auto fail = [&](CGoCallResHandle h) {
+    std::string m(h.pStrErr); free((void *)h.pStrErr);
+    if (vec) deviceFree(vec);
+    if (cnt) deviceFree(cnt);
+    throw EngineError(m);
+  };
+  CGoCallResHandle h = deviceMalloc(&vec, (size_t)totals[1]);
+  if (h.pStrErr) fail(h);
+  h = deviceMalloc(&cnt, sizeof(uint16_t) * (size_t)dims);
+  if (h.pStrErr) fail(h);
+  h = deviceMalloc(&out, (size_t)st->rowLayout.rowBytes * dims);
+  if (h.pStrErr) fail(h);
+  hllVectorEmitKernel<<<n, 256, 0, s>>>(st->table.regs, st->table.acc, slotOf.as<uint32_t>(), order.as<uint32_t>(), counts.as<uint32_t>(),
+                                        outIdx.as<uint32_t>(), byteOff.as<uint32_t>(), static_cast<uint8_t *>(vec),
+                                        static_cast<uint16_t *>(cnt));
+  checkLastError("hllVectorEmit");
+  DimLayout Lout = makeDimLayout(st->spec.NumDimsPerDimWidth, dims);
+  gatherDims(blockAll.as<uint8_t>(), Lin, rowsOf.as<uint32_t>(), dims, static_cast<uint8_t *>(out), Lout, s);
+  ARES_CUDA(cudaStreamSynchronize(s));
+  *dimValuesPtr = static_cast<uint8_t *>(out);
+  *hllVectorPtr = static_cast<uint8_t *>(vec);
+  *hllVectorSizePtr = (size_t)totals[1];
+  *hllDimRegIDCountPtr = static_cast<uint16_t *>(cnt);
+  return dims;
+}
+
 static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outValues, cudaStream_t s, bool ordered = true) {
   for (int i = 0; i < NUM_DIM_WIDTH; i++)
     if (out.NumDimsPerDimWidth[i] != st->spec.NumDimsPerDimWidth[i]) throw EngineError("dimension layout differs from AggSpec");
@@ -2030,6 +2237,7 @@ static int64_t finalize(AggState *st, const DimensionVector &out, uint8_t *outVa
     if (status == SF_OK) return st->resultHost[0];
     if (status == SF_TABLE_OVERFLOW) { const uint32_t c[2] = {st->resultHost[2], 1}; checkOverflow(st, c); }
     if (status == SF_OUTPUT_TOO_SMALL) throw EngineError("output DimensionVector capacity is smaller than the number of groups");
+    if (status == SF_PEER_LATE) throw EngineError("exchange over peer memory: a peer's part did not arrive within the wait bound");
     if (status == SF_PART_TRUNCATED) throw EngineError("exchange part truncated: a rank held more rows than the fixed part carries; repeat the exchange with exact sizes");
     // SF_TOO_MANY: more groups than one CTA sorts — the multi-launch path below
   }
@@ -2096,26 +2304,7 @@ static int64_t finalizeHLL(AggState *st, uint8_t **dimValuesPtr, uint8_t **hllVe
   if (!st->hll) throw EngineError("AggStateFinalizeHLL needs a state created with AGGR_HLL");
   if (!dimValuesPtr || !hllVectorPtr || !hllVectorSizePtr || !hllDimRegIDCountPtr) throw EngineError("null output pointer");
   *dimValuesPtr = nullptr; *hllVectorPtr = nullptr; *hllVectorSizePtr = 0; *hllDimRegIDCountPtr = nullptr;
-  if (st->hllDense) {
-    DenseCarried dc;
-    denseCarried(st, s, dc, false);
-    if (dc.entries == 0) return 0;
-    const int dims = hllRegisterVectors(dc.hash.as<uint64_t>(), dc.values.as<uint32_t>(), dc.index.as<uint32_t>(), (int)dc.entries,
-                                        hllVectorPtr, hllVectorSizePtr, hllDimRegIDCountPtr, s);
-    void *out = nullptr;
-    CGoCallResHandle h = deviceMalloc(&out, (size_t)st->rowLayout.rowBytes * dims);
-    if (h.pStrErr) {
-      std::string m(h.pStrErr); free((void *)h.pStrErr);
-      deviceFree(*hllVectorPtr); deviceFree(*hllDimRegIDCountPtr);
-      *hllVectorPtr = nullptr; *hllDimRegIDCountPtr = nullptr;
-      throw EngineError(m);
-    }
-    DimLayout Lin = makeDimLayout(st->spec.NumDimsPerDimWidth, dc.groups), Lout = makeDimLayout(st->spec.NumDimsPerDimWidth, dims);
-    gatherDims(dc.block.as<uint8_t>(), Lin, dc.index.as<uint32_t>(), dims, static_cast<uint8_t *>(out), Lout, s);
-    ARES_CUDA(cudaStreamSynchronize(s));
-    *dimValuesPtr = static_cast<uint8_t *>(out);
-    return dims;
-  }
+  if (st->hllDense) return denseVectors(st, s, dimValuesPtr, hllVectorPtr, hllVectorSizePtr, hllDimRegIDCountPtr);
   const int64_t entries = groupCount(st, s);
   if (entries == 0) return 0;
   const int n = (int)entries;
@@ -2241,8 +2430,56 @@ CGoCallResHandle AggStateMergeParts(void *state, const uint8_t *parts, int numPa
     DimLayout L = makeDimLayout(st->spec.NumDimsPerDimWidth, capRows);
     mergePartsKernel<<<smCount() * 2, 256, 0, (cudaStream_t)cudaStream>>>(parts, numParts, partStride, dimOffset, valuesOffset, L,
                                                                          st->measWidth, st->op, st->keyMode, (uint8_t)st->hashBits,
-                                                                         st->hll ? (st->hllDense ? 2 : 1) : 0, st->table);
+                                                                         st->hll ? (st->hllDense ? 2 : 1) : 0, st->table, nullptr, 0u);
     checkLastError("AggStateMergeParts");
+    return 0;
+  });
+}
+
+// Exchange over peer memory (sharded queries on one NVLink / NVSwitch node).  `peerSlots[r]` = the address, in THIS
+// process, of this rank's part slot inside rank r's receive buffer; `peerFlags[r]` = the address of flags[myRank] on rank
+// r (the host maps the peers' buffers: CUDA IPC / fabric handles, e.g. torch symmetric memory).  One launch; asynchronous.
+CGoCallResHandle AggStateExportPartToPeers(void *state, uint8_t *const *peerSlots, uint32_t *const *peerFlags, int numPeers, int myRank,
+                                           size_t partBytes, int capRows, size_t dimOffset, size_t valuesOffset, uint32_t epoch,
+                                           void *cudaStream, int device) {
+  return guarded("AggStateExportPartToPeers", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    if (st->hll) throw EngineError("AggStateExportPartToPeers: HLL states exchange through AggStateExport");
+    if (capRows <= 0 || capRows > kSmallFinalizeMax) throw EngineError("AggStateExportPartToPeers: capRows must be in [1, 32768]");
+    if (numPeers <= 0 || numPeers > 16 || myRank < 0 || myRank >= numPeers) throw EngineError("AggStateExportPartToPeers: 1..16 peers");
+    if (partBytes % 16 != 0) throw EngineError("AggStateExportPartToPeers: partBytes must be a multiple of 16");
+    PeerExportArgs E;
+    memset(&E, 0, sizeof(E));
+    for (int r = 0; r < numPeers; r++) { E.peerSlot[r] = peerSlots[r]; E.peerFlag[r] = peerFlags[r]; }
+    uint8_t *part = peerSlots[myRank];
+    E.F.G = st->table;
+    E.F.L = makeDimLayout(st->spec.NumDimsPerDimWidth, capRows);
+    E.F.outBlock = part + dimOffset; E.F.outValues = part + valuesOffset;
+    E.F.resultDev = reinterpret_cast<uint32_t *>(part);
+    E.F.rowBytes = st->rowLayout.rowBytes; E.F.width = st->measWidth; E.F.outCapacity = capRows;
+    E.F.keyMode = st->keyMode; E.F.hashBits = (uint8_t)st->hashBits; E.F.op = st->op;
+    E.partBytes = partBytes; E.numPeers = (uint32_t)numPeers; E.myRank = (uint32_t)myRank; E.epoch = epoch;
+    exportToPeersKernel<<<kFinCtas, 1024, 0, (cudaStream_t)cudaStream>>>(E);
+    checkLastError("AggStateExportPartToPeers");
+    return 0;
+  });
+}
+
+// Receiving side: as AggStateMergeParts, but the merge kernel itself waits (bounded) until every peer has stored `epoch`
+// into flags[peer].  A peer that does not arrive is reported by the next AggStateFinalize.
+CGoCallResHandle AggStateMergePartsWhenFlagged(void *state, const uint8_t *parts, int numParts, size_t partStride, int capRows,
+                                               size_t dimOffset, size_t valuesOffset, const uint32_t *flags, uint32_t epoch,
+                                               void *cudaStream, int device) {
+  return guarded("AggStateMergePartsWhenFlagged", device, [&]() -> int64_t {
+    AggState *st = asState(state);
+    if (numParts <= 0) return 0;
+    if (flags == nullptr) throw EngineError("AggStateMergePartsWhenFlagged: flags is null");
+    ensureRoom(st, (uint64_t)numParts * (uint64_t)capRows, (cudaStream_t)cudaStream);
+    DimLayout L = makeDimLayout(st->spec.NumDimsPerDimWidth, capRows);
+    mergePartsKernel<<<smCount() * 2, 256, 0, (cudaStream_t)cudaStream>>>(parts, numParts, partStride, dimOffset, valuesOffset, L,
+                                                                         st->measWidth, st->op, st->keyMode, (uint8_t)st->hashBits,
+                                                                         0, st->table, flags, epoch);
+    checkLastError("AggStateMergePartsWhenFlagged");
     return 0;
   });
 }

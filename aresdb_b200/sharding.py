@@ -54,6 +54,7 @@ class ShardedFusedQuery:
         self._fixed_cap = self.EXCHANGE_ROWS if (self.world > 1 and expected_groups <= self.EXCHANGE_ROWS and not q.is_hll
                                                  and os.environ.get("ARESDB_B200_EXCHANGE", "fixed") != "exact") else 0
         self._send = self._recv = None
+        self._peer, self._peer_ok = None, None   # exchange over peer memory: set up at the first exchange
 
     def reset(self):
         self.local.reset()
@@ -77,12 +78,62 @@ class ShardedFusedQuery:
         if self._send is None:
             self._send = torch.zeros(part, dtype=torch.uint8, device=sp.dev)
             self._recv = torch.empty(self.world * part, dtype=torch.uint8, device=sp.dev)
+        if self._peer is None and self._peer_ok is None:
+            self._setup_peers(part)
+        if self._peer is not None:
+            return self._exchange_peers(cap, dim_bytes)
         lib.AggStateExportPart(self.local.state, self._send.data_ptr(), cap, self._HDR, self._HDR + dim_bytes, sp.stream, sp.device)
         dist.all_gather_into_tensor(self._recv, self._send)
         self.merged.reset()
         lib.AggStateMergeParts(self.merged.state, self._recv.data_ptr(), self.world, part, cap, self._HDR, self._HDR + dim_bytes,
                                sp.stream, sp.device)
         return self.world * cap
+
+    _FLAGS = 256   # two parities x 16 ranks x uint32, in front of the two receive buffers
+
+    def _setup_peers(self, part: int):
+        """Maps every rank's receive buffer into every process (torch symmetric memory: CUDA IPC / fabric handles over
+        NVLink) for the exchange over peer memory.  All ranks agree on the outcome; on failure the NCCL all-gather stays."""
+        import os
+        import sys
+        import torch
+        ok = 0
+        if os.environ.get("ARESDB_B200_EXCHANGE", "peer") == "peer" and self.world <= 16:
+            try:
+                import torch.distributed._symmetric_memory as symm
+                buf = symm.empty(self._FLAGS + 2 * self.world * part, dtype=torch.uint8, device=self.space.dev)
+                buf.zero_()
+                hdl = symm.rendezvous(buf, self.dist.group.WORLD)
+                ptrs = [int(p) for p in hdl.buffer_ptrs]
+                torch.cuda.synchronize()
+                self._peer = dict(buf=buf, hdl=hdl, ptrs=ptrs, epoch=0, part=part)
+                ok = 1
+            except Exception as e:   # no peer access between these GPUs, or a torch without symmetric memory
+                print(f"[aresdb_b200] exchange over peer memory unavailable ({type(e).__name__}: {e}); using the NCCL all-gather",
+                      file=sys.stderr)
+        agree = torch.tensor([ok], device=self.space.dev, dtype=torch.int32)
+        self.dist.all_reduce(agree, op=self.dist.ReduceOp.MIN)   # (also: nobody writes before everybody has zeroed its flags)
+        self._peer_ok = bool(agree.item())
+        if not self._peer_ok:
+            self._peer = None
+
+    def _exchange_peers(self, cap: int, dim_bytes: int):
+        """AggStateExportPartToPeers (ONE launch: export + copy of the part into every peer's receive buffer over NVLink +
+        the arrival flags) -> AggStateMergePartsWhenFlagged (the merge kernel waits for the peers' flags itself).  No
+        collective call, no host wait; receive buffers alternate by epoch parity (a rank is at most one exchange ahead)."""
+        import ctypes as C
+        pe, sp, lib, w, r = self._peer, self.space, self.lib, self.world, self.rank
+        pe["epoch"] += 1
+        epoch, par, part = pe["epoch"], pe["epoch"] & 1, pe["part"]
+        base = self._FLAGS + par * w * part
+        slots = (C.c_void_p * w)(*[pe["ptrs"][p] + base + r * part for p in range(w)])
+        flags = (C.c_void_p * w)(*[pe["ptrs"][p] + par * 64 + r * 4 for p in range(w)])
+        lib.AggStateExportPartToPeers(self.local.state, slots, flags, w, r, part, cap, self._HDR, self._HDR + dim_bytes, epoch,
+                                      sp.stream, sp.device)
+        self.merged.reset()
+        lib.AggStateMergePartsWhenFlagged(self.merged.state, pe["ptrs"][r] + base, w, part, cap, self._HDR, self._HDR + dim_bytes,
+                                          pe["ptrs"][r] + par * 64, epoch, sp.stream, sp.device)
+        return w * cap
 
     def _exchange(self):
         if self._fixed_cap:

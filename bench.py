@@ -438,8 +438,9 @@ def gpu_run(args):
             return finish()
 
         def timed(fn, steps, warmup):
+            keep = None
             for _ in range(warmup):
-                fn()
+                keep = fn()   # (held like the timed loop holds `last`: result buffers reach their steady state here)
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()

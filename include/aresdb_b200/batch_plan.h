@@ -189,6 +189,21 @@ CGoCallResHandle AggStateExportPart(void *state, uint8_t *part, int capRows, siz
 CGoCallResHandle AggStateMergeParts(void *state, const uint8_t *parts, int numParts, size_t partStride, int capRows,
                                     size_t dimOffset, size_t valuesOffset, void *cudaStream, int device);
 
+/* The same exchange over PEER MEMORY (one NVLink / NVSwitch node), without a collective library: the host maps every
+ * rank's receive buffer into every process (CUDA IPC / fabric handles — torch symmetric memory does it) and hands over
+ * peerSlots[r] = the address of THIS rank's part slot inside rank r's receive buffer and peerFlags[r] = the address of
+ * flags[myRank] on rank r.  AggStateExportPartToPeers is ONE launch: it writes the part into the local slot, copies it
+ * into every peer's slot with 16-byte stores over NVLink and then stores `epoch` into the flag on every peer (release,
+ * system scope).  AggStateMergePartsWhenFlagged is AggStateMergeParts whose kernel first waits (bounded: ~2 s, then the
+ * next AggStateFinalize fails) until all numParts flags have reached `epoch`.  Use two receive buffers alternately and a
+ * growing epoch: a rank can be at most one exchange ahead of its peers.  numPeers <= 16, partBytes % 16 == 0. */
+CGoCallResHandle AggStateExportPartToPeers(void *state, uint8_t *const *peerSlots, uint32_t *const *peerFlags, int numPeers, int myRank,
+                                           size_t partBytes, int capRows, size_t dimOffset, size_t valuesOffset, uint32_t epoch,
+                                           void *cudaStream, int device);
+CGoCallResHandle AggStateMergePartsWhenFlagged(void *state, const uint8_t *parts, int numParts, size_t partStride, int capRows,
+                                               size_t dimOffset, size_t valuesOffset, const uint32_t *flags, uint32_t epoch,
+                                               void *cudaStream, int device);
+
 /* AGGR_HLL states: the final outputs of the reference's last-batch HyperLogLog call
  * (query/hll.cu:262-290, adopted by query/time_series_aggregate.go:661-681).  res = number of dimension
  * groups g.  *dimValuesPtr = a DimensionVector block of VectorCapacity g (groups in key order),
