@@ -441,6 +441,7 @@ def gpu_run(args):
             keep = None
             for _ in range(warmup):
                 keep = fn()   # (held like the timed loop holds `last`: result buffers reach their steady state here)
+            keep = None
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
