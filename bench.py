@@ -438,19 +438,20 @@ def gpu_run(args):
             return finish()
 
         def timed(fn, steps, warmup):
+            import gc
             keep = None
             for _ in range(warmup):
                 keep = fn()   # (held like the timed loop holds `last`: result buffers reach their steady state here)
             keep = None
+            # everything that takes host time happens BEFORE the barrier, so that the ranks leave it together
+            gc.collect()
+            gc.disable()   # (a collection inside a 0.5 ms step would be the whole step)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+            launches0 = lib.kernel_launch_count()
             torch.cuda.synchronize()
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            evs = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-            launches0 = lib.kernel_launch_count()
-            import gc
-            gc.collect()
-            gc.disable()   # (a collection inside a 0.5 ms step would be the whole step)
             evs[0].record()
             last = None
             for i in range(steps):
