@@ -134,3 +134,72 @@ def test_export_part_merge_parts_on_device():
             for k in keep:
                 if isinstance(k, FusedBatchExecutor):
                     k.close()
+
+
+@pytest.mark.gpu
+def test_exchange_over_peer_memory_kernels_on_one_device():
+    """AggStateExportPartToPeers / AggStateMergePartsWhenFlagged with both "ranks" on one GPU: two states export into each
+    other's receive buffers (part in the sender's slot of BOTH buffers, flag raised to the epoch on both), each receive
+    buffer is then folded by a merge kernel that waits for the two flags.  Same results as the collective form; two epochs on
+    alternating buffers; a part that cannot hold its sender's rows, and a peer that never arrives (bounded wait), are
+    reported by the receiver's finalize."""
+    import ctypes as C
+    import torch
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import cabi as A
+    from aresdb_b200 import synth
+    from aresdb_b200.executor import FusedBatchExecutor, dim_offsets
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    hbs = [synth.generate_batch(d, 20000, num_cities=30) for d in range(4)]
+    dev, st = eng.space.dev, eng.space.stream
+    FLAGS = 256
+    for name in ("cfg3_sum", "cfg4_hash", "no_dims_wide"):
+        q = T.queries()[name]
+        exp = T.run_legacy(orc, q, hbs)
+        for cap in (32768, 64):
+            _, _, _, dim_bytes = dim_offsets(q.num_dims_per_width, cap)
+            dim_bytes = (dim_bytes + 15) // 16 * 16
+            part = (64 + dim_bytes + q.measure_bytes * cap + 63) // 64 * 64
+            bufs = [torch.zeros(FLAGS + 2 * 2 * part, dtype=torch.uint8, device=dev) for _ in range(2)]   # flags | parity 0 | parity 1
+            locals_, keep = [], []
+            for half in (hbs[:2], hbs[2:]):
+                ex = FusedBatchExecutor(eng.lib, eng.space, q)
+                for hb in half:
+                    b = T.upload(eng, hb)
+                    keep.append(b)
+                    ex.process_batch(b)
+                locals_.append(ex)
+            for epoch in (1, 2):
+                par = epoch & 1
+                base = FLAGS + par * 2 * part
+                for r, ex in enumerate(locals_):
+                    slots = (C.c_void_p * 2)(*[bufs[p].data_ptr() + base + r * part for p in range(2)])
+                    flags = (C.c_void_p * 2)(*[bufs[p].data_ptr() + par * 64 + r * 4 for p in range(2)])
+                    eng.lib.AggStateExportPartToPeers(ex.state, slots, flags, 2, r, part, cap, 64, 64 + dim_bytes, epoch, st, 0)
+                for r in range(2):
+                    merged = FusedBatchExecutor(eng.lib, eng.space, q)
+                    eng.lib.AggStateMergePartsWhenFlagged(merged.state, bufs[r].data_ptr() + base, 2, part, cap, 64, 64 + dim_bytes,
+                                                          bufs[r].data_ptr() + par * 64, epoch, st, 0)
+                    hdr = bufs[r][base:base + 2 * part].view(2, part)[:, :12].contiguous().view(torch.int32).cpu().numpy()
+                    if (hdr[:, 2] <= cap).all():
+                        got = merged.result()
+                        T.assert_same_result(got, exp, ordered=q.reduce_mode == A.ARES_REDUCE_SORT, ctx=f"{name}/cap{cap}/epoch{epoch}/rank{r}")
+                    else:
+                        with pytest.raises(A.AresError, match="exchange part truncated"):
+                            merged.result()
+                    merged.close()
+            for ex in locals_:
+                ex.close()
+    # a peer that never raises its flag: the merge kernel gives up after its bound and the finalize says so
+    q = T.queries()["cfg3_count"]
+    cap = 1024
+    _, _, _, dim_bytes = dim_offsets(q.num_dims_per_width, cap)
+    dim_bytes = (dim_bytes + 15) // 16 * 16
+    part = (64 + dim_bytes + q.measure_bytes * cap + 63) // 64 * 64
+    buf = torch.zeros(FLAGS + 2 * part, dtype=torch.uint8, device=dev)
+    merged = FusedBatchExecutor(eng.lib, eng.space, q)
+    eng.lib.AggStateMergePartsWhenFlagged(merged.state, buf.data_ptr() + FLAGS, 2, part, cap, 64, 64 + dim_bytes, buf.data_ptr(), 7, st, 0)
+    with pytest.raises(A.AresError, match="did not arrive"):
+        merged.result()
+    merged.close()
