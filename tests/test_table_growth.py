@@ -24,84 +24,94 @@ from aresdb_b200.query import AggQuery, Measure
 eng, orc = H.get_backend("b200"), H.get_backend("oracle")
 TS, CITY, STATUS, FARE = T.TS, T.CITY, T.STATUS, T.FARE
 hbs = [synth.generate_batch(d, 60000, num_cities=50, null_rate=0.01) for d in range(3)]
-case = {case!r}
-if case == "hash":        # ~1.7e5 near-unique groups through the hash-table kernels: two doublings from 2^17 slots
-    q = AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE))
-    exp = T.run_legacy(orc, q, hbs)
-    got = T.run_fused(eng, q, hbs)
-    assert exp.groups > 150000
-    T.assert_same_result(got, exp, ctx=case)
-elif case == "hash_big":  # the DEFAULT table (2^21 slots) against 2 x 2.5e6 near-unique rows: every CTA folds several tiles,
-    # the stop comes mid-batch, warps drain at different tiles and the resumed launch picks each of them up where it stopped
-    big = [synth.generate_batch(d, 2500000, num_cities=200, null_rate=0.01) for d in range(2)]
-    q = AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE))
-    exp = T.run_legacy(orc, q, big)
-    got = T.run_fused(eng, q, big)
-    assert exp.groups > 4000000
-    assert (got.packed_rows() == exp.packed_rows()).all() and got.measures.tobytes() == exp.measures.tobytes()
-elif case == "hash32":    # hash-reduce mode with the bypass kernel
-    q = AggQuery([], [CITY, E.floor(TS, E.Lit(2))], Measure("count"), reduce_mode=A.ARES_REDUCE_HASH)
-    exp = T.run_legacy(orc, q, hbs)
-    got = T.run_fused(eng, q, hbs, expected_groups=100000)
-    assert exp.groups > 100000
-    # group identity in this mode is the 32-bit hash: ~5 pairs of different rows collide at this size and merge; which
-    # member names the merged group is unspecified on the reference's device path too (concurrent insert), so the
-    # comparison is by hash, and every row named must be a row of the data
-    import hashes as HS
-    by_hash = lambda r: dict(zip(HS.murmur3_32(r.packed_rows()).tolist(), r.measures.tolist()))
-    assert got.groups == exp.groups and by_hash(got) == by_hash(exp), "hash32: groups by hash differ"
-    every = T.run_legacy(orc, AggQuery([], [CITY, E.floor(TS, E.Lit(2))], Measure("count")), hbs)
-    assert every.groups > exp.groups and set(got.rows) <= set(every.rows)
-elif case == "spill":     # direct-indexed kernels with the zone map of ANOTHER batch: every row is out of range
-    q = AggQuery([E.eq(STATUS, E.Lit(1))], [E.floor(TS, E.Lit(60)), CITY], Measure("sum", FARE))
-    small = [synth.generate_batch(d, 30000, num_cities=50) for d in range(2)]
-    exp = T.run_legacy(orc, q, small)
-    zms = [synth.zone_map(hb) for hb in small][::-1]
-    before = T.dense_launches(eng)
-    got = T.run_fused(eng, q, small, zone_maps=zms)
-    assert T.dense_launches(eng) - before == 2 and exp.groups > 4096
-    T.assert_same_result(got, exp, ctx=case)
-elif case == "partition":   # radix-partitioned aggregation forced on (ARESDB_B200_PARTITION=1): entries sorted by table partition per
-    # tile, folded partition by partition — same results as the direct form, for sums / counts / min, few and many groups
-    big = [synth.generate_batch(d, 700000, num_cities=120, null_rate=0.02) for d in range(2)]
-    qs = dict(unique=AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE)),
-              cfg3=AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0))], [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE)),
-              count=AggQuery([], [CITY, STATUS], Measure("count")),
-              minc=AggQuery([E.eq(STATUS, E.Lit(2))], [E.floor(TS, E.Lit(60))], Measure("min", CITY)))
-    for name, q in qs.items():
-        exp = T.run_legacy(orc, q, big)
-        got = T.run_fused(eng, q, big)
-        assert (got.packed_rows() == exp.packed_rows()).all() and got.measures.tobytes() == exp.measures.tobytes(), name
-elif case == "merge":     # AggStateMerge of more rows than the table holds
-    from aresdb_b200.executor import FusedBatchExecutor
-    q = AggQuery([], [TS, CITY], Measure("count"))
-    parts = []
-    for half in (hbs[:1], hbs[1:]):
-        ex = FusedBatchExecutor(eng.lib, eng.space, q)
-        keep = [T.upload(eng, hb) for hb in half]
-        for b in keep:
-            ex.process_batch(b)
-        parts.append(ex.finalize_into())
-        ex.close()
-    merged = FusedBatchExecutor(eng.lib, eng.space, q)
-    for g, out in parts:
-        merged.merge(out.dimension_vector(q), out.measures.ptr, g)
-    got = merged.result()
-    merged.close()
-    T.assert_same_result(got, T.run_legacy(orc, q, hbs), ctx=case)
+for case in {cases!r}:
+  if case == "hash":        # ~1.7e5 near-unique groups through the hash-table kernels: two doublings from 2^17 slots
+      q = AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE))
+      exp = T.run_legacy(orc, q, hbs)
+      got = T.run_fused(eng, q, hbs)
+      assert exp.groups > 150000
+      T.assert_same_result(got, exp, ctx=case)
+  elif case == "hash_big":  # the DEFAULT table (2^21 slots) against 2 x 2.5e6 near-unique rows: every CTA folds several tiles,
+      # the stop comes mid-batch, warps drain at different tiles and the resumed launch picks each of them up where it stopped
+      big = [synth.generate_batch(d, 2500000, num_cities=200, null_rate=0.01) for d in range(2)]
+      q = AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE))
+      exp = T.run_legacy(orc, q, big)
+      got = T.run_fused(eng, q, big)
+      assert exp.groups > 4000000
+      assert (got.packed_rows() == exp.packed_rows()).all() and got.measures.tobytes() == exp.measures.tobytes()
+  elif case == "hash32":    # hash-reduce mode with the bypass kernel
+      q = AggQuery([], [CITY, E.floor(TS, E.Lit(2))], Measure("count"), reduce_mode=A.ARES_REDUCE_HASH)
+      exp = T.run_legacy(orc, q, hbs)
+      got = T.run_fused(eng, q, hbs, expected_groups=100000)
+      assert exp.groups > 100000
+      # group identity in this mode is the 32-bit hash: ~5 pairs of different rows collide at this size and merge; which
+      # member names the merged group is unspecified on the reference's device path too (concurrent insert), so the
+      # comparison is by hash, and every row named must be a row of the data
+      import hashes as HS
+      by_hash = lambda r: dict(zip(HS.murmur3_32(r.packed_rows()).tolist(), r.measures.tolist()))
+      assert got.groups == exp.groups and by_hash(got) == by_hash(exp), "hash32: groups by hash differ"
+      every = T.run_legacy(orc, AggQuery([], [CITY, E.floor(TS, E.Lit(2))], Measure("count")), hbs)
+      assert every.groups > exp.groups and set(got.rows) <= set(every.rows)
+  elif case == "spill":     # direct-indexed kernels with the zone map of ANOTHER batch: every row is out of range
+      q = AggQuery([E.eq(STATUS, E.Lit(1))], [E.floor(TS, E.Lit(60)), CITY], Measure("sum", FARE))
+      small = [synth.generate_batch(d, 30000, num_cities=50) for d in range(2)]
+      exp = T.run_legacy(orc, q, small)
+      zms = [synth.zone_map(hb) for hb in small][::-1]
+      before = T.dense_launches(eng)
+      got = T.run_fused(eng, q, small, zone_maps=zms)
+      assert T.dense_launches(eng) - before == 2 and exp.groups > 4096
+      T.assert_same_result(got, exp, ctx=case)
+  elif case == "partition":   # radix-partitioned aggregation forced on (ARESDB_B200_PARTITION=1): entries sorted by table partition per
+      # tile, folded partition by partition — same results as the direct form, for sums / counts / min, few and many groups
+      big = [synth.generate_batch(d, 700000, num_cities=120, null_rate=0.02) for d in range(2)]
+      qs = dict(unique=AggQuery([E.ne(CITY, E.Lit(0))], [TS, CITY], Measure("sum", FARE)),
+                cfg3=AggQuery([E.eq(STATUS, E.Lit(1)), E.gt(FARE, E.Lit(5.0))], [E.floor(TS, E.Lit(3600)), CITY], Measure("sum", FARE)),
+                count=AggQuery([], [CITY, STATUS], Measure("count")),
+                minc=AggQuery([E.eq(STATUS, E.Lit(2))], [E.floor(TS, E.Lit(60))], Measure("min", CITY)))
+      for name, q in qs.items():
+          exp = T.run_legacy(orc, q, big)
+          got = T.run_fused(eng, q, big)
+          assert (got.packed_rows() == exp.packed_rows()).all() and got.measures.tobytes() == exp.measures.tobytes(), name
+  elif case == "merge":     # AggStateMerge of more rows than the table holds
+      from aresdb_b200.executor import FusedBatchExecutor
+      q = AggQuery([], [TS, CITY], Measure("count"))
+      parts = []
+      for half in (hbs[:1], hbs[1:]):
+          ex = FusedBatchExecutor(eng.lib, eng.space, q)
+          keep = [T.upload(eng, hb) for hb in half]
+          for b in keep:
+              ex.process_batch(b)
+          parts.append(ex.finalize_into())
+          ex.close()
+      merged = FusedBatchExecutor(eng.lib, eng.space, q)
+      for g, out in parts:
+          merged.merge(out.dimension_vector(q), out.measures.ptr, g)
+      got = merged.result()
+      merged.close()
+      T.assert_same_result(got, T.run_legacy(orc, q, hbs), ctx=case)
 print("ok")
 """
 
 
-@pytest.mark.parametrize("jit", ["1", "0"])
-@pytest.mark.parametrize("case,slots", [("hash", 1 << 17), ("hash_big", 0), ("hash32", 1 << 17), ("spill", 1 << 12), ("merge", 1 << 12),
-                                        ("partition", 0), ("partition", 1 << 18)])
-def test_table_grows(case, slots, jit):
-    if jit == "0" and case in ("spill", "partition"):
-        pytest.skip("the interpreter has no direct-indexed / partitioned form")
-    code = CHILD.format(tests=str(ROOT / "tests"), root=str(ROOT), case=case)
+# one child process per ENVIRONMENT (table size, JIT on / off, partitioned form), several cases in it: a child pays for
+# the interpreter start-up, the library load and the NVRTC compiles once
+GROUPS = [
+    ("slots17-jit", ["hash", "hash32"], 1 << 17, "1", False),
+    ("slots17-interpreter", ["hash", "hash32"], 1 << 17, "0", False),
+    ("default-jit", ["hash_big"], 0, "1", False),
+    ("default-interpreter", ["hash_big"], 0, "0", False),
+    ("slots12-jit", ["spill", "merge"], 1 << 12, "1", False),
+    ("slots12-interpreter", ["merge"], 1 << 12, "0", False),
+    ("partition-default", ["partition"], 0, "1", True),
+    ("partition-slots18", ["partition"], 1 << 18, "1", True),
+]
+
+
+@pytest.mark.parametrize("name,cases,slots,jit,partition", GROUPS, ids=[g[0] for g in GROUPS])
+def test_table_grows(name, cases, slots, jit, partition):
+    code = CHILD.format(tests=str(ROOT / "tests"), root=str(ROOT), cases=cases)
     env = dict(os.environ, ARESDB_B200_JIT=jit)
-    if case == "partition":
+    if partition:
         env["ARESDB_B200_PARTITION"] = "1"
     if slots:
         env["ARESDB_B200_TABLE_SLOTS"] = str(slots)
