@@ -15,7 +15,12 @@ query's time range (UTC, numeric offsets like "-8" / "05:30", or an IANA name wi
 * time zones              query/common/time_filter.go:69-85 (ParseTimezone), query/time_bucketizer.go:72-146 (the time
                           column is shifted with CONVERT_TZ = Plus before it is bucketized), utils/time.go:110-116
 
-Not covered (they raise): joins, time-zone columns / daylight-saving switches inside the range, geo, array functions,
+* joins                   query/aql_compiler.go:168-282 (processJoinConditions / matchEqualJoin): up to 8 dimension tables,
+                          each joined directly to the main table by ONE equality between a main-table column and the
+                          table's single primary-key column; `alias.column` references become foreign-column operands
+                          (VarRef.TableID = position in `joins` + 1); filters that read a joined table run after the join
+
+Not covered (they raise): geo joins, time-zone columns / daylight-saving switches inside the range, array functions,
 non-aggregate queries.
 """
 from __future__ import annotations
@@ -27,7 +32,7 @@ from dataclasses import dataclass, field
 
 from . import cabi as A
 from . import expr as E
-from .query import AggQuery, Measure
+from .query import AggQuery, Join, Measure
 
 SECONDS = {"m": 60, "h": 3600, "d": 86400}
 SECONDS_PER_WEEK = 7 * 86400
@@ -59,6 +64,8 @@ class Column:
 class Table:
     name: str
     columns: list = field(default_factory=list)
+    primary_key: list = field(default_factory=list)   # column names (dimension tables: the join key)
+    is_fact_table: bool = True
 
     def index_of(self, name: str) -> int:
         for i, c in enumerate(self.columns):
@@ -69,6 +76,13 @@ class Table:
     def ref(self, name: str) -> E.Col:
         i = self.index_of(name)
         return E.Col(i, self.columns[i].data_type, name)
+
+
+@dataclass
+class JoinedTable:
+    """A dimension table a query may join: its schema and the resident table the executors read (joins.DimensionTable)."""
+    schema: Table
+    resident: object = None
 
 
 # ---- time filter -----------------------------------------------------------------------------------
@@ -281,8 +295,9 @@ class _Str:
 
 
 class _Parser:
-    def __init__(self, text: str, table: Table):
-        self.table, self.toks, pos = table, [], 0
+    def __init__(self, text: str, table: Table, foreign=()):
+        # foreign: (alias, Table schema) per joined table, in `joins` order
+        self.table, self.foreign, self.toks, pos = table, list(foreign), [], 0
         while pos < len(text):
             if text[pos:].strip() == "":
                 break
@@ -335,11 +350,26 @@ class _Parser:
         # enum literal against an enum column -> its dictionary id (unknown literal: matches nothing, id -1)
         for a, b in ((lhs, rhs), (rhs, lhs)):
             if isinstance(b, _Str):
-                if not isinstance(a, E.Col) or self.table.columns[a.index].enum is None:
+                column = (self.table.columns[a.index] if isinstance(a, E.Col)
+                          else self.foreign[a.table][1].columns[a.index] if isinstance(a, E.ForeignCol) else None)
+                if column is None or column.enum is None:
                     raise AQLError("string literals are only comparable with enum columns")
-                lit = E.Lit(self.table.columns[a.index].enum.get(b.value, -1))
+                lit = E.Lit(column.enum.get(b.value, -1))
                 lhs, rhs = (a, lit) if b is rhs else (lit, a)
         return E.Binary(op, lhs, rhs)
+
+    def column(self, v: str):
+        """`column`, `main_table.column` or `alias.column` of a joined table."""
+        if "." in v:
+            prefix, name = v.split(".", 1)
+            for t, (alias, schema) in enumerate(self.foreign):
+                if prefix == alias:
+                    i = schema.index_of(name)
+                    return E.ForeignCol(t, i, schema.columns[i].data_type, name)
+            if prefix != self.table.name:
+                raise AQLError(f"unknown table {prefix}")
+            v = name
+        return self.table.ref(v)
 
     def unary(self):
         kind, v = self.take()
@@ -372,8 +402,7 @@ class _Parser:
                 return self.call(v.lower(), args)
             if v.lower() in ("true", "false"):
                 return E.Lit(1 if v.lower() == "true" else 0, E.Type.Boolean)
-            name = v.split(".", 1)[1] if v.startswith(self.table.name + ".") else v
-            return self.table.ref(name)
+            return self.column(v)
         raise AQLError(f"unexpected token {v}")
 
     def call(self, name, args):
@@ -384,17 +413,67 @@ class _Parser:
         raise AQLError(f"unsupported function {name}")
 
 
-def parse_expression(text: str, table: Table):
-    return _Parser(text, table).parse()
+def parse_expression(text: str, table: Table, foreign=()):
+    return _Parser(text, table, foreign).parse()
+
+
+MAX_FOREIGN_TABLES = 8
+
+
+def process_joins(query: dict, table: Table, dimension_tables: dict | None):
+    """The query's `joins` clause -> ([Join], [(alias, schema)]).  Same acceptance rules as the reference
+    (query/aql_compiler.go:168-282): at most 8 tables; one condition per join, an equality of two columns, one of the main
+    table and one of THIS joined table (either order); the joined table is a dimension table with a single-column primary
+    key, and the joined column is that key (many-to-one)."""
+    specs = query.get("joins") or []
+    if len(specs) > MAX_FOREIGN_TABLES:
+        raise AQLError(f"At most {MAX_FOREIGN_TABLES} foreign tables allowed, got: {len(specs)}")
+    foreign, residents = [], []
+    for spec in specs:
+        known = (dimension_tables or {}).get(spec.get("table"))
+        if known is None:
+            raise AQLError(f"unknown table {spec.get('table')}")
+        foreign.append((spec.get("alias") or spec["table"], known.schema))
+        residents.append(known.resident)
+    joins = []
+    for t, spec in enumerate(specs):
+        schema = foreign[t][1]
+        conditions = spec.get("conditions") or []
+        if any("geography_intersects" in c.lower() for c in conditions):
+            raise AQLError("geo joins are outside this engine")
+        if len(conditions) != 1:
+            raise AQLError(f"1 join conditions expected, got {len(conditions)}")
+        if schema.is_fact_table:
+            raise AQLError(f"join table {schema.name} is fact table, only dimension table supported")
+        if len(schema.primary_key) > 1:
+            raise AQLError("composite key not supported")
+        e = parse_expression(conditions[0], table, foreign)
+        if not isinstance(e, E.Binary):
+            raise AQLError("binary expression expected in join condition")
+        if e.op != A.Equal:
+            raise AQLError("equal join expected")
+        left, right = e.lhs, e.rhs
+        for side in (left, right):
+            if not isinstance(side, (E.Col, E.ForeignCol)):
+                raise AQLError("column in join condition expected")
+        if isinstance(left, E.ForeignCol):     # main table at left, foreign table at right
+            left, right = right, left
+        if not isinstance(left, E.Col) or not isinstance(right, E.ForeignCol) or right.table != t:
+            raise AQLError(f"foreign table must be joined directly to the main table, join condition: {conditions[0]}")
+        if not schema.primary_key or schema.primary_key[0] != right.name:
+            raise AQLError("join column is not primary key of foreign table")
+        joins.append(Join(residents[t], left))
+    return joins, foreign
 
 
 # ---- query -----------------------------------------------------------------------------------------
-def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES_REDUCE_SORT) -> AggQuery:
-    """One element of the AQL `queries` array -> AggQuery.  `now` (epoch seconds) anchors relative time filters."""
+def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES_REDUCE_SORT,
+                  dimension_tables: dict | None = None) -> AggQuery:
+    """One element of the AQL `queries` array -> AggQuery.  `now` (epoch seconds) anchors relative time filters;
+    `dimension_tables` {name: JoinedTable} are the tables the `joins` clause may name."""
     if query.get("table") != table.name:
         raise AQLError(f"unknown table {query.get('table')}")
-    if query.get("joins"):
-        raise AQLError("joins are outside this engine")
+    joins, foreign = process_joins(query, table, dimension_tables)
     if "(" in str(query.get("timezone", "")):
         raise AQLError("time-zone columns (joins with the timezone table) are outside this engine")
     tz = parse_timezone(query.get("timezone"))
@@ -402,7 +481,7 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
     if len(measures) != 1:
         raise AQLError("expect one measure per query")   # aql_compiler.go:1140-1146
     m = measures[0]
-    agg = parse_expression(m.get("sqlExpression") or m.get("expr"), table)
+    agg = parse_expression(m.get("sqlExpression") or m.get("expr"), table, foreign)
     if not isinstance(agg, _Call):
         raise AQLError("expect aggregate function")
     if agg.name == "count":
@@ -416,7 +495,7 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
         else:
             measure = Measure(agg.name, arg)
 
-    filters = [parse_expression(f, table) for f in (m.get("rowFilters") or []) + (query.get("rowFilters") or [])]
+    filters = [parse_expression(f, table, foreign) for f in (m.get("rowFilters") or []) + (query.get("rowFilters") or [])]
     tf = query.get("timeFilter") or {}
     time_col = None
     if tf.get("column"):
@@ -448,13 +527,13 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
         tz_offset = offsets.pop()
     dims = []
     for d in query.get("dimensions") or []:
-        e = parse_expression(d.get("sqlExpression") or d.get("expr"), table)
+        e = parse_expression(d.get("sqlExpression") or d.get("expr"), table, foreign)
         if d.get("timeBucketizer"):
             if tz_offset:
                 e = E.Binary(A.Plus, e, E.Lit(tz_offset, E.Type.Signed if tz_offset < 0 else E.Type.Unsigned))
             e = time_dimension_expr(d["timeBucketizer"], e)
         dims.append(e)
-    q = AggQuery(filters, dims, measure, reduce_mode)
+    q = AggQuery(filters, dims, measure, reduce_mode, joins=joins)
     q.tz_offset = tz_offset     # result formatting: DimensionMeta.from_offset (utils.AdjustOffset, utils/time.go:110-116)
     return q
 
