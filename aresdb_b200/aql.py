@@ -20,7 +20,14 @@ query's time range (UTC, numeric offsets like "-8" / "05:30", or an IANA name wi
                           table's single primary-key column; `alias.column` references become foreign-column operands
                           (VarRef.TableID = position in `joins` + 1); filters that read a joined table run after the join
 
-Not covered (they raise): geo joins, time-zone columns / daylight-saving switches inside the range, array functions,
+* time-zone columns       query/aql_compiler.go:439-465 (processTimezone), query/aql_processor.go:459-508
+                          (prepareTimezoneTable), query/time_bucketizer.go:78-92: `"timezone": "tzcolumn(join_key)"` joins the
+                          configured timezone table on `join_key = alias.id` (alias `__timezone_lookup` unless the query joins
+                          that table itself), maps the enum column `tzcolumn` — its dictionary holds IANA names — to the
+                          zones' offsets at `now` (an int16 table on the device), and shifts the time column by the joined
+                          row's offset before bucketizing
+
+Not covered (they raise): geo joins, a daylight-saving switch inside the range of a FIXED named zone, array functions,
 non-aggregate queries.
 """
 from __future__ import annotations
@@ -467,16 +474,64 @@ def process_joins(query: dict, table: Table, dimension_tables: dict | None):
 
 
 # ---- query -----------------------------------------------------------------------------------------
+DEFAULT_TIMEZONE_ALIAS = "__timezone_lookup"
+
+
+def parse_timezone_column(text) -> tuple | None:
+    """`column(join_key)` -> (column of the timezone table, join key of the main table); anything else: None
+    (parseTimezoneColumnString, query/aql_compiler.go:1395-1406)."""
+    m = re.fullmatch(r"\s*([A-Za-z_][A-Za-z_0-9]*)\s*\(\s*([A-Za-z_][A-Za-z_0-9.]*)\s*\)\s*", str(text or ""))
+    return (m.group(1), m.group(2)) if m else None
+
+
 def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES_REDUCE_SORT,
-                  dimension_tables: dict | None = None) -> AggQuery:
+                  dimension_tables: dict | None = None, timezone_table: str | None = None, upload=None) -> AggQuery:
     """One element of the AQL `queries` array -> AggQuery.  `now` (epoch seconds) anchors relative time filters;
-    `dimension_tables` {name: JoinedTable} are the tables the `joins` clause may name."""
+    `dimension_tables` {name: JoinedTable} are the tables the `joins` clause may name; `timezone_table` is the configured
+    timezone table (utils config Query.TimezoneTable.TableName) and `upload(int16 array) -> buffer with .ptr` places the
+    offset table of a time-zone column in the executor's memory space."""
     if query.get("table") != table.name:
         raise AQLError(f"unknown table {query.get('table')}")
+    tz_column = parse_timezone_column(query.get("timezone"))
+    tz_alias = None
+    if tz_column is not None:       # processTimezone: the timezone table joins the query (once)
+        if not timezone_table:
+            raise AQLError("a time-zone column needs the configured timezone table")
+        specs = list(query.get("joins") or [])
+        tz_alias = next((j.get("alias") or j["table"] for j in specs if j.get("table") == timezone_table), None)
+        if tz_alias is None:
+            tz_alias = DEFAULT_TIMEZONE_ALIAS
+            specs.append({"table": timezone_table, "alias": tz_alias, "conditions": [f"{tz_column[1]}={tz_alias}.id"]})
+        query = dict(query, joins=specs)
     joins, foreign = process_joins(query, table, dimension_tables)
-    if "(" in str(query.get("timezone", "")):
-        raise AQLError("time-zone columns (joins with the timezone table) are outside this engine")
-    tz = parse_timezone(query.get("timezone"))
+    tz = _dt.timezone.utc if tz_column is not None else parse_timezone(query.get("timezone"))
+    tz_operand = None
+    if tz_column is not None:       # prepareTimezoneTable: dictionary id -> the zone's offset at `now`
+        t = next(i for i, (alias, _) in enumerate(foreign) if alias == tz_alias)
+        schema = foreign[t][1]
+        try:
+            ci = schema.index_of(tz_column[0])
+        except AQLError:
+            raise AQLError(f"unknown timezone column {tz_column[0]}") from None
+        names = schema.columns[ci].enum
+        if names is None:
+            raise AQLError(f"unknown timezone column {tz_column[0]}")
+        import numpy as np
+        seconds = np.zeros(max(names.values(), default=-1) + 1, np.int64)
+        for zone, i in names.items():
+            try:
+                import zoneinfo
+                seconds[i] = int(_dt.datetime.fromtimestamp(int(now), zoneinfo.ZoneInfo(zone)).utcoffset().total_seconds())
+            except Exception as e:
+                raise AQLError(f"error parsing timezone {zone}") from e
+        # the table is int16, filled with Go's int16(offset): offsets from +9:06:08 on (Sydney, Auckland ...) WRAP, there
+        # as here (aql_processor.go:488-492)
+        lookup = seconds.astype(np.int16)
+        if upload is None:
+            raise AQLError("a time-zone column needs `upload` (the offset table lives in the executor's memory space)")
+        buf = upload(lookup)
+        joins[t].timezone_ptr, joins[t].timezone_size, joins[t].timezone_keep = buf.ptr, len(lookup), buf
+        tz_operand = E.ForeignCol(t, ci, schema.columns[ci].data_type, tz_column[0], timezone=True)
     measures = query.get("measures") or []
     if len(measures) != 1:
         raise AQLError("expect one measure per query")   # aql_compiler.go:1140-1146
@@ -529,6 +584,8 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
     for d in query.get("dimensions") or []:
         e = parse_expression(d.get("sqlExpression") or d.get("expr"), table, foreign)
         if d.get("timeBucketizer"):
+            if tz_operand is not None:      # (timeColumn CONVERT_TZ timezoneColumn): the joined row's offset
+                e = E.Binary(A.Plus, e, tz_operand)
             if tz_offset:
                 e = E.Binary(A.Plus, e, E.Lit(tz_offset, E.Type.Signed if tz_offset < 0 else E.Type.Unsigned))
             e = time_dimension_expr(d["timeBucketizer"], e)

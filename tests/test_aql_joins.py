@@ -102,3 +102,55 @@ def test_compiled_join_query_equals_the_hand_built_one(backend):
              "measures": [{"sqlExpression": "sum(api_cities.surge)"}], "dimensions": [{"sqlExpression": "status"}]}
     got2 = T.run_legacy(be, aql.compile_query(text2, trips, 0, dimension_tables=known), hbs)
     T.assert_same_result(got2, T.run_legacy(be, TJ.join_queries(table, tzb.ptr, tzn)["sum_surge"], hbs), ctx="sum_surge")
+
+
+ZONES = ["America/Los_Angeles", "America/New_York", "Europe/Amsterdam", "Asia/Kolkata", "Asia/Tokyo", "Australia/Sydney",
+         "America/Sao_Paulo", "Africa/Johannesburg", "Asia/Kathmandu", "Pacific/Auckland", "UTC", "America/St_Johns"]
+
+
+@pytest.mark.parametrize("backend", ["ref", "oracle"])
+def test_time_zone_column_joins_the_timezone_table_and_shifts_by_the_joined_offset(backend):
+    """`"timezone": "tz(city_id)"`: the configured timezone table joins on city_id = __timezone_lookup.id, the enum column
+    `tz` (dictionary of IANA names) becomes an int16 offset table at `now`, and the hour bucket is taken in the joined city's
+    local time — the hand-built `local_hour` query of tests/test_joins.py with the same offset table."""
+    import datetime as dt
+    import zoneinfo
+    import numpy as np
+    be = H.get_backend(backend)
+    table, _ = TJ._dimension_table(be)
+    trips, cities = _schemas()
+    cities.columns[2] = aql.Column("tz", A.Uint8, enum={z: i for i, z in enumerate(ZONES)})
+    known = {"api_cities": aql.JoinedTable(cities, resident=table)}
+    now = 1_720_000_000          # July: daylight saving in the northern zones
+    offsets = np.array([int(dt.datetime.fromtimestamp(now, zoneinfo.ZoneInfo(z)).utcoffset().total_seconds()) for z in ZONES],
+                       np.int64).astype(np.int16)   # int16(offset) as in the reference: +10 h and +12 h wrap
+    assert offsets[0] == -7 * 3600 and offsets[3] == 19800 and offsets[8] == 20700 and offsets[11] == -9000
+    assert offsets[5] == 36000 - 65536 and offsets[9] == 43200 - 65536
+    hbs = [synth.generate_batch(d, n, num_cities=80, null_rate=0.03) for d, n in ((0, 6000), (1, 2500))]
+    text = {"table": "trips", "timezone": "tz(city_id)", "measures": [{"sqlExpression": "count(*)"}], "rowFilters": ["city_id != 0"],
+            "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}]}
+    uploads = []
+
+    def upload(a):
+        uploads.append(a.copy())
+        return be.put(a)
+
+    q = aql.compile_query(text, trips, now, dimension_tables=known, timezone_table="api_cities", upload=upload)
+    assert len(q.joins) == 1 and q.joins[0].on.index == 1 and q.joins[0].timezone_size == 12 and (uploads[0] == offsets).all()
+    tzb = be.put(offsets)
+    by_hand = TJ.join_queries(table, tzb.ptr, len(offsets))["local_hour"]
+    got, exp = T.run_legacy(be, q, hbs), T.run_legacy(be, by_hand, hbs)
+    assert exp.groups > 24
+    T.assert_same_result(got, exp, ctx="local_hour")
+    # the query joins the timezone table itself: its alias is used, no second join
+    text2 = dict(text, joins=[{"table": "api_cities", "alias": "c", "conditions": ["city_id = c.id"]}])
+    q2 = aql.compile_query(text2, trips, now, dimension_tables=known, timezone_table="api_cities", upload=upload)
+    assert len(q2.joins) == 1
+    T.assert_same_result(T.run_legacy(be, q2, hbs), exp, ctx="local_hour, explicit join")
+    for bad, match in ((dict(text, timezone="nope(city_id)"), "unknown timezone column"),
+                       (dict(text, timezone="region(city_id)"), "error parsing timezone"),
+                       (dict(text, timezone="surge(city_id)"), "unknown timezone column")):
+        with pytest.raises(aql.AQLError, match=match):
+            aql.compile_query(bad, trips, now, dimension_tables=known, timezone_table="api_cities", upload=upload)
+    with pytest.raises(aql.AQLError, match="configured timezone table"):
+        aql.compile_query(text, trips, now, dimension_tables=known, upload=upload)
