@@ -27,8 +27,8 @@ query's time range (UTC, numeric offsets like "-8" / "05:30", or an IANA name wi
                           zones' offsets at `now` (an int16 table on the device), and shifts the time column by the joined
                           row's offset before bucketizing
 
-Not covered (they raise): geo joins, a daylight-saving switch inside the range of a FIXED named zone, array functions,
-non-aggregate queries.
+Not covered (they raise): geo joins, MORE than one daylight-saving switch inside the range of a named zone (one switch
+is handled as the reference does, query/time_bucketizer.go:94-133), array functions, non-aggregate queries.
 """
 from __future__ import annotations
 
@@ -563,35 +563,56 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
 
     # fixed offset of the query's zone over [from, to): buildTimeDimensionExpr (query/time_bucketizer.go:72-146) shifts
     # the time column by it (CONVERT_TZ is Plus, query/time_series_aggregate.go:87) before bucketizing
-    tz_offset = 0
+    tz_offset, tz_to_offset, dst_switch = 0, 0, 0
     if tz is not _dt.timezone.utc:
         ends = [t for t in ((frm, to) if tf.get("column") else ()) if t is not None]
+        offset_at = lambda t: int(_dt.datetime.fromtimestamp(int(t), tz).utcoffset().total_seconds())
         if isinstance(tz, _dt.timezone):                     # numeric offset: constant by definition
-            probe = ends or [int(now)]
+            tz_offset = tz_to_offset = offset_at((ends or [now])[0])
         else:
             if len(ends) < 2:
-                raise AQLError("a named time zone needs a time filter with both ends (its offset must be constant over the range)")
-            # every offset change strictly inside [from, to) matters — a range can cross TWO switches and end at the
-            # offset it started with (January to January): walk the range in steps no transition pair can hide in
-            # (zones switch at most a few times a year; 7 days is far below the shortest gap between two switches)
+                raise AQLError("a named time zone needs a time filter with both ends (its offset is taken at the ends of the range)")
             lo, hi = int(ends[0]), int(ends[1])
-            probe = list(range(lo, max(hi, lo + 1), 7 * 86400)) + [max(hi - 1, lo)]
-        offsets = {int(_dt.datetime.fromtimestamp(t, tz).utcoffset().total_seconds()) for t in probe}
-        if len(offsets) != 1:
-            raise AQLError("a daylight-saving switch inside the time range is outside this front-end")
-        tz_offset = offsets.pop()
+            tz_offset, tz_to_offset = offset_at(lo), offset_at(hi)
+            # every offset change inside [from, to) matters — a range can cross TWO switches and end at the offset it started
+            # with (January to January; the reference compares the two ends only and would then shift the whole range by one
+            # offset): walk the range in steps no transition pair can hide in (7 days is far below the shortest gap
+            # between two switches) and count the changes
+            probe = list(range(lo, max(hi, lo + 1), 7 * 86400)) + [max(hi - 1, lo), hi]
+            seen = [offset_at(t) for t in probe]
+            changes = sum(1 for a, b in zip(seen, seen[1:]) if a != b)
+            if changes > 1 or (changes == 1 and tz_offset == tz_to_offset):
+                raise AQLError("more than one daylight-saving switch inside the time range is outside this front-end")
+            if tz_offset != tz_to_offset:
+                # ONE switch: utils.CalculateDSTSwitchTs (utils/time.go:93-107) — bisect down to an hour, round down
+                f, t = lo, hi
+                while t - f > 3600:
+                    mid = f + (t - f) // 2
+                    if offset_at(f) != offset_at(mid):
+                        t = mid
+                    else:
+                        f = mid
+                dst_switch = t - t % 3600
     dims = []
     for d in query.get("dimensions") or []:
         e = parse_expression(d.get("sqlExpression") or d.get("expr"), table, foreign)
         if d.get("timeBucketizer"):
             if tz_operand is not None:      # (timeColumn CONVERT_TZ timezoneColumn): the joined row's offset
                 e = E.Binary(A.Plus, e, tz_operand)
-            if tz_offset:
+            if dst_switch:
+                # buildTimeDimensionExpr's "simulated IF" (query/time_bucketizer.go:96-133, its test
+                # time_bucketizer_test.go:256-330), verbatim: timeCol + (fromOffset + (fromOffset - toOffset) * (timeCol >= switchTs))
+                shift = E.Binary(A.Plus, E.Lit(tz_offset, E.Type.Signed),
+                                 E.Binary(A.Multiply, E.Lit(tz_offset - tz_to_offset, E.Type.Signed),
+                                          E.Binary(A.GreaterThanOrEqual, e, E.Lit(dst_switch))))
+                e = E.Binary(A.Plus, e, shift)
+            elif tz_offset:
                 e = E.Binary(A.Plus, e, E.Lit(tz_offset, E.Type.Signed if tz_offset < 0 else E.Type.Unsigned))
             e = time_dimension_expr(d["timeBucketizer"], e)
         dims.append(e)
     q = AggQuery(filters, dims, measure, reduce_mode, joins=joins)
-    q.tz_offset = tz_offset     # result formatting: DimensionMeta.from_offset (utils.AdjustOffset, utils/time.go:110-116)
+    # result formatting: DimensionMeta.from_offset / to_offset / dst_switch (utils.AdjustOffset, utils/time.go:110-116)
+    q.tz_offset, q.tz_to_offset, q.dst_switch = tz_offset, tz_to_offset, dst_switch
     return q
 
 

@@ -26,6 +26,8 @@ class DimensionMeta:
     time_bucketizer: str | None = None     # set for time dimensions
     time_unit: str = ""                    # "", "second", "minute", "hour", "day", "millisecond"
     from_offset: int = 0                   # seconds the query's time zone is ahead of UTC (AggQuery.tz_offset)
+    to_offset: int = 0                     # ... at the end of the range, and the switch instant when they differ
+    dst_switch: int = 0                    # (AggQuery.tz_to_offset / dst_switch)
 
 
 def format_float32(x) -> str:
@@ -52,7 +54,11 @@ def _utc(ts: int) -> _dt.datetime:
 
 def format_time_dimension(val: int, meta: DimensionMeta) -> str:
     if meta.time_unit:
-        val -= meta.from_offset             # numeric output is an instant again (utils.AdjustOffset, utils/time.go:110-116)
+        # numeric output is an instant again (utils.AdjustOffset, utils/time.go:110-116)
+        offset = meta.from_offset
+        if meta.dst_switch > 0 and val >= meta.dst_switch + meta.to_offset:
+            offset = meta.to_offset
+        val -= offset
         div = {"day": 86400, "hour": 3600, "minute": 60}.get(meta.time_unit)
         if div:
             val = int(val / div) if val < 0 else val // div   # Go integer division truncates

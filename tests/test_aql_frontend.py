@@ -224,9 +224,59 @@ def test_named_zone_without_a_switch_in_range_and_with_one():
         pytest.skip("no tz database on this box")
     assert agg.tz_offset == -7 * 3600                          # PDT
     assert sorted(int(f.rhs.value) for f in agg.filters) == [1_726_815_600, 1_726_988_400]   # local midnights 09-20 .. 09-22
-    q["timeFilter"] = {"column": "request_at", "from": "2024-11-01", "to": "2024-11-05"}      # DST ends 2024-11-03
-    with pytest.raises(aql.AQLError):
+    q["timeFilter"] = {"column": "request_at", "from": "2024-11-01", "to": "2024-11-05"}      # DST ends 2024-11-03 09:00 UTC
+    one = aql.compile_query(q, _tz_table(), 1_731_000_000)
+    assert (one.tz_offset, one.tz_to_offset, one.dst_switch) == (-25200, -28800, 1_730_624_400)
+    q["timeFilter"] = {"column": "request_at", "from": "2024-01-01", "to": "2025-01-01"}      # two switches, same offset at both ends
+    with pytest.raises(aql.AQLError, match="more than one daylight-saving switch"):
         aql.compile_query(q, _tz_table(), 1_731_000_000)
+
+
+def test_one_switch_in_range_builds_the_references_expression_and_evaluates_to_it():
+    """The reference's own case (query/time_bucketizer_test.go:256-330): Los Angeles, 1509772380 .. 1509882360 ->
+    requested_at + (-25200 + 3600 * (requested_at >= 1509872400)), FLOOR 3600 — structure and constants; then the same query
+    through the reference call sequence on the HOST build and the C restatement against numpy."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, synth
+    from aresdb_b200.postprocess import DimensionMeta, format_time_dimension
+    table = aql.Table("trips", [aql.Column(n, t) for n, t in zip(synth.COLUMN_NAMES, synth.COLUMN_TYPES)])
+    q = {"table": "trips", "timezone": "America/Los_Angeles", "measures": [{"sqlExpression": "count(*)"}],
+         "timeFilter": {"column": "request_at", "from": "1509772380", "to": "1509882360"},
+         "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}]}
+    try:
+        agg = aql.compile_query(q, table, 1_509_900_000)
+    except aql.AQLError as e:
+        if "parse" in str(e):
+            pytest.skip("no tz database on this box")
+        raise
+    d = agg.dimensions[0]
+    assert d.op == A.Floor and int(d.rhs.value) == 3600 and d.lhs.op == A.Plus and isinstance(d.lhs.lhs, E.Col)
+    shift = d.lhs.rhs
+    assert shift.op == A.Plus and int(shift.lhs.value) == -25200 and shift.lhs.type == E.Type.Signed
+    assert shift.rhs.op == A.Multiply and int(shift.rhs.lhs.value) == 3600 and shift.rhs.lhs.type == E.Type.Signed
+    assert shift.rhs.rhs.op == A.GreaterThanOrEqual and int(shift.rhs.rhs.rhs.value) == 1_509_872_400
+    assert (agg.tz_offset, agg.tz_to_offset, agg.dst_switch) == (-25200, -28800, 1_509_872_400)
+    # rows on both sides of the switch
+    rng = np.random.default_rng(5)
+    n = 5000
+    ts = rng.integers(1_509_772_380 - 3000, 1_509_882_360 + 3000, n).astype(np.uint32)
+    ones = np.ones(n, np.uint8)
+    hb = synth.HostBatch([ts, np.full(n, 3, np.uint16), ones.copy(), np.ones(n, np.float32)], [ones, ones.copy(), ones.copy(), ones.copy()], n, 0)
+    keep = (ts >= 1_509_772_380) & (ts < aql.parse_time_filter(q["timeFilter"], 0, aql.parse_timezone("America/Los_Angeles"))[1])
+    t64 = ts.astype(np.int64)
+    local = t64 + (-25200 + 3600 * (t64 >= 1_509_872_400))
+    exp = {}
+    for b in (local[keep] // 3600 * 3600).tolist():
+        exp[b] = exp.get(b, 0) + 1
+    for backend in ("ref", "oracle"):
+        res = T.run_legacy(H.get_backend(backend), agg, [hb])
+        got = dict(zip(np.array(res.decoded_dims()[0], np.int64).tolist(), res.measures.tolist()))
+        assert got == exp and len(got) > 20, backend
+    # numeric output back to instants (utils.AdjustOffset): buckets before the switch by the from-offset, later ones by the to-offset
+    meta = DimensionMeta(time_bucketizer="hour", time_unit="second", from_offset=-25200, to_offset=-28800, dst_switch=1_509_872_400)
+    assert format_time_dimension(1_509_872_400 - 28800 - 3600, meta) == str(1_509_872_400 - 28800 - 3600 + 25200)
+    assert format_time_dimension(1_509_872_400 - 28800, meta) == str(1_509_872_400)
 
 
 def test_numeric_time_dimension_output_is_an_instant_again():
