@@ -9,8 +9,10 @@ query's time range (UTC, numeric offsets like "-8" / "05:30", or an IANA name wi
                           (regular -> FLOOR, recurring -> FLOOR(MOD) [/ unit], irregular -> calendar functors)
 * measures                query/aql_compiler.go:1139-1250 (count -> sum(1), sum widening, hll) and
                           query/context/query_context_helper.go:540-575 (countdistincthll)
-* row / common filters    SQL-ish boolean expressions over columns and literals, enum literals translated
-                          through the column's dictionary (query/aql_compiler.go:540-600)
+* row / common filters    SQL-ish boolean expressions over columns and literals with the reference parser's operator
+                          precedence (query/expr/token.go:302-331): comparisons, AND / OR / NOT, + - * / %, & | ^ ~,
+                          IN / NOT IN lists (expanded into OR chains, query_context_helper.go:93-130), IS [NOT] NULL; enum
+                          literals translated through the column's dictionary (query/aql_compiler.go:540-600)
 
 * time zones              query/common/time_filter.go:69-85 (ParseTimezone), query/time_bucketizer.go:72-146 (the time
                           column is shifted with CONVERT_TZ = Plus before it is bucketized), utils/time.go:110-116
@@ -283,10 +285,13 @@ def time_dimension_expr(bucketizer: str, time_col: E.Expr) -> E.Expr:
 
 
 # ---- SQL-ish expressions ---------------------------------------------------------------------------
-_TOKEN = re.compile(r"\s*(?:(\d+\.\d*|\.\d+|\d+)|'((?:[^']|'')*)'|([A-Za-z_][A-Za-z_0-9.]*)|(<>|!=|<=|>=|[-+*/%()=<>,]))")
+_TOKEN = re.compile(r"\s*(?:(\d+\.\d*|\.\d+|\d+)|'((?:[^']|'')*)'|([A-Za-z_][A-Za-z_0-9.]*)|(<>|!=|<=|>=|[-+*/%()=<>,&|^~]))")
+# operator precedence of the reference's expression parser (query/expr/token.go:302-331), bitwise XOR above * / % included
 _BINARY = {"or": (1, A.Or), "and": (2, A.And), "=": (4, A.Equal), "!=": (4, A.NotEqual), "<>": (4, A.NotEqual),
            "<": (4, A.LessThan), "<=": (4, A.LessThanOrEqual), ">": (4, A.GreaterThan), ">=": (4, A.GreaterThanOrEqual),
-           "+": (5, A.Plus), "-": (5, A.Minus), "*": (6, A.Multiply), "/": (6, A.Divide), "%": (6, A.Mod)}
+           "in": (4, "in"), "is": (4, "is"),
+           "|": (5, A.BitwiseOr), "&": (6, A.BitwiseAnd),
+           "+": (8, A.Plus), "-": (8, A.Minus), "*": (9, A.Multiply), "/": (9, A.Divide), "%": (9, A.Mod), "^": (10, A.BitwiseXor)}
 AGGREGATES = ("count", "sum", "min", "max", "avg", "hll", "countdistincthll")
 
 
@@ -346,12 +351,55 @@ class _Parser:
         while True:
             kind, v = self.peek()
             key = v.lower() if kind == "id" else v
+            negated = False
+            if kind == "id" and key == "not":       # only as NOT IN here (query/expr/parser.go:319-329)
+                nxt = self.toks[self.i + 1] if self.i + 1 < len(self.toks) else (None, None)
+                if nxt[0] != "id" or nxt[1].lower() != "in":
+                    raise AQLError("expected IN after NOT")
+                negated, key = True, "in"
             if kind not in ("op", "id") or key not in _BINARY or _BINARY[key][0] < min_prec:
                 return lhs
             prec, op = _BINARY[key]
             self.take()
-            rhs = self.expression(prec + 1)
-            lhs = self.binary(op, lhs, rhs)
+            if negated:
+                self.take()
+            if op == "in":
+                lhs = self.inclusion(lhs, negated)
+            elif op == "is":
+                lhs = self.is_test(lhs)
+            else:
+                rhs = self.expression(prec + 1)
+                lhs = self.binary(op, lhs, rhs)
+
+    def inclusion(self, lhs, negated: bool):
+        """`column IN (a, b, ...)` -> ((column = a) OR (column = b)) OR ...; NOT IN -> NOT of that (expandINop,
+        query/context/query_context_helper.go:93-130, 335-341).  An empty list is the literal false."""
+        if not isinstance(lhs, (E.Col, E.ForeignCol)):
+            raise AQLError("lhs of IN or NOT_IN must be a valid column")
+        self.expect("(")
+        values = []
+        if self.peek() != ("op", ")"):
+            values.append(self.expression(0))
+            while self.peek() == ("op", ","):
+                self.take()
+                values.append(self.expression(0))
+        self.expect(")")
+        e = E.Lit(0, E.Type.Boolean)
+        for i, v in enumerate(values):
+            eq = self.binary(A.Equal, lhs, v)
+            e = eq if i == 0 else E.Binary(A.Or, e, eq)
+        return E.Unary(A.Not, e) if negated else e
+
+    def is_test(self, lhs):
+        """`x IS [NOT] NULL` (rewriteIsOp, query/expr/parser.go:240-270)."""
+        kind, v = self.take()
+        affirmative = True
+        if kind == "id" and v.lower() == "not":
+            affirmative = False
+            kind, v = self.take()
+        if kind == "id" and v.lower() in ("null", "unknown"):
+            return E.Unary(A.IsNull if affirmative else A.IsNotNull, lhs)
+        raise AQLError(f"bad literal {v} following IS" + ("" if affirmative else " NOT"))
 
     def binary(self, op, lhs, rhs):
         # enum literal against an enum column -> its dictionary id (unknown literal: matches nothing, id -1)
@@ -391,6 +439,8 @@ class _Parser:
         if kind == "op" and v == "-":
             e = self.unary()
             return E.Lit(-e.value) if isinstance(e, E.Lit) else E.Unary(A.Negate, e)
+        if kind == "op" and v == "~":
+            return E.Unary(A.BitwiseNot, self.unary())
         if kind == "id" and v.lower() == "not":
             return E.Unary(A.Not, self.expression(3))
         if kind == "id":

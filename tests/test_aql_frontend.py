@@ -310,3 +310,45 @@ def test_fixed_offset_query_end_to_end_on_the_checker():
         want[int(b)] = want.get(int(b), 0) + 1
     have = {int(d): int(m) for d, m in zip(got.decoded_dims()[0], got.measures)}
     assert have == want and len(have) == 16                     # local hours 00 .. 15 of the data's day
+
+
+def test_in_lists_null_tests_and_bitwise_operators_end_to_end():
+    """`IN` / `NOT IN` (expanded into OR chains of equalities, enum literals through the dictionary), `IS [NOT] NULL`, `& | ^ ~`
+    with the reference parser's precedence (query/expr/token.go:302-331) — parsed here, evaluated by the reference call
+    sequence on the HOST build and the C restatement, against numpy with three-valued logic (a NULL operand never passes)."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, synth
+    enum = {"none": 0, "completed": 1, "cancelled": 2, "other": 3}
+    table = aql.Table("trips", [aql.Column("request_at", A.Uint32), aql.Column("city_id", A.Uint16),
+                                aql.Column("status", A.Uint8, enum=enum), aql.Column("fare", A.Float32)])
+    hb = synth.generate_batch(0, 8000, num_cities=9, null_rate=0.08)
+    ts, city, status, fare = hb.values
+    vt, vc, vs, vf = [v != 0 for v in hb.valid]
+    cases = {
+        "city_id in (1, 3, 5)": vc & np.isin(city, [1, 3, 5]),
+        "city_id not in (1, 3)": vc & ~np.isin(city, [1, 3]),
+        "status in ('completed', 'other', 'never heard of')": vs & np.isin(status, [1, 3]),
+        "fare is not null": vf,
+        "fare is null or city_id in (2)": ~vf | (vc & (city == 2)),
+        "city_id & 1 = 1": vc & ((city & 1) == 1),
+        "city_id | 4 = 5 and status is not null": vc & ((city | 4) == 5) & vs,
+        "city_id ^ 1 * 2 = 4": vc & (((city ^ 1) * 2) == 4),      # XOR binds tighter than * in this grammar
+        "~city_id & 7 = 6": vc & (((~city.astype(np.int64)) & 7) == 6),
+        "city_id in ()": np.zeros(len(city), bool),
+    }
+    for text, keep in cases.items():
+        q = {"table": "trips", "measures": [{"sqlExpression": "count(*)"}], "rowFilters": [text],
+             "dimensions": [{"sqlExpression": "status"}]}
+        agg = aql.compile_query(q, table, 0)
+        exp = {}
+        for s_, ok in zip(status[keep].tolist(), vs[keep].tolist()):
+            k = s_ if ok else None
+            exp[k] = exp.get(k, 0) + 1
+        for backend in ("ref", "oracle"):
+            res = T.run_legacy(H.get_backend(backend), agg, [hb])
+            got = dict(zip(res.decoded_dims()[0], res.measures.tolist()))
+            assert got == exp, (text, backend)
+    for bad in ("fare + 1 in (2)", "city_id not 3", "fare is 3", "city_id in 1"):
+        with pytest.raises(aql.AQLError):
+            aql.parse_expression(bad, table)
