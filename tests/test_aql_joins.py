@@ -154,3 +154,34 @@ def test_time_zone_column_joins_the_timezone_table_and_shifts_by_the_joined_offs
             aql.compile_query(bad, trips, now, dimension_tables=known, timezone_table="api_cities", upload=upload)
     with pytest.raises(aql.AQLError, match="configured timezone table"):
         aql.compile_query(text, trips, now, dimension_tables=known, upload=upload)
+
+
+@pytest.mark.gpu
+def test_compiled_join_and_time_zone_column_queries_on_the_fused_path():
+    """The same AQL texts through ExecuteBatchPlan on the GPU (the lookup is a gather stage of the fused kernel, the
+    time-zone offset table a plan operand) against the reference call sequence on the oracle."""
+    import datetime as dt
+    import zoneinfo
+    import numpy as np
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    trips, cities = _schemas()
+    cities.columns[2] = aql.Column("tz", A.Uint8, enum={z: i for i, z in enumerate(ZONES)})
+    now = 1_720_000_000
+    hbs = [synth.generate_batch(d, n, num_cities=80, null_rate=0.03) for d, n in ((0, 20000), (1, 7777))]
+    texts = {
+        "by_region": {"table": "trips", "joins": [{"table": "api_cities", "alias": "c", "conditions": ["trips.city_id = c.id"]}],
+                      "measures": [{"sqlExpression": "sum(fare)", "rowFilters": ["status = 1"]}], "rowFilters": ["c.surge > 1.0", "c.region in (1, 2, 5)"],
+                      "dimensions": [{"sqlExpression": "c.region"}, {"sqlExpression": "request_at", "timeBucketizer": "hour"}]},
+        "local_hour": {"table": "trips", "timezone": "tz(city_id)", "measures": [{"sqlExpression": "count(*)"}], "rowFilters": ["city_id != 0"],
+                       "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}]},
+    }
+    res = {}
+    for be in (orc, eng):
+        table, _ = TJ._dimension_table(be)
+        known = {"api_cities": aql.JoinedTable(cities, resident=table)}
+        for name, text in texts.items():
+            q = aql.compile_query(text, trips, now, dimension_tables=known, timezone_table="api_cities", upload=be.put)
+            res[(name, be is eng)] = T.run_fused(be, q, hbs) if be is eng else T.run_legacy(be, q, hbs)
+    for name in texts:
+        assert res[(name, False)].groups > 10
+        T.assert_same_result(res[(name, True)], res[(name, False)], ctx=name)
