@@ -603,13 +603,14 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
     filters = [parse_expression(f, table, foreign) for f in (m.get("rowFilters") or []) + (query.get("rowFilters") or [])]
     tf = query.get("timeFilter") or {}
     time_col = None
+    time_filters = []        # kept apart from the common filters (OOPK.TimeFilters): archive batches inside the range skip them
     if tf.get("column"):
         time_col = table.ref(tf["column"])
         frm, to = parse_time_filter(tf, now, tz)
         if frm is not None:
-            filters.append(E.Binary(A.GreaterThanOrEqual, time_col, E.Lit(frm, E.Type.Unsigned)))
+            time_filters.append(E.Binary(A.GreaterThanOrEqual, time_col, E.Lit(frm, E.Type.Unsigned)))
         if to is not None:
-            filters.append(E.Binary(A.LessThan, time_col, E.Lit(to, E.Type.Unsigned)))
+            time_filters.append(E.Binary(A.LessThan, time_col, E.Lit(to, E.Type.Unsigned)))
 
     # fixed offset of the query's zone over [from, to): buildTimeDimensionExpr (query/time_bucketizer.go:72-146) shifts
     # the time column by it (CONVERT_TZ is Plus, query/time_series_aggregate.go:87) before bucketizing
@@ -660,7 +661,8 @@ def compile_query(query: dict, table: Table, now: int, reduce_mode: int = A.ARES
                 e = E.Binary(A.Plus, e, E.Lit(tz_offset, E.Type.Signed if tz_offset < 0 else E.Type.Unsigned))
             e = time_dimension_expr(d["timeBucketizer"], e)
         dims.append(e)
-    q = AggQuery(filters, dims, measure, reduce_mode, joins=joins)
+    q = AggQuery(filters, dims, measure, reduce_mode, joins=joins, time_filters=time_filters)
+    q.time_range = (frm, to) if tf.get("column") else (None, None)
     # result formatting: DimensionMeta.from_offset / to_offset / dst_switch (utils.AdjustOffset, utils/time.go:110-116)
     q.tz_offset, q.tz_to_offset, q.dst_switch = tz_offset, tz_to_offset, dst_switch
     return q

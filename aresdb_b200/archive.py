@@ -9,8 +9,9 @@ row range sort column by sort column and ships only those rows (qc.prefilterSlic
 cVectorParty.SliceByValue / SliceIndex, memstore/vector_party.go:371-432).  The sliced batch keeps ABSOLUTE row numbers
 in its count vectors; index space = the finest requested column (transferArchiveBatch, query/aql_processor.go:568-626).
 
-This module mirrors that logic on numpy arrays and hands the result to the executors as an ordinary `Batch`
-(RLE columns are expanded once per batch on the device and then take the fused fast path).
+This module mirrors that logic on numpy arrays and hands the result to the executors as an ordinary `Batch` (the fused
+kernel decodes the RLE columns in place, from their runs), and the scan of a shard's archive batches: which days a time
+filter touches, and that only the first and the last of them evaluate it.
 """
 from __future__ import annotations
 
@@ -196,3 +197,35 @@ def match_prefilters(filters: list, sort_columns: list) -> Prefilters:
         break                                                   # stop after the first range filter
     out.prefilter_ids.sort()
     return out
+
+
+# ---- which archive batches a query scans, and which of them evaluate its time filter -------------------------------
+SECONDS_PER_DAY = 86400
+
+
+def archive_batch_ids(time_range, now: int) -> range:
+    """Archive batch IDs (= days since the epoch) a query with time filter [from, to) scans: from / 86400 up to
+    (to + 86399) / 86400, open ends = day 0 / the day of `now` (TableScanner.ArchiveBatchIDStart / End, reference
+    query/aql_compiler.go:1044-1057)."""
+    frm, to = time_range
+    start = 0 if frm is None else int(frm) // SECONDS_PER_DAY
+    end = (int(now if to is None else to) + SECONDS_PER_DAY - 1) // SECONDS_PER_DAY
+    return range(start, max(end, start))
+
+
+def scan_archive_batches(executor, batches: dict, time_range, now: int) -> list:
+    """Feeds the resident archive batches {day: Batch} of a shard to `executor` the way processShard does
+    (query/aql_processor.go:222-248): days in the scanned range, empty ones skipped, and the time filter evaluated for the
+    FIRST and the LAST scanned day only — every row of a day in between lies inside [from, to) by construction (an archive
+    batch holds the rows of its day, and the fact table's time column is never NULL).
+    Returns [(day, evaluated the time filter)] of the batches processed."""
+    ids = archive_batch_ids(time_range, now)
+    done = []
+    for day in ids:
+        b = batches.get(day)
+        if b is None or b.num_rows == 0:
+            continue
+        first_or_last = day == ids.start or day == ids.stop - 1
+        executor.process_batch(b, time_filters=first_or_last)
+        done.append((day, first_or_last))
+    return done

@@ -128,7 +128,7 @@ class LegacyBatchExecutor:
                            e.op, stream, dev)
         return A.scratch_input(frame.ptr, 4 * size, dt)
 
-    def process_batch(self, batch: Batch, is_last: bool = False):
+    def process_batch(self, batch: Batch, is_last: bool = False, time_filters: bool = True):
         """One batch through preExec -> filter -> project -> reduce -> postExec.  `is_last` only
         matters for hll queries (HyperLogLog builds the register vectors on the last batch,
         reference query/aql_batchexecutor.go:228-233)."""
@@ -152,7 +152,10 @@ class LegacyBatchExecutor:
                 ctx["size"] = self._call("BinaryFilter", inputs[0], inputs[1], ctx["index"].ptr, predicate.ptr,
                                          ctx["size"], recs, nrec, bc, batch.start_count, fn, stream, dev)
 
-        for f in q.filters[:q.num_main_filters]:
+        lo, hi = q.time_filter_range
+        for i, f in enumerate(q.filters[:q.num_main_filters]):
+            if not time_filters and lo <= i < hi:     # an archive batch strictly inside the time range (customFilterFunc)
+                continue
             self._eval(f, batch, ctx, filter_action)
             ctx["frames"].clear()
         # join (aql_batchexecutor.go:115-147): one RecordID per surviving index position and joined table
@@ -332,6 +335,7 @@ class FusedBatchExecutor:
         self._plan.NumInsts = len(self.insts)
         for i, pi in enumerate(self.insts):
             self._plan.Insts[i] = pi
+        self._plan_nt = None
         self.calls = 0
         self.skipped = 0   # batches whose zone map contradicts a filter (skipping.py): never launched
         self.expected_groups = expected_groups
@@ -352,11 +356,27 @@ class FusedBatchExecutor:
                 self._plan.ForeignColumns[k].Table = t
                 self._plan.ForeignColumns[k].Column = f
 
-    def process_batch(self, batch: Batch, stream=None):
+    def _plan_without_time_filters(self):
+        """The plan of an archive batch strictly inside the query's time range: same columns, joins and sinks, the two
+        time-filter instructions left out (a different plan shape: its own specialised kernel)."""
+        if self._plan_nt is None:
+            insts = self.q.plan_instructions(time_filters=False)
+            p = A.BatchPlan()
+            C.memmove(C.byref(p), C.byref(self._plan), C.sizeof(A.BatchPlan))   # foreign tables / columns as in the full plan
+            p.NumInsts = len(insts)
+            for i, pi in enumerate(insts):
+                p.Insts[i] = pi
+            self._plan_nt = p
+        return self._plan_nt
+
+    def process_batch(self, batch: Batch, stream=None, time_filters: bool = True):
+        """`time_filters=False`: an archive batch that lies strictly inside the query's time range skips the time filter
+        (archiveBatchCustomFilterExecutor evaluates it for the first and the last batch only, query/aql_processor.go:627-638)."""
         if should_skip_batch(self.q, batch.ranges):
             self.skipped += 1
             return
-        p = self._plan
+        lo, hi = self.q.time_filter_range
+        p = self._plan if time_filters or lo == hi else self._plan_without_time_filters()
         p.NumColumns = len(batch.columns)
         for i, vp in enumerate(batch.columns):
             p.Columns[i] = vp

@@ -33,13 +33,21 @@ class Join:
 
 
 class AggQuery:
-    def __init__(self, filters, dimensions, measure: Measure, reduce_mode: int = A.ARES_REDUCE_SORT, joins=None):
+    def __init__(self, filters, dimensions, measure: Measure, reduce_mode: int = A.ARES_REDUCE_SORT, joins=None, time_filters=None):
         self.joins = list(joins or [])
         resolved = [E.resolve(f) for f in filters]
+        # the query's time filter (AQL timeFilter: `col >= from`, `col < to`) is kept apart from the common filters: it runs
+        # in the batch's custom-filter step, and archive batches strictly inside the range skip it
+        # (OOPK.TimeFilters; archiveBatchCustomFilterExecutor, reference query/aql_processor.go:627-638)
+        timed = [E.resolve(f) for f in (time_filters or [])]
+        if any(E.uses_foreign(f) for f in timed):
+            raise ValueError("time filters read the main table")
         # main-table filters run before the join, filters that read a joined table after it
         # (MainTableCommonFilters / ForeignTableCommonFilters, reference query/aql_batchexecutor.go:100-147)
-        self.filters = [f for f in resolved if not E.uses_foreign(f)] + [f for f in resolved if E.uses_foreign(f)]
-        self.num_main_filters = sum(1 for f in resolved if not E.uses_foreign(f))
+        main = [f for f in resolved if not E.uses_foreign(f)]
+        self.filters = main + timed + [f for f in resolved if E.uses_foreign(f)]
+        self.time_filter_range = (len(main), len(main) + len(timed))     # positions in self.filters
+        self.num_main_filters = len(main) + len(timed)
         self.dimensions = [E.resolve(d) for d in dimensions]
         self.reduce_mode = reduce_mode
         # ---- dimensions: widest first, stable (reference query/aql_compiler.go:1341-1370) ----------
@@ -110,9 +118,10 @@ class AggQuery:
         return spec
 
     # ---- fused plan ------------------------------------------------------------------------------
-    def plan_instructions(self) -> list[A.PlanInst]:
+    def plan_instructions(self, time_filters: bool = True) -> list[A.PlanInst]:
         """Post-order flattening of every expression: one PlanInst per non-leaf AST node (what
-        processExpression turns into one cgo call, reference query/time_series_aggregate.go:493-593)."""
+        processExpression turns into one cgo call, reference query/time_series_aggregate.go:493-593).
+        `time_filters=False`: the plan of an archive batch strictly inside the query's time range."""
         insts: list[A.PlanInst] = []
         self.foreign_columns = []   # distinct (table, column, timezone) leaves in first-use order = BatchPlan.ForeignColumns
 
@@ -149,8 +158,10 @@ class AggQuery:
             pi.Sink, pi.SinkArg, pi.SinkDataType = sink, sink_arg, sink_dt
             insts.append(pi)
 
-        for f in self.filters:
-            emit(f, A.PLAN_SINK_FILTER, 0, A.Bool)
+        lo, hi = self.time_filter_range
+        for i, f in enumerate(self.filters):
+            if time_filters or not lo <= i < hi:
+                emit(f, A.PLAN_SINK_FILTER, 0, A.Bool)
         for pos, qi in enumerate(self.dim_order):
             emit(self.dimensions[qi], A.PLAN_SINK_DIMENSION, pos, self.dim_types[qi])
         emit(self.measure, A.PLAN_SINK_MEASURE, 0, self.measure_data_type)

@@ -168,3 +168,74 @@ def test_random_queries_match_slice_run(archive, seed):
     sl = AR.prefilter_slice(archive, SCAN, N, pf.equality_values, pf.range_prefilter)
     got = run(orc, AggQuery(rest, dims, Measure("count")), archive, sl)
     T.assert_same_result(got, exp, ctx=f"seed {seed}: {len(pf.prefilter_ids)} prefilters of {len(filters)} filters")
+
+
+def test_archive_scan_evaluates_the_time_filter_on_the_first_and_last_day_only():
+    """processShard's archive loop (query/aql_processor.go:222-248, 627-638): the days the time filter touches are scanned,
+    the filter itself runs for the first and the last of them; results equal the scan that filters every batch — on the
+    reference's HOST build and the oracle — and the plan of a middle batch has two filter instructions less."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, archive, cabi as A, synth
+    from aresdb_b200.executor import LegacyBatchExecutor
+    table = aql.Table("trips", [aql.Column(n, t) for n, t in zip(synth.COLUMN_NAMES, synth.COLUMN_TYPES)])
+    day0 = synth.BASE_TS // 86400
+    assert synth.BASE_TS % 86400 == 0
+    frm, to = synth.BASE_TS + 86400 + 7 * 3600, synth.BASE_TS + 4 * 86400 + 5 * 3600      # day 1 07:00 .. day 4 05:00
+    text = {"table": "trips", "measures": [{"sqlExpression": "sum(fare)", "rowFilters": ["status = 1"]}],
+            "timeFilter": {"column": "request_at", "from": str(frm), "to": str(to - 1)},
+            "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}, {"sqlExpression": "city_id"}]}
+    q = aql.compile_query(text, table, synth.BASE_TS + 10 * 86400)
+    lo, hi = q.time_filter_range
+    assert hi - lo == 2 and q.time_range[0] == frm
+    assert len(q.plan_instructions()) - len(q.plan_instructions(time_filters=False)) == 2
+    assert list(archive.archive_batch_ids(q.time_range, 0)) == [day0 + 1, day0 + 2, day0 + 3, day0 + 4]
+    assert list(archive.archive_batch_ids((None, frm), 0)) == list(range(0, day0 + 2))
+    assert archive.archive_batch_ids((frm, None), synth.BASE_TS + 2 * 86400 + 5).stop == day0 + 3
+    # (an archive batch's time column is never NULL and lies inside its day: that is what makes the rule exact)
+    hbs = {day0 + d: synth.generate_batch(d, 3000 + 500 * d, num_cities=6, null_rate=0.0) for d in range(6)}
+    for backend in ("ref", "oracle"):
+        be = H.get_backend(backend)
+        results = []
+        for rule in (True, False):
+            ex = LegacyBatchExecutor(be.lib, be.space, q)
+            keep = {day: T.upload(be, hb) for day, hb in hbs.items()}
+            if rule:
+                done = archive.scan_archive_batches(ex, keep, q.time_range, 0)
+                assert done == [(day0 + 1, True), (day0 + 2, False), (day0 + 3, False), (day0 + 4, True)]
+            else:
+                for day in archive.archive_batch_ids(q.time_range, 0):
+                    ex.process_batch(keep[day])
+            results.append(ex.result())
+        assert results[0].groups > 60
+        T.assert_same_result(results[0], results[1], ctx=backend)
+
+
+@pytest.mark.gpu
+def test_archive_scan_on_the_fused_path():
+    """The same scan through ExecuteBatchPlan: first / last day with the full plan, the days in between with the plan
+    that has no time-filter instructions (its own specialised kernel), zone maps on — equal to the oracle's call sequence
+    that filters every batch."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, archive, synth
+    from aresdb_b200.executor import FusedBatchExecutor
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    table = aql.Table("trips", [aql.Column(n, t) for n, t in zip(synth.COLUMN_NAMES, synth.COLUMN_TYPES)])
+    day0 = synth.BASE_TS // 86400
+    frm, to = synth.BASE_TS + 86400 + 7 * 3600, synth.BASE_TS + 4 * 86400 + 5 * 3600
+    for measure in ("sum(fare)", "count(*)"):
+        text = {"table": "trips", "measures": [{"sqlExpression": measure, "rowFilters": ["status = 1", "fare > 5.0"]}],
+                "timeFilter": {"column": "request_at", "from": str(frm), "to": str(to - 1)},
+                "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}, {"sqlExpression": "city_id"}]}
+        q = aql.compile_query(text, table, synth.BASE_TS + 10 * 86400)
+        hbs = {day0 + d: synth.generate_batch(d, 30000 + 5000 * d, num_cities=20, null_rate=0.0) for d in range(6)}
+        exp = T.run_legacy(orc, q, [hbs[d] for d in archive.archive_batch_ids(q.time_range, 0)])
+        for zone_maps in (False, True):
+            ex = FusedBatchExecutor(eng.lib, eng.space, q)
+            keep = {day: T.upload(eng, hb, 0, synth.zone_map(hb) if zone_maps else None) for day, hb in hbs.items()}
+            done = archive.scan_archive_batches(ex, keep, q.time_range, 0)
+            assert [d for d, _ in done] == list(range(day0 + 1, day0 + 5)) and [f for _, f in done] == [True, False, False, True]
+            got = ex.result()
+            ex.close()
+            T.assert_same_result(got, exp, ctx=f"{measure} zone_maps={zone_maps}")
