@@ -173,6 +173,71 @@ class HLL:
             out[index] = rho
         return out
 
+    # ---- what the broker does with register sets of several nodes (query/common/hll.go:148-215, 669-733) -------------
+    def to_dense(self):
+        """ConvertToDense."""
+        if self.dense:
+            return
+        self.dense = self.dense_registers().tobytes()
+        self.sparse = None
+
+    def to_sparse(self) -> bool:
+        """ConvertToSparse: only when it is the cheaper form (fewer than a quarter of the registers hit)."""
+        if self.non_zero_registers * 4 >= HLL_REGISTERS:
+            return False
+        if self.sparse is not None:
+            return True
+        d = np.frombuffer(self.dense, np.uint8)
+        self.sparse = [(int(i), int(d[i])) for i in np.nonzero(d)[0]]
+        self.dense = None
+        return True
+
+    def set(self, index: int, rho: int):
+        """Set: one more register (each at most once); switches to dense at a quarter of the registers."""
+        self.non_zero_registers += 1
+        if self.dense:
+            b = bytearray(self.dense)
+            b[index] = rho
+            self.dense = bytes(b)
+            return
+        self.sparse = (self.sparse or []) + [(index, rho)]
+        if self.non_zero_registers * 4 >= HLL_REGISTERS:
+            self.to_dense()
+
+    def merge(self, other: "HLL"):
+        """Merge: register-wise maximum; the receiver becomes dense."""
+        self.to_dense()
+        mine = np.frombuffer(self.dense, np.uint8).copy()
+        theirs = other.dense_registers()
+        self.non_zero_registers += int(np.count_nonzero((mine == 0) & (theirs != 0)))
+        self.dense = np.maximum(mine, theirs).tobytes()
+
+    def encode(self) -> bytes:
+        """Encode (cache form): the dense bytes, or 3 bytes per sparse register (index low, index high, rho)."""
+        if self.dense:
+            return self.dense
+        return b"".join(bytes((i & 0xFF, i >> 8, r)) for i, r in self.sparse or [])
+
+    def encode_binary(self) -> bytes:
+        """EncodeBinary (wire form): the dense bytes, or 4 bytes per sparse register — `uint32(int8(rho)) << 16 | index`,
+        the sign extension of a rho >= 128 included, as the reference writes it."""
+        if self.dense:
+            return self.dense
+        return b"".join(struct.pack("<I", ((((r - 256 if r >= 128 else r) & 0xFFFFFFFF) << 16) & 0xFFFFFFFF) | i) for i, r in self.sparse or [])
+
+    @classmethod
+    def decode(cls, data: bytes) -> "HLL":
+        """Decode: 16384 bytes are dense registers, anything else 3-byte sparse registers."""
+        if len(data) == HLL_REGISTERS:
+            return cls(int(np.count_nonzero(np.frombuffer(data, np.uint8))), dense=bytes(data))
+        n = len(data) // 3
+        return cls(n, sparse=[(data[3 * i] | (data[3 * i + 1] << 8), data[3 * i + 2]) for i in range(n)])
+
+    def compute(self) -> float:
+        """Compute: the HyperLogLog++ estimate of the register set."""
+        from .postprocess import hll_estimate
+        return hll_estimate(self.dense_registers())
+
 
 def read_hll(vector: bytes, count: int, offset: int) -> tuple:
     """readHLL: `count` below the dense threshold = that many 4-byte (index u16, rho u8) entries, else 16384 bytes."""

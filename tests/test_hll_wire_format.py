@@ -123,3 +123,35 @@ def test_a_real_hll_result_round_trips_through_the_wire_format(backend, name):
         days = sorted(int(k) for k in parsed if k != "NULL")
         assert sorted(int(k) for k in shifted if k != "NULL") == [d + 28800 for d in days]
         assert ("NULL" in shifted) == ("NULL" in parsed)
+
+
+def test_register_set_operations_known_answers():
+    """Set / Merge / ConvertToDense / ConvertToSparse / Encode / EncodeBinary / Decode / Compute
+    (query/common/hll_test.go:160-262)."""
+    h = W.HLL(2, sparse=[(100, 1), (200, 2)])
+    assert h.compute() == 2.0
+    back = W.HLL.decode(h.encode())
+    assert (back.non_zero_registers, back.sparse, back.dense) == (2, [(100, 1), (200, 2)], None)
+    dense = bytearray(DENSE)
+    dense[100], dense[200] = 1, 2
+    d = W.HLL(2, dense=bytes(dense))
+    back = W.HLL.decode(d.encode())
+    assert (back.non_zero_registers, back.sparse, back.dense) == (2, None, bytes(dense))
+    one = W.HLL(1, sparse=[(100, 1)])
+    assert one.encode_binary() == bytes([100, 0, 1, 0])
+    hll, off = W.read_hll(one.encode_binary(), 1, 0)
+    assert (hll.non_zero_registers, hll.sparse, off) == (1, [(100, 1)], 4)
+    assert W.HLL(1, sparse=[(1, 255)]).encode_binary() == bytes([1, 0, 255, 255])      # int8(rho) sign-extends
+    s = W.HLL(0)
+    s.set(100, 1)
+    s.set(200, 2)
+    assert (s.non_zero_registers, s.sparse, s.dense) == (2, [(100, 1), (200, 2)], None)
+    for i in range(201, 4300):
+        s.set(i, 3)
+    assert s.sparse is None and len(s.dense) == DENSE and s.non_zero_registers == 4101
+    assert [s.dense[i] for i in (100, 200, 201, 4299, 4300)] == [1, 2, 3, 3, 0]
+    assert not s.to_sparse()                                                              # more than a quarter of the registers
+    a, b = W.HLL(2, sparse=[(5, 3), (7, 1)]), W.HLL(2, sparse=[(5, 2), (9, 4)])
+    a.merge(b)
+    assert a.non_zero_registers == 3 and [a.dense[i] for i in (5, 7, 9)] == [3, 1, 4]
+    assert a.to_sparse() and sorted(a.sparse) == [(5, 3), (7, 1), (9, 4)] and a.dense is None
