@@ -325,3 +325,64 @@ def parse_hll_query_results(data: bytes, ignore_enum: bool = False) -> tuple:
             results.append(parse_hll_data(payload, ignore_enum))
             errors.append(None)
     return results, errors
+
+
+_MEM_BYTES = {MEM_BOOL: 1, MEM_INT8: 1, MEM_UINT8: 1, MEM_SMALL_ENUM: 1, MEM_INT16: 2, MEM_UINT16: 2, MEM_BIG_ENUM: 2,
+              MEM_INT32: 4, MEM_UINT32: 4, MEM_FLOAT32: 4, MEM_INT64: 8}
+
+
+def _value_bytes(text: str, mem_type: int) -> bytes:
+    """ValueFromString for the dimension types a group-by produces."""
+    n = _MEM_BYTES[mem_type]
+    if mem_type == MEM_FLOAT32:
+        return struct.pack("<f", float(text))
+    if mem_type == MEM_BOOL:
+        return bytes([1 if text.lower() == "true" or text == "1" else 0])
+    signed = mem_type in (MEM_INT8, MEM_INT16, MEM_INT32, MEM_INT64)
+    return int(text).to_bytes(n, "little", signed=signed)
+
+
+def build_vectors_from_hll_result(result: dict, data_types: list, enum_dicts: dict, dimension_vector_index: list) -> tuple:
+    """BuildVectorsFromHLLResult (query/common/hll.go:1002-1125): a nested {dimension string: ... HLL} result — e.g. what a
+    broker holds after merging its nodes' answers — back to (register vector, dimension block, count vector).  Keys are
+    visited in string order, children first; enum names go back through `enum_dicts` {dimension: {name: id}}; a register set
+    below the dense threshold is written sparse (4 bytes per register), else dense; layout position p of the block holds
+    query dimension dimension_vector_index[p]."""
+    nd = len(data_types)
+    dim_vectors, validity = [bytearray() for _ in range(nd)], [bytearray() for _ in range(nd)]
+    hll_vector, count_vector = bytearray(), bytearray()
+
+    def walk(d: int, node) -> int:
+        if isinstance(node, HLL):
+            count = node.non_zero_registers
+            leaf = HLL(node.non_zero_registers, None if node.sparse is None else list(node.sparse), node.dense)
+            if count < DENSE_THRESHOLD:
+                if not leaf.to_sparse():
+                    raise ValueError("Failed to convert HLL to sparse")
+            else:
+                leaf.to_dense()
+            hll_vector.extend(leaf.encode_binary())
+            count_vector.extend(struct.pack("<H", count))
+            return 1
+        if not isinstance(node, dict):
+            raise ValueError(f"unknown type {type(node).__name__}")
+        width = _MEM_BYTES[data_types[d]]
+        size = 0
+        for key in sorted(node):
+            child = walk(d + 1, node[key])
+            if key == NULL_STRING:
+                value, ok = bytes(width), 0
+            elif d in enum_dicts:
+                if width not in (1, 2):
+                    raise ValueError(f"data width {width} doesn't match any enum")
+                value, ok = int(enum_dicts[d].get(key, 0)).to_bytes(width, "little"), 1
+            else:
+                value, ok = _value_bytes(key, data_types[d]), 1
+            dim_vectors[d].extend(value * child)
+            validity[d].extend(bytes([ok]) * child)
+            size += child
+        return size
+
+    walk(0, result)
+    block = b"".join(bytes(dim_vectors[i]) for i in dimension_vector_index) + b"".join(bytes(validity[i]) for i in dimension_vector_index)
+    return bytes(hll_vector), block, bytes(count_vector)

@@ -155,3 +155,28 @@ def test_register_set_operations_known_answers():
     a.merge(b)
     assert a.non_zero_registers == 3 and [a.dense[i] for i in (5, 7, 9)] == [3, 1, 4]
     assert a.to_sparse() and sorted(a.sparse) == [(5, 3), (7, 1), (9, 4)] and a.dense is None
+
+
+def test_build_vectors_from_a_nested_result_known_answer():
+    """BuildVectorsFromHLLResult (query/common/hll_test.go:264-318): keys in string order, children first, enum names
+    back to ids, small register sets sparse."""
+    dense = bytearray(DENSE)
+    dense[0] = dense[1] = 1
+    two = lambda: W.HLL(2, dense=bytes(dense))
+    result = {"NULL": {"NULL": {"NULL": W.HLL(3, sparse=[(1, 255), (2, 254), (3, 253)])}},
+              "1": {"c": {"2": two(), "3": two()}},
+              "4294967295": {"d": {"514": W.HLL(4, sparse=[(255, 1), (254, 2), (253, 3), (252, 4)])}, "e": {"4": two()}}}
+    hll, dims, counts = W.build_vectors_from_hll_result(result, [W.MEM_UINT32, W.MEM_UINT8, W.MEM_INT16], {1: {"c": 0, "d": 1, "e": 2}}, [0, 2, 1])
+    assert hll == bytes([0, 0, 1, 0, 1, 0, 1, 0, 0, 0, 1, 0, 1, 0, 1, 0, 255, 0, 1, 0, 254, 0, 2, 0, 253, 0, 3, 0, 252, 0, 4, 0,
+                         0, 0, 1, 0, 1, 0, 1, 0, 1, 0, 255, 255, 2, 0, 254, 255, 3, 0, 253, 255])
+    assert dims == bytes([1, 0, 0, 0, 1, 0, 0, 0, 255, 255, 255, 255, 255, 255, 255, 255, 0, 0, 0, 0,
+                          2, 0, 3, 0, 2, 2, 4, 0, 0, 0,
+                          0, 0, 1, 2, 0,
+                          1, 1, 1, 1, 0, 1, 1, 1, 1, 0, 1, 1, 1, 1, 0])
+    assert counts == bytes([2, 0, 2, 0, 4, 0, 2, 0, 3, 0])
+    # and the vectors serialize into a payload the parser reads back to the same nested result
+    payload = W.serialize_hll_data([0, 0, 1, 1, 1], [0, 2, 1], [W.MEM_UINT32, W.MEM_UINT8, W.MEM_INT16], {1: ["c", "d", "e"]},
+                                   dims, np.frombuffer(counts, np.uint16), hll)
+    back = W.parse_hll_data(payload)
+    assert set(back) == set(result) and set(back["4294967295"]) == {"d", "e"} and set(back["1"]["c"]) == {"2", "3"}
+    assert back["NULL"]["NULL"]["NULL"].sparse == [(1, 255), (2, 254), (3, 253)]
