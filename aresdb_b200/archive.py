@@ -229,3 +229,19 @@ def scan_archive_batches(executor, batches: dict, time_range, now: int) -> list:
         executor.process_batch(b, time_filters=first_or_last)
         done.append((day, first_or_last))
     return done
+
+
+def scan_shard(executor, live_batches: list, archive_batches: dict, cutoff: int, time_range, now: int) -> dict:
+    """processShard (query/aql_processor.go:166-248): the live batches first — scanned when the range reaches past the
+    archiving cutoff, each with the cutoff filter `time >= cutoff` (rows below it are the archive's) —, then the archive days
+    when the range starts below the cutoff.  Zone-map skipping of live batches happens inside the executor."""
+    frm, to = time_range
+    done = {"live": 0, "archive": []}
+    if to is None or cutoff < to:
+        for b in live_batches:
+            if b.num_rows:
+                executor.process_batch(b, cutoff=cutoff)
+                done["live"] += 1
+    if archive_batches and (frm is None or cutoff > frm):
+        done["archive"] = scan_archive_batches(executor, archive_batches, time_range, now)
+    return done

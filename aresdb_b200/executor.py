@@ -128,7 +128,7 @@ class LegacyBatchExecutor:
                            e.op, stream, dev)
         return A.scratch_input(frame.ptr, 4 * size, dt)
 
-    def process_batch(self, batch: Batch, is_last: bool = False, time_filters: bool = True):
+    def process_batch(self, batch: Batch, is_last: bool = False, time_filters: bool = True, cutoff: int = 0):
         """One batch through preExec -> filter -> project -> reduce -> postExec.  `is_last` only
         matters for hll queries (HyperLogLog builds the register vectors on the last batch,
         reference query/aql_batchexecutor.go:228-233)."""
@@ -153,7 +153,10 @@ class LegacyBatchExecutor:
                                          ctx["size"], recs, nrec, bc, batch.start_count, fn, stream, dev)
 
         lo, hi = q.time_filter_range
-        for i, f in enumerate(q.filters[:q.num_main_filters]):
+        main = list(enumerate(q.filters[:q.num_main_filters]))
+        if cutoff > 0:                                # a live batch: the cutoff filter opens the custom-filter step
+            main.insert(lo, (-1, q.cutoff_filter(cutoff)))
+        for i, f in main:
             if not time_filters and lo <= i < hi:     # an archive batch strictly inside the time range (customFilterFunc)
                 continue
             self._eval(f, batch, ctx, filter_action)
@@ -335,7 +338,7 @@ class FusedBatchExecutor:
         self._plan.NumInsts = len(self.insts)
         for i, pi in enumerate(self.insts):
             self._plan.Insts[i] = pi
-        self._plan_nt = None
+        self._plan_variants = {}
         self.calls = 0
         self.skipped = 0   # batches whose zone map contradicts a filter (skipping.py): never launched
         self.expected_groups = expected_groups
@@ -356,27 +359,33 @@ class FusedBatchExecutor:
                 self._plan.ForeignColumns[k].Table = t
                 self._plan.ForeignColumns[k].Column = f
 
-    def _plan_without_time_filters(self):
-        """The plan of an archive batch strictly inside the query's time range: same columns, joins and sinks, the two
-        time-filter instructions left out (a different plan shape: its own specialised kernel)."""
-        if self._plan_nt is None:
-            insts = self.q.plan_instructions(time_filters=False)
+    def _plan_variant(self, time_filters: bool, cutoff: int):
+        """A plan with other custom filters than the query's full set: an archive batch strictly inside the time range
+        leaves the time filters out, a live batch adds the cutoff filter.  Same columns, joins and sinks; a different plan
+        SHAPE compiles its own specialised kernel, a different cutoff is only a different literal."""
+        key = (time_filters, cutoff)
+        p = self._plan_variants.get(key)
+        if p is None:
+            insts = self.q.plan_instructions(time_filters=time_filters, cutoff=cutoff)
             p = A.BatchPlan()
             C.memmove(C.byref(p), C.byref(self._plan), C.sizeof(A.BatchPlan))   # foreign tables / columns as in the full plan
             p.NumInsts = len(insts)
             for i, pi in enumerate(insts):
                 p.Insts[i] = pi
-            self._plan_nt = p
-        return self._plan_nt
+            if len(self._plan_variants) > 8:
+                self._plan_variants.clear()
+            self._plan_variants[key] = p
+        return p
 
-    def process_batch(self, batch: Batch, stream=None, time_filters: bool = True):
+    def process_batch(self, batch: Batch, stream=None, time_filters: bool = True, cutoff: int = 0):
         """`time_filters=False`: an archive batch that lies strictly inside the query's time range skips the time filter
-        (archiveBatchCustomFilterExecutor evaluates it for the first and the last batch only, query/aql_processor.go:627-638)."""
+        (archiveBatchCustomFilterExecutor evaluates it for the first and the last batch only, query/aql_processor.go:627-638).
+        `cutoff` > 0: a live batch of a fact table also evaluates `time >= cutoff` (liveBatchCustomFilterExecutor :543-567)."""
         if should_skip_batch(self.q, batch.ranges):
             self.skipped += 1
             return
         lo, hi = self.q.time_filter_range
-        p = self._plan if time_filters or lo == hi else self._plan_without_time_filters()
+        p = self._plan if (time_filters or lo == hi) and cutoff <= 0 else self._plan_variant(time_filters or lo == hi, max(cutoff, 0))
         p.NumColumns = len(batch.columns)
         for i, vp in enumerate(batch.columns):
             p.Columns[i] = vp

@@ -47,6 +47,7 @@ class AggQuery:
         main = [f for f in resolved if not E.uses_foreign(f)]
         self.filters = main + timed + [f for f in resolved if E.uses_foreign(f)]
         self.time_filter_range = (len(main), len(main) + len(timed))     # positions in self.filters
+        self.time_column = 0          # fact tables: column 0 is the time column
         self.num_main_filters = len(main) + len(timed)
         self.dimensions = [E.resolve(d) for d in dimensions]
         self.reduce_mode = reduce_mode
@@ -118,7 +119,13 @@ class AggQuery:
         return spec
 
     # ---- fused plan ------------------------------------------------------------------------------
-    def plan_instructions(self, time_filters: bool = True) -> list[A.PlanInst]:
+    def cutoff_filter(self, cutoff: int) -> E.Expr:
+        """`time column >= cutoff`: what a LIVE batch of a fact table evaluates besides the query's own filters — rows older
+        than the shard's archiving cutoff are served by the archive batches (createCutoffTimeFilter, reference
+        query/aql_processor.go:543-552; the time column of a fact table is column 0)."""
+        return E.resolve(E.Binary(A.GreaterThanOrEqual, E.Col(self.time_column, A.Uint32, "time"), E.Lit(int(cutoff), E.Type.Unsigned)))
+
+    def plan_instructions(self, time_filters: bool = True, cutoff: int = 0) -> list[A.PlanInst]:
         """Post-order flattening of every expression: one PlanInst per non-leaf AST node (what
         processExpression turns into one cgo call, reference query/time_series_aggregate.go:493-593).
         `time_filters=False`: the plan of an archive batch strictly inside the query's time range."""
@@ -160,8 +167,12 @@ class AggQuery:
 
         lo, hi = self.time_filter_range
         for i, f in enumerate(self.filters):
+            if i == lo and cutoff > 0:          # the custom-filter step: cutoff filter first, then the time filters
+                emit(self.cutoff_filter(cutoff), A.PLAN_SINK_FILTER, 0, A.Bool)
             if time_filters or not lo <= i < hi:
                 emit(f, A.PLAN_SINK_FILTER, 0, A.Bool)
+        if cutoff > 0 and lo >= len(self.filters):
+            emit(self.cutoff_filter(cutoff), A.PLAN_SINK_FILTER, 0, A.Bool)
         for pos, qi in enumerate(self.dim_order):
             emit(self.dimensions[qi], A.PLAN_SINK_DIMENSION, pos, self.dim_types[qi])
         emit(self.measure, A.PLAN_SINK_MEASURE, 0, self.measure_data_type)

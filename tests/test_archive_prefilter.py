@@ -239,3 +239,91 @@ def test_archive_scan_on_the_fused_path():
             got = ex.result()
             ex.close()
             T.assert_same_result(got, exp, ctx=f"{measure} zone_maps={zone_maps}")
+
+
+def test_shard_scan_live_batches_with_the_cutoff_filter_then_archive_days():
+    """processShard (query/aql_processor.go:166-248): live batches carry rows on both sides of the archiving cutoff — those
+    below it are the archive's and are cut by `time >= cutoff` —, archive days are scanned when the range starts below the
+    cutoff.  count(*) by hour against numpy, on the reference's HOST build and the oracle; ranges that end before the cutoff
+    or start after it touch one store only."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, archive, synth
+    from aresdb_b200.executor import LegacyBatchExecutor
+    table = aql.Table("trips", [aql.Column(n, t) for n, t in zip(synth.COLUMN_NAMES, synth.COLUMN_TYPES)])
+    day0 = synth.BASE_TS // 86400
+    cutoff = synth.BASE_TS + 3 * 86400
+    arch = {day0 + d: synth.generate_batch(d, 2500, num_cities=4, null_rate=0.0) for d in range(3)}          # days 0..2
+    rng = np.random.default_rng(11)
+    live = []
+    for i in range(3):          # unsorted rows of days 1..5: part of them already archived
+        hb = synth.generate_batch(7 + i, 3000, num_cities=4, null_rate=0.0)
+        hb.values[0] = (synth.BASE_TS + rng.integers(1 * 86400, 6 * 86400, hb.num_rows)).astype(np.uint32)
+        live.append(hb)
+
+    def expected(frm, to):
+        out = {}
+        days = archive.archive_batch_ids((frm, to), 0)
+        ts = [arch[d].values[0] for d in days if d in arch and cutoff > frm] + ([hb.values[0][hb.values[0] >= cutoff] for hb in live] if cutoff < to else [])
+        for t in np.concatenate(ts).astype(np.int64) if ts else []:
+            if frm <= t < to:
+                out[int(t) // 3600 * 3600] = out.get(int(t) // 3600 * 3600, 0) + 1
+        return out
+
+    ranges = {"both": (synth.BASE_TS + 86400 + 1800, synth.BASE_TS + 5 * 86400 - 1800),
+              "archive only": (synth.BASE_TS + 3600, synth.BASE_TS + 2 * 86400),
+              "live only": (cutoff + 7200, cutoff + 2 * 86400)}
+    for backend in ("ref", "oracle"):
+        be = H.get_backend(backend)
+        for name, (frm, to) in ranges.items():
+            text = {"table": "trips", "measures": [{"sqlExpression": "count(*)"}],
+                    "timeFilter": {"column": "request_at", "from": str(frm), "to": str(to - 1)},
+                    "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}]}
+            q = aql.compile_query(text, table, synth.BASE_TS + 30 * 86400)
+            frm, to = q.time_range
+            ex = LegacyBatchExecutor(be.lib, be.space, q)
+            done = archive.scan_shard(ex, [T.upload(be, hb) for hb in live], {d: T.upload(be, hb) for d, hb in arch.items()}, cutoff,
+                                      q.time_range, 0)
+            assert (done["live"] > 0) == (name != "archive only") and (len(done["archive"]) > 0) == (name != "live only")
+            res = ex.result()
+            got = dict(zip(np.array(res.decoded_dims()[0], np.int64).tolist(), res.measures.tolist()))
+            assert got == expected(frm, to) and len(got) > 10, (backend, name)
+    # the cutoff filter is one more filter instruction, ahead of the time filters
+    assert len(q.plan_instructions(cutoff=cutoff)) == len(q.plan_instructions()) + 1
+
+
+@pytest.mark.gpu
+def test_shard_scan_on_the_fused_path():
+    """Live batches with the cutoff filter (a plan with one more filter instruction, the cutoff a literal), archive days
+    with / without the time filters: ExecuteBatchPlan against the oracle's call sequence over the same scan."""
+    import harness as H
+    import test_pipeline_parity as T
+    from aresdb_b200 import aql, archive, synth
+    from aresdb_b200.executor import FusedBatchExecutor, LegacyBatchExecutor
+    eng, orc = H.get_backend("b200"), H.get_backend("oracle")
+    table = aql.Table("trips", [aql.Column(n, t) for n, t in zip(synth.COLUMN_NAMES, synth.COLUMN_TYPES)])
+    day0 = synth.BASE_TS // 86400
+    cutoff = synth.BASE_TS + 3 * 86400
+    arch = {day0 + d: synth.generate_batch(d, 20000, num_cities=12, null_rate=0.0) for d in range(3)}
+    rng = np.random.default_rng(11)
+    live = []
+    for i in range(3):
+        hb = synth.generate_batch(7 + i, 25000, num_cities=12, null_rate=0.0)
+        hb.values[0] = (synth.BASE_TS + rng.integers(1 * 86400, 6 * 86400, hb.num_rows)).astype(np.uint32)
+        live.append(hb)
+    frm, to = synth.BASE_TS + 86400 + 1800, synth.BASE_TS + 5 * 86400 - 1800
+    text = {"table": "trips", "measures": [{"sqlExpression": "sum(fare)", "rowFilters": ["status = 1"]}],
+            "timeFilter": {"column": "request_at", "from": str(frm), "to": str(to)},
+            "dimensions": [{"sqlExpression": "request_at", "timeBucketizer": "hour"}, {"sqlExpression": "city_id"}]}
+    q = aql.compile_query(text, table, synth.BASE_TS + 30 * 86400)
+    results = []
+    for be, cls in ((orc, LegacyBatchExecutor), (eng, FusedBatchExecutor)):
+        ex = cls(be.lib, be.space, q)
+        keep_live = [T.upload(be, hb, 0, synth.zone_map(hb) if be is eng else None) for hb in live]
+        keep_arch = {d: T.upload(be, hb, 0, synth.zone_map(hb) if be is eng else None) for d, hb in arch.items()}
+        done = archive.scan_shard(ex, keep_live, keep_arch, cutoff, q.time_range, 0)
+        # days 1 .. 4 are scanned; the archive holds 1 and 2: the first scanned day with the time filter, day 2 without
+        assert done["live"] == 3 and done["archive"] == [(day0 + 1, True), (day0 + 2, False)]
+        results.append(ex.result())
+    assert results[0].groups > 500
+    T.assert_same_result(results[1], results[0], ctx="shard scan")
