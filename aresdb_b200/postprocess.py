@@ -196,3 +196,56 @@ def hll_nested_result(result: HLLResult, metas: list | None = None) -> dict:
             else:
                 cur = cur.setdefault(key, {})
     return out
+
+
+# ---- merging the nested results of several nodes -------------------------------------------------------------------
+class MergeError(ValueError):
+    pass
+
+
+def merge_nested_results(lhs: dict, rhs: dict, agg: str) -> dict:
+    """The merge a broker applies to its nodes' nested results, in place into `lhs` (reference broker/result_merge.go:44-140;
+    the device-side counterpart of this engine is AggStateMerge / the exchange step).  `agg`: "count" / "sum" add, "max" /
+    "min" keep the extreme, "hll" merges register sets (hll_data.HLL.merge), "avg" divides lhs (the sum query's result) by rhs
+    (the count query's) and needs every key on both sides.  A key on one side only is taken as it is."""
+    if agg not in ("count", "sum", "max", "min", "avg", "hll"):
+        raise MergeError(f"unknown aggregation {agg}")
+
+    def leaf(l, r, path):
+        if hasattr(l, "merge") and hasattr(l, "non_zero_registers"):      # an HLL register set
+            if agg != "hll":
+                raise MergeError("error merging: HLL value found for non Hll aggregation")
+            l.merge(r)
+            return l
+        if agg in ("count", "sum"):
+            return l + r
+        if agg == "max":
+            return r if r > l else l
+        if agg == "min":
+            return r if r < l else l
+        if agg == "avg":
+            return l / r
+        raise MergeError(f"error merging: number found for {agg} aggregation, path: {path}")
+
+    def walk(l: dict, r: dict, path: list):
+        for k in list(l):
+            if k not in r or r[k] is None:
+                if agg == "avg":
+                    raise MergeError(f"error calculating avg: some dimension has only sum. path: {path + [k]}")
+                continue
+            if l[k] is None:
+                l[k] = r[k]
+            elif type(l[k]) is not type(r[k]) and not (isinstance(l[k], (int, float)) and isinstance(r[k], (int, float))):
+                raise MergeError(f"error merging: different type lhs: {type(l[k]).__name__} vs. rhs: {type(r[k]).__name__}")
+            elif isinstance(l[k], dict):
+                walk(l[k], r[k], path + [k])
+            else:
+                l[k] = leaf(l[k], r[k], path + [k])
+        for k in r:
+            if k not in l:
+                if agg == "avg":
+                    raise MergeError(f"error calculating avg: some dimension has only count. path: {path + [k]}")
+                l[k] = r[k]
+
+    walk(lhs, rhs, [])
+    return lhs

@@ -116,3 +116,42 @@ def test_hll_estimate_reference_known_answer_and_bias_range():
     # table edges: below the first and beyond the last raw estimate the window shrinks but k stays 6
     assert PP.hll_estimate_bias(1000.0) == sum(B.BIASES[:6]) / 6.0
     assert PP.hll_estimate_bias(1e6) == sum(B.BIASES[-6:]) / 6.0
+
+
+def test_merging_nested_results_of_several_nodes_known_answers():
+    """broker/result_merge.go through its own cases (broker/result_merge_test.go:26-459): same and different shapes for
+    sum / count / max / min, avg = sum result / count result with every key on both sides, hll = register-set merge."""
+    import copy
+    from aresdb_b200.postprocess import MergeError, merge_nested_results
+    a = {"1234": {"foo": 123, "bar": 2}}
+    b = {"1234": {"foo": 1, "bar": 1}}
+    for agg, exp in (("sum", {"1234": {"foo": 124, "bar": 3}}), ("count", {"1234": {"foo": 124, "bar": 3}}),
+                     ("max", {"1234": {"foo": 123, "bar": 2}}), ("min", {"1234": {"foo": 1, "bar": 1}})):
+        assert merge_nested_results(copy.deepcopy(a), copy.deepcopy(b), agg) == exp
+        assert merge_nested_results({}, {}, agg) == {}
+        # different shapes: a key on one side only is taken as it is
+        assert merge_nested_results({"1234": {"foo": 123}}, copy.deepcopy(b), agg) == {"1234": {"foo": exp["1234"]["foo"], "bar": 1}}
+        assert merge_nested_results({}, copy.deepcopy(b), agg) == b
+        assert merge_nested_results({"1234": {"foo": 123}}, {}, agg) == {"1234": {"foo": 123}}
+    assert merge_nested_results({"1234": {"foo": 2, "bar": 1}}, {"1234": {"foo": 1, "bar": 2}}, "avg") == {"1234": {"foo": 2, "bar": 0.5}}
+    assert merge_nested_results({}, {}, "avg") == {}
+    for l, r in (({"1234": {"foo": 2}}, b), ({}, b), ({"1234": {"foo": 123}}, {})):
+        with pytest.raises(MergeError, match="error calculating avg"):
+            merge_nested_results(copy.deepcopy(l), copy.deepcopy(r), "avg")
+    with pytest.raises(MergeError, match="different type"):
+        merge_nested_results({"k": {"x": 1}}, {"k": 2}, "sum")
+    # hll: a result merged with itself is itself (the reference's case on its golden buffer), and a real union
+    from pathlib import Path
+    from aresdb_b200 import hll_data as W
+    z = np.load(Path(__file__).resolve().parent / "golden" / "hll_wire_format.npz")
+    lhs = W.parse_hll_query_results(z["hll_query_results"].tobytes(), True)[0][0]
+    rhs = W.parse_hll_query_results(z["hll_query_results"].tobytes(), True)[0][0]
+    before = {k: v3.dense_registers().tobytes() for k, v1 in lhs.items() for v2 in v1.values() for v3 in v2.values()}
+    merged = merge_nested_results(lhs, rhs, "hll")
+    after = {k: v3.dense_registers().tobytes() for k, v1 in merged.items() for v2 in v1.values() for v3 in v2.values()}
+    assert after == before and merged["NULL"]["NULL"]["NULL"].non_zero_registers == 3
+    x, y = {"g": W.HLL(2, sparse=[(5, 3), (7, 1)])}, {"g": W.HLL(2, sparse=[(5, 2), (9, 4)]), "h": W.HLL(1, sparse=[(1, 1)])}
+    m = merge_nested_results(x, y, "hll")
+    assert m["g"].non_zero_registers == 3 and m["g"].compute() == pytest.approx(3.0, abs=0.01) and m["h"].sparse == [(1, 1)]
+    with pytest.raises(MergeError, match="HLL value found"):
+        merge_nested_results({"g": W.HLL(1, sparse=[(1, 1)])}, {"g": W.HLL(1, sparse=[(2, 1)])}, "sum")
