@@ -680,3 +680,15 @@ def time_bucket_start(ts: int, bucketizer: str) -> int:
     if bucketizer == "week":   # Monday 00:00 (reference query/functor.cu:207-212)
         return ts - (ts - SECONDS_PER_4_DAYS) % SECONDS_PER_WEEK
     return ts - ts % _regular_bucket_seconds(bucketizer)
+
+
+def compile_request(request, table: Table, now: int, **kwargs) -> list:
+    """A whole AQL request — the JSON text (or parsed object) of a `.aql` file: {"queries": [...]} — -> one AggQuery per
+    element, in order (the handler runs them one after the other, api/query_handler.go)."""
+    import json
+    if isinstance(request, (str, bytes)):
+        request = json.loads(request)
+    queries = request.get("queries") if isinstance(request, dict) else None
+    if not isinstance(queries, list):
+        raise AQLError("expect {\"queries\": [...]}")
+    return [compile_query(q, table, now, **kwargs) for q in queries]

@@ -352,3 +352,19 @@ def test_in_lists_null_tests_and_bitwise_operators_end_to_end():
     for bad in ("fare + 1 in (2)", "city_id not 3", "fare is 3", "city_id in 1"):
         with pytest.raises(aql.AQLError):
             aql.parse_expression(bad, table)
+
+
+def test_a_whole_aql_file_compiles_verbatim(trips):
+    """The text of the reference's example files (examples/1k_trips/queries/*.aql, restated here: one element each) through
+    compile_request: the same plans as the per-query entry point."""
+    import json
+    z, table, now = trips
+    for name, q in _queries().items():
+        text = json.dumps({"queries": [q]}, indent=2)
+        got = aql.compile_request(text, table, now)
+        one = aql.compile_query(q, table, now)
+        assert len(got) == 1 and [repr(f) for f in got[0].filters] == [repr(f) for f in one.filters]
+        assert repr(got[0].dimensions) == repr(one.dimensions) and got[0].agg_func == one.agg_func
+    assert len(aql.compile_request({"queries": list(_queries().values())}, table, now)) == 2
+    with pytest.raises(aql.AQLError):
+        aql.compile_request("{}", table, now)
